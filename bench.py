@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- chain loss forward+backward throughput (frames/s) on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config chime5]
+
+Own arm: one step = one ComputeChainObjfAndDeriv-equivalent call (numerator
+forward-backward + denominator alpha/beta + derivative, incl. the negation the
+reference's backward() does) over one synthetic minibatch of BASELINE.json
+config 2 ("chime5": P=2928, N=10000, A~300k, B=128 x T=50 per GPU, leaky 0.1,
+l2 5e-5).  N>1: one process per GPU (torchrun), each rank owns B sequences
+(weak scaling), the 3 result scalars are all-reduced over NCCL every step.
+
+Reference arm (--impl reference): the Kaldi-CPU-equivalent restatement
+(oracle/, kaldi_fp32 mode) on the host cores, bounded sample, rank 0 only.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "chain_loss_fwd_bwd_frames_per_sec"
+UNIT = "frames/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx = float(f[2])
+                except ValueError:
+                    continue
+                for n, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def make_workload(name, B, T, rank):
+    from torchain_b200 import synth
+    c = dict(synth.CONFIGS[name])
+    if B:
+        c["B"] = B
+    if T:
+        c["T"] = T
+    den = synth.make_den_fst(1234, c["N"], c["P"], mean_deg=c["mean_deg"])
+    sup = synth.make_supervision(1235 + 1000 * rank, den, c["B"], c["T"], num_paths=4, weight=1.0)
+    c.update(den=den, sup=sup)
+    return c
+
+
+def alg_bytes(c):
+    """algorithmic bytes per sequence-frame."""
+    hbm = 4 * (3 * c["P"] + 2 * (c["N"] + 1))
+    gather = 16 * c["den"].num_arcs
+    return hbm, gather
+
+
+def cpu_baseline(c, seconds_budget=20.0, threads=None):
+    """Oracle (kaldi_fp32) on a bounded sample: the same den graph and options, the first
+    Bs sequences of a T-frame minibatch.  Returns (frames/s, cores, sample description)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from torchain_b200 import synth
+    den = c["den"]
+    ncores = threads or ol.load().oracle_max_threads()
+    oden = ol.OracleDen(den)
+    T = c["T"]
+    Bs = min(c["B"], max(8, 2 * ncores))
+    best = None
+    while True:
+        sup = synth.make_supervision(77, den, Bs, T, num_paths=4, weight=1.0)
+        y = synth.make_nnet_output(78, Bs, T, c["P"], scale=2.0)
+        osup = ol.OracleSup(sup)
+        t0 = time.perf_counter()
+        ol.chain(oden, osup, y, l2=c["l2"], leaky=c["leaky"], mode="kaldi_fp32", threads=ncores)
+        dt = time.perf_counter() - t0
+        best = (Bs * T / dt, Bs, dt)
+        if dt * 4 > seconds_budget or Bs >= c["B"]:
+            break
+        Bs = min(c["B"], Bs * 2)
+    fps, Bs, dt = best
+    return fps, ncores, "B=%d of %d sequences x T=%d frames, same den graph/options, %.1f s" % (Bs, c["B"], T, dt)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    c = make_workload(args.config, args.batch, args.frames, 0)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    from torchain_b200 import synth
+    ncores = ol.load().oracle_max_threads()
+    oden = ol.OracleDen(c["den"])
+    Bs = min(c["B"], max(8, 2 * ncores))
+    T = c["T"]
+    sup = synth.make_supervision(77, c["den"], Bs, T, num_paths=4, weight=1.0)
+    y = synth.make_nnet_output(78, Bs, T, c["P"], scale=2.0)
+    osup = ol.OracleSup(sup)
+    for _ in range(args.warmup):
+        ol.chain(oden, osup, y, l2=c["l2"], leaky=c["leaky"], mode="kaldi_fp32", threads=ncores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ol.chain(oden, osup, y, l2=c["l2"], leaky=c["leaky"], mode="kaldi_fp32", threads=ncores)
+    dt = (time.perf_counter() - t0) / args.steps
+    fps = Bs * T / dt
+    sample = "B=%d of %d sequences x T=%d frames per step, same den graph/options" % (Bs, c["B"], T)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "chime5-shaped chain loss: P=%d N=%d A=%d B=%d T=%d leaky=%g l2=%g" % (
+            c["P"], c["N"], c["den"].num_arcs, c["B"], c["T"], c["leaky"], c["l2"]),
+            "note": "Kaldi-CPU-equivalent restatement (oracle kaldi_fp32); Kaldi itself is not buildable here"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from torchain_b200 import _lib, io
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    c = make_workload(args.config, args.batch, args.frames, rank)
+    den, sup = c["den"], c["sup"]
+    B, T, P = c["B"], c["T"], c["P"]
+    g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
+                                        den.final_cost, den.num_pdfs)
+    s = io.Supervision.from_arrays(sup.weight, B, T, sup.label_dim, sup.arc_begin, sup.arc_dst, sup.arc_label,
+                                   sup.arc_cost, sup.final_cost)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    y = torch.randn(T * B, P, device=dev, generator=gen) * 2.0
+    deriv = torch.empty_like(y)
+    res_dev = torch.zeros(3, device=dev)
+    res_host = np.zeros(3, dtype=np.float32)
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        ok = lib.torchain_ComputeChainObjfAndDeriv_ex(
+            g.ptr, s.ptr, y.data_ptr(), T * B, P, y.stride(0),
+            None if world > 1 else res_host.ctypes.data_as(ctypes.c_void_p), res_dev.data_ptr(),
+            deriv.data_ptr(), deriv.stride(0), None, 0,
+            c["l2"], c["leaky"], 0.0, -1.0, local, ctypes.c_void_p(stream.cuda_stream))
+        if ok != 1:
+            raise RuntimeError(_lib.last_error())
+        if world > 1:  # the path's only exchange: objf / l2_term / weight summed over ranks
+            dist.all_reduce(res_dev)
+            res_host[:] = res_dev.cpu().numpy()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    lib.torchain_profile_enable(1)
+    dummy_ms, dummy_n = ctypes.c_double(0), ctypes.c_int64(0)
+    lib.torchain_profile_read(g.ptr, ctypes.byref(dummy_ms), ctypes.byref(dummy_n), 1)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.torchain_kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = lib.torchain_kernel_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    den_ms, den_n = ctypes.c_double(0), ctypes.c_int64(0)
+    lib.torchain_profile_read(g.ptr, ctypes.byref(den_ms), ctypes.byref(den_n), 1)
+    lib.torchain_profile_enable(0)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * B * T / (ms_per_step * 1e-3)
+
+    # ---- e2e: the reference-facing C-ABI call with HOST (pinned) buffers, copies inside the timed region
+    y_pin = torch.empty(T * B, P, pin_memory=True)
+    y_pin.copy_(y)
+    d_pin = torch.empty(T * B, P, pin_memory=True)
+    r_e2e = np.zeros(3, dtype=np.float32)
+
+    def e2e_step():
+        ok = lib.torchain_ComputeChainObjfAndDeriv_host(
+            g.ptr, s.ptr, y_pin.data_ptr(), T * B, P, P, r_e2e.ctypes.data_as(ctypes.c_void_p),
+            d_pin.data_ptr(), P, None, 0, c["l2"], c["leaky"], 0.0, local)
+        if ok != 1:
+            raise RuntimeError(_lib.last_error())
+
+    for _ in range(2):
+        e2e_step()
+    sync_all()
+    t0 = time.perf_counter()
+    n_e2e = max(3, min(args.steps, 10))
+    for _ in range(n_e2e):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * T / float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (persistent denominator kernel)
+    hbm_peak, peak_src = peaks()
+    hbm_alg, gather_alg = alg_bytes(c)
+    den_launch_ms = den_ms.value / max(1, den_n.value)
+    hbm_gbs = hbm_alg * B * T / (den_launch_ms * 1e-3) / 1e9
+    gather_gbs = gather_alg * B * T / (den_launch_ms * 1e-3) / 1e9
+    l2_peak = lib.torchain_microbench_l2_gather(local, 32 << 20, 512, 400)
+    frac_hbm = hbm_gbs / hbm_peak
+    frac_l2 = gather_gbs / l2_peak if l2_peak > 0 else None
+    roofline = {
+        "bound": "hbm", "kernel": "den_chain_kernel", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
+        "frac": max(frac_hbm, frac_l2 or 0.0), "frac_hbm": frac_hbm, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
+        "traffic": None,
+        "alg_bytes_per_launch": hbm_alg * B * T, "launch_ms": den_launch_ms, "launches_timed": int(den_n.value),
+        "gather": {"achieved": gather_gbs, "peak": l2_peak, "unit": "GB/s", "frac": frac_l2,
+                   "alg_bytes_per_launch": gather_alg * B * T,
+                   "peak_source": "measured live: L2-resident random 512 B-row gather (torchain_microbench_l2_gather)"},
+        "note": "frac = max(hbm frac, L2-gather frac) per SURVEY.md 8d; the recurrence is gather(L2)-bound",
+    }
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        fps, cores, sample = cpu_baseline(c)
+        fps1, _, sample1 = cpu_baseline(c, seconds_budget=8.0, threads=1)
+        cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+               "value_1thread": fps1, "sample_1thread": sample1}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "chime5-shaped chain loss: P=%d N=%d A=%d, B=%d seqs x T=%d frames per GPU, leaky=%g l2=%g" % (
+            P, c["N"], den.num_arcs, B, T, c["leaky"], c["l2"]),
+            "name": args.config, "parallelism": "seq-shard x%d" % world,
+            "l2_policy": "working set per step (y+deriv+alpha store = %.2f GB) exceeds the 126 MB L2; no flush" % (
+                (2 * T * B * P * 4 + (T + 1) * c["N"] * B * 4) / 1e9)},
+        "results": {"objf": float(res_host[0]), "l2_term": float(res_host[1]), "weight": float(res_host[2])},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": T * B * P * 4,
+                "d2h_bytes_per_step": T * B * P * 4 + 12, "ms_per_step": float(te.item()) * 1e3,
+                "api": "torchain_ComputeChainObjfAndDeriv_host (pinned host nnet_output in, derivative + results out)"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="chime5")
+    ap.add_argument("--batch", type=int, default=0, help="sequences per GPU (default: the config's)")
+    ap.add_argument("--frames", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,187 @@
+/* torchain_b200.h -- C ABI of libtorchain_b200.so
+ *
+ * Drop-in boundary for the LF-MMI ("chain") loss hot path of nttcslab-sp/torchain.
+ * Every entry point is plain C: raw pointers, sizes, strides, a device index and
+ * a CUDA stream handle (void* == cudaStream_t).  No torch / TH / THC / Kaldi types.
+ *
+ * Each declaration cites the reference interface it replaces
+ * (paths are into the reference tree, /root/reference in the build container).
+ *
+ * Conventions
+ *   - functions returning int: 1 = success, 0 = failure (reference convention,
+ *     src/my_lib_chain.cpp:135, src/my_lib_example.cpp:42); after a failure
+ *     torchain_last_error() returns a thread-local message.  Nothing throws
+ *     across this boundary (the reference lets Kaldi abort the process instead).
+ *   - functions returning void*: NULL = failure (src/my_lib_example.cpp:73).
+ *   - numeric failure (NaN/inf objective or the alpha*beta sanity check off by
+ *     more than 2) is NOT an error: objf = -10*weight and zero derivatives, as
+ *     Kaldi's ComputeChainObjfAndDeriv does.
+ *   - there is no CPU fallback: every compute entry needs a CUDA device.
+ */
+#ifndef TORCHAIN_B200_H_
+#define TORCHAIN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- errors / library info ------------------------------------------------ */
+
+/* Thread-local description of the last failure on this thread ("" if none). */
+const char* torchain_last_error(void);
+
+/* ABI version of this library (bumped on incompatible change). */
+int torchain_abi_version(void);
+
+/* Number of kernels of THIS library launched by the calling process so far
+ * (all threads).  bench.py reports the delta over its timed region. */
+int64_t torchain_kernel_launch_count(void);
+
+/* Replaces: void my_lib_set_kaldi_device(THCudaTensor* t)   src/my_lib.h:48,
+ * src/my_lib_chain.cpp:34-36, src/common.hpp:120-132.  The reference overwrote
+ * Kaldi's process-wide CuDevice singleton; this library has no global device
+ * state (device and stream are per-call arguments), so this only validates that
+ * `device` exists.  Kept so torchain.io.set_kaldi_device keeps working. */
+int my_lib_set_kaldi_device(int device);
+
+/* ---- denominator graph ---------------------------------------------------- */
+
+/* Replaces: void* my_lib_denominator_graph_new(const char* rxfilename, int num_pdf)
+ * src/my_lib.h:29, src/my_lib_example.cpp:129-134 (fst::ReadFstKaldi + new
+ * kaldi::chain::DenominatorGraph).  Reads an OpenFst binary VectorFst<StdArc>
+ * ("vector"/"standard") or an AT&T/Kaldi text FST, with no OpenFst dependency. */
+void* my_lib_denominator_graph_new(const char* rxfilename, int num_pdf);
+
+/* Same object from arrays (what DenominatorGraph's ctor consumes after
+ * ReadFstKaldi): arc a goes src[a] -> dst[a] with ilabel[a] = pdf_id + 1 and
+ * tropical cost[a] = -log(prob); final_cost[s] = +inf for non-final states
+ * (final weights only enter the initial-probability estimate, as in Kaldi). */
+void* torchain_denominator_graph_from_arrays(int32_t num_states, int32_t num_arcs,
+                                             const int32_t* src, const int32_t* dst,
+                                             const int32_t* ilabel, const float* cost,
+                                             int32_t start, const float* final_cost,
+                                             int32_t num_pdfs);
+
+/* Replaces: void my_lib_denominator_graph_free(void*)   src/my_lib.h:30,
+ * src/my_lib_example.cpp:136-138. */
+void my_lib_denominator_graph_free(void* den_graph_ptr);
+
+int torchain_denominator_graph_num_states(void* den_graph_ptr);
+int torchain_denominator_graph_num_arcs(void* den_graph_ptr);
+int torchain_denominator_graph_num_pdfs(void* den_graph_ptr);
+/* Copies the N initial probabilities (Kaldi DenominatorGraph::InitialProbs()). */
+int torchain_denominator_graph_initial_probs(void* den_graph_ptr, float* out_n);
+
+/* ---- supervision ---------------------------------------------------------- */
+
+/* Replaces: void* my_lib_supervision_new(void* reader_ptr) and
+ * my_lib_supervision_rand_new   src/my_lib.h:19,21, src/my_lib_example.cpp:71-76,
+ * src/my_lib_example_rand.cpp:244-249, i.e. `new kaldi::chain::Supervision(...)`.
+ * The Kaldi egs readers that fed those are outside the hot path; here the
+ * Supervision is built from the arrays of its merged FST: an epsilon-free
+ * acceptor over num_sequences*frames_per_sequence frames, states topologically
+ * sorted with state 0 the start, arcs of state s at [arc_begin[s], arc_begin[s+1]),
+ * arc_label = pdf_id + 1, tropical costs, final_cost = +inf for non-final. */
+void* torchain_supervision_from_arrays(float weight, int32_t num_sequences,
+                                       int32_t frames_per_sequence, int32_t label_dim,
+                                       int32_t num_states, const int32_t* arc_begin,
+                                       const int32_t* arc_dst, const int32_t* arc_label,
+                                       const float* arc_cost, const float* final_cost);
+
+/* The reference's reader-based constructors; egs reading is out of scope, so
+ * these always return NULL and set the error string. */
+void* my_lib_supervision_new(void* reader_ptr);
+void* my_lib_supervision_rand_new(void* reader_ptr);
+
+/* Replace src/my_lib.h:22-25, src/my_lib_example.cpp:78-95. */
+void my_lib_supervision_free(void* supervision_ptr);
+int my_lib_supervision_num_pdf(void* supervision_ptr);
+int my_lib_supervision_num_sequence(void* supervision_ptr);
+int my_lib_supervision_num_frame(void* supervision_ptr);
+/* Number of independent numerator chains the merged FST was split into
+ * (num_sequences when it factorises per sequence, else 1). */
+int torchain_supervision_num_chains(void* supervision_ptr);
+
+/* ---- the chain loss ------------------------------------------------------- */
+
+/* Replaces: int my_lib_ComputeChainObjfAndDeriv(void* den_graph_ptr,
+ *   void* supervision_ptr, THCudaTensor* nnet_output_ptr, THFloatTensor* results,
+ *   THCudaTensor* nnet_output_deriv_ptr, THCudaTensor* xent_output_deriv_ptr,
+ *   float l2_regularize, float leaky_hmm_coefficient, float xent_regularize)
+ * src/my_lib.h:33-42, src/my_lib_chain.cpp:104-136.  Same argument order and
+ * meaning; each tensor becomes (device pointer, row stride in elements) the way
+ * common::make_matrix viewed it (src/common.hpp:109-117); rows/cols are the
+ * matrix shape and must equal (num_sequences*frames_per_sequence, num_pdfs);
+ * rows are ordered frame-major: row = frame * num_sequences + sequence.
+ *
+ *   nnet_output        device, rows x cols fp32, read-only
+ *   results            HOST float[3] = {objf, l2_term, weight}  (THFloatTensor)
+ *   nnet_output_deriv  device, rows x cols fp32; need not be initialised
+ *   xent_output_deriv  device or NULL; written only if xent_regularize != 0
+ *                      (= supervision.weight * numerator posteriors)
+ *   device, stream     CUDA device index and cudaStream_t the work is enqueued on
+ *
+ * Synchronises `stream` once, to deliver `results` to the host. */
+int my_lib_ComputeChainObjfAndDeriv(void* den_graph_ptr, void* supervision_ptr,
+                                    const float* nnet_output, int64_t rows, int64_t cols,
+                                    int64_t nnet_output_stride,
+                                    float* results,
+                                    float* nnet_output_deriv, int64_t deriv_stride,
+                                    float* xent_output_deriv, int64_t xent_stride,
+                                    float l2_regularize, float leaky_hmm_coefficient,
+                                    float xent_regularize,
+                                    int device, void* stream);
+
+/* Extended form used by the Python autograd op:
+ *   deriv_scale   both derivative outputs are multiplied by this; -1 yields the
+ *                 negated gradient torchain's backward returns
+ *                 (torchain/functions.py:106-115) without a separate kernel.
+ *   results_dev   if non-NULL, {objf, l2_term, weight} are also written to this
+ *                 DEVICE float[3] (lets a caller defer the host read).
+ *   results       HOST float[3] or NULL; if NULL the call does not synchronise. */
+int torchain_ComputeChainObjfAndDeriv_ex(void* den_graph_ptr, void* supervision_ptr,
+                                         const float* nnet_output, int64_t rows, int64_t cols,
+                                         int64_t nnet_output_stride,
+                                         float* results, float* results_dev,
+                                         float* nnet_output_deriv, int64_t deriv_stride,
+                                         float* xent_output_deriv, int64_t xent_stride,
+                                         float l2_regularize, float leaky_hmm_coefficient,
+                                         float xent_regularize, float deriv_scale,
+                                         int device, void* stream);
+
+/* Host-buffer form (what a non-torch host binding would call): nnet_output,
+ * nnet_output_deriv (and xent_output_deriv, may be NULL) are HOST pointers,
+ * ideally pinned; the call copies the input to the device, runs the loss and
+ * copies derivatives and results back before returning. */
+int torchain_ComputeChainObjfAndDeriv_host(void* den_graph_ptr, void* supervision_ptr,
+                                           const float* nnet_output_host, int64_t rows, int64_t cols,
+                                           int64_t nnet_output_stride,
+                                           float* results,
+                                           float* nnet_output_deriv_host, int64_t deriv_stride,
+                                           float* xent_output_deriv_host, int64_t xent_stride,
+                                           float l2_regularize, float leaky_hmm_coefficient,
+                                           float xent_regularize, int device);
+
+/* ---- measurement helpers (used by bench.py; not part of the reference API) -- */
+
+/* Per-kernel timing for the roofline line of bench.py: when enabled, every launch
+ * of the persistent denominator kernel is bracketed by CUDA events on the
+ * caller's stream; torchain_profile_read waits for them and returns the
+ * accumulated device time (ms) and launch count since the last reset. */
+void torchain_profile_enable(int on);
+int torchain_profile_read(void* den_graph_ptr, double* den_kernel_ms, int64_t* den_kernel_launches, int reset);
+
+/* L2-resident random 512-byte-row gather: the measured denominator of the
+ * gather roofline.  Returns achieved GB/s, <0 on error. */
+double torchain_microbench_l2_gather(int device, int64_t table_bytes, int row_bytes, int iters);
+/* red.global.add.v4.f32 to random 512-byte rows of an L2-resident table; GB/s of operand bytes. */
+double torchain_microbench_l2_red(int device, int64_t table_bytes, int row_bytes, int iters);
+/* Mean latency in microseconds of the software grid barrier at one CTA per SM. */
+double torchain_microbench_grid_barrier(int device, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TORCHAIN_B200_H_ */

@@ -1,0 +1,167 @@
+"""CPU suite, part 2: the C-ABI library loads without a GPU, exports every symbol
+include/torchain_b200.h declares, and its host-side handle logic (no compute
+calls) behaves like the reference's handle layer (/root/reference/torchain/io.py:20-31,51-57)."""
+import ctypes
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from torchain_b200 import _lib, io, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "torchain_b200.h")
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:my_lib|torchain)_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+    # and the Python binding table covers exactly the header
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_abi_version_and_error_string():
+    lib = _lib.load()
+    assert lib.torchain_abi_version() == 1
+    assert lib.my_lib_supervision_new(None) is None
+    assert "egs readers" in _lib.last_error()
+
+
+def test_den_graph_from_arrays_matches_oracle_initial_probs():
+    den = synth.make_den_fst(7, 300, 40, mean_deg=4.0)
+    g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
+                                        den.final_cost, den.num_pdfs)
+    assert (g.n_state, g.n_arc, g.n_pdf) == (den.num_states, den.num_arcs, den.num_pdfs)
+    ref = ol.OracleDen(den).initial_probs()
+    assert np.abs(g.initial_probs - ref).max() < 1e-7
+
+
+def test_den_graph_rejects_bad_arrays():
+    den = synth.make_den_fst(7, 20, 5, mean_deg=2.0)
+    bad = den.ilabel.copy()
+    bad[0] = 0   # label 0 would be pdf -1
+    with pytest.raises(ValueError):
+        io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, bad, den.cost, den.start,
+                                        den.final_cost, den.num_pdfs)
+    with pytest.raises(ValueError):
+        io.DenominatorGraph("/nonexistent/den.fst", 10)
+
+
+def write_openfst_binary(path, den):
+    """OpenFst VectorFst<StdArc> binary layout."""
+    order = np.argsort(den.src, kind="stable")
+    with open(path, "wb") as f:
+        f.write(struct.pack("<i", 2125659606))
+        for s in (b"vector", b"standard"):
+            f.write(struct.pack("<i", len(s)) + s)
+        f.write(struct.pack("<iiQqqq", 2, 0, 0, den.start, den.num_states, den.num_arcs))
+        k = 0
+        counts = np.bincount(den.src, minlength=den.num_states)
+        for s in range(den.num_states):
+            f.write(struct.pack("<fq", float(den.final_cost[s]), int(counts[s])))
+            for _ in range(counts[s]):
+                a = order[k]
+                k += 1
+                f.write(struct.pack("<iifi", int(den.ilabel[a]), int(den.ilabel[a]), float(den.cost[a]),
+                                    int(den.dst[a])))
+
+
+def test_den_graph_from_openfst_binary_and_text(tmp_path):
+    den = synth.make_den_fst(11, 60, 9, mean_deg=3.0)
+    ref = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
+                                          den.final_cost, den.num_pdfs).initial_probs
+    p = str(tmp_path / "den.fst")
+    write_openfst_binary(p, den)
+    g = io.DenominatorGraph(p, den.num_pdfs)
+    assert (g.n_state, g.n_arc) == (den.num_states, den.num_arcs)
+    assert np.array_equal(g.initial_probs, ref)
+    # AT&T text form
+    t = str(tmp_path / "den.txt")
+    with open(t, "w") as f:
+        for a in range(den.num_arcs):
+            f.write("%d %d %d %d %.9g\n" % (den.src[a], den.dst[a], den.ilabel[a], den.ilabel[a], den.cost[a]))
+        for s in range(den.num_states):
+            f.write("%d %.9g\n" % (s, den.final_cost[s]))
+    g2 = io.DenominatorGraph(t, den.num_pdfs)
+    assert (g2.n_state, g2.n_arc) == (den.num_states, den.num_arcs)
+    assert np.abs(g2.initial_probs - ref).max() < 1e-6
+
+
+def test_supervision_handle_shape_and_split():
+    den = synth.make_den_fst(3, 50, 12, mean_deg=3.0)
+    for bc in (False, True):
+        sup = synth.make_supervision(4, den, 5, 7, num_paths=3, weight=0.5, boundary_final_costs=bc)
+        h = io.Supervision.from_arrays(sup.weight, sup.num_sequences, sup.frames_per_sequence, sup.label_dim,
+                                       sup.arc_begin, sup.arc_dst, sup.arc_label, sup.arc_cost, sup.final_cost)
+        assert h.shape == (5, 7, 12) and (h.n_batch, h.n_frame, h.n_pdf) == (5, 7, 12)
+        assert h.num_chains == 5   # the merged FST factorises per sequence
+
+
+def test_supervision_unsplittable_falls_back_to_one_chain():
+    den = synth.make_den_fst(3, 50, 12, mean_deg=3.0)
+    sup = synth.make_supervision(4, den, 3, 6, num_paths=3)
+    # perturb ONE copied start arc at the first sequence boundary so the coupling is no longer rank one
+    cost = sup.arc_cost.copy()
+    times = np.full(sup.num_states, -1)
+    times[0] = 0
+    for s in range(sup.num_states):
+        for a in range(sup.arc_begin[s], sup.arc_begin[s + 1]):
+            times[sup.arc_dst[a]] = times[s] + 1
+    boundary = np.where(times == 6)[0]
+    if len(boundary) < 2:
+        pytest.skip("needs two boundary states")
+    cost[sup.arc_begin[boundary[1]]] += 0.5
+    h = io.Supervision.from_arrays(sup.weight, 3, 6, sup.label_dim, sup.arc_begin, sup.arc_dst, sup.arc_label,
+                                   cost, sup.final_cost)
+    assert h.num_chains == 1
+
+
+def test_supervision_null_and_invalid():
+    with pytest.raises(ValueError, match="null supervision ptr"):   # reference io.py:23-24
+        io.Supervision(None)
+    den = synth.make_den_fst(3, 30, 6, mean_deg=2.0)
+    sup = synth.make_supervision(4, den, 2, 4, num_paths=2)
+    with pytest.raises(ValueError):   # wrong frames_per_sequence
+        io.Supervision.from_arrays(1.0, 2, 5, sup.label_dim, sup.arc_begin, sup.arc_dst, sup.arc_label,
+                                   sup.arc_cost, sup.final_cost)
+
+
+def test_chain_results_formula():
+    """Reference functions.py:9-19."""
+    from torchain_b200.functions import ChainResults
+    r = ChainResults()
+    r.data[0], r.data[1], r.data[2] = -120.0, -3.0, 60.0
+    assert float(r.loss) == 2.0
+    assert "ChainResults(loss=2.0" in repr(r)
+
+
+def test_to2d_row_order():
+    """Reference functions.py:118-125: (B, C, T) -> row t*B + b."""
+    import torch
+    from torchain_b200.functions import to2d
+    x = torch.arange(2 * 3 * 4, dtype=torch.float32).view(2, 3, 4)
+    y = to2d(x)
+    assert y.shape == (8, 3)
+    for b in range(2):
+        for t in range(4):
+            assert torch.equal(y[t * 2 + b], x[b, :, t])
+
+
+def test_chain_loss_requires_cuda():
+    """Reference functions.py:67: CUDA-only; there is no CPU fallback."""
+    import torch
+    from torchain_b200.functions import chain_loss
+    with pytest.raises(AssertionError, match="Only CUDA"):
+        chain_loss(torch.zeros(4, 3), None, None)

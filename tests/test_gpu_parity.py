@@ -1,0 +1,211 @@
+"""GPU suite: the sm_100a path, called through the C ABI (ctypes) and through the
+Python autograd op, against the oracle / golden fixtures on identical inputs."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from common import DERIV_RTOL, GOLDEN, OBJF_RTOL, deriv_err, load_golden, rel
+from torchain_b200 import _lib, io, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def handles(den, sup):
+    g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
+                                        den.final_cost, den.num_pdfs)
+    s = io.Supervision.from_arrays(sup.weight, sup.num_sequences, sup.frames_per_sequence, sup.label_dim,
+                                   sup.arc_begin, sup.arc_dst, sup.arc_label, sup.arc_cost, sup.final_cost)
+    return g, s
+
+
+def run_abi(g, s, y_np, l2, leaky, xent=0.0, want_xent=False, stride_pad=0):
+    """my_lib_ComputeChainObjfAndDeriv with raw device pointers."""
+    import torch
+    lib = _lib.load()
+    rows, cols = y_np.shape
+    y = torch.zeros(rows, cols + stride_pad, device="cuda")
+    y[:, :cols] = torch.from_numpy(np.ascontiguousarray(y_np, dtype=np.float32)).cuda()
+    deriv = torch.full((rows, cols + stride_pad), float("nan"), device="cuda")   # callee must not need zeroing
+    xd = torch.full((rows, cols), float("nan"), device="cuda") if want_xent else None
+    res = np.zeros(3, dtype=np.float32)
+    ok = lib.my_lib_ComputeChainObjfAndDeriv(
+        g.ptr, s.ptr, y.data_ptr(), rows, cols, y.stride(0), res.ctypes.data_as(ctypes.c_void_p),
+        deriv.data_ptr(), deriv.stride(0), xd.data_ptr() if want_xent else None, cols,
+        l2, leaky, xent, torch.cuda.current_device(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert ok == 1, _lib.last_error()
+    torch.cuda.synchronize()
+    return res, deriv[:, :cols].cpu().numpy(), (xd.cpu().numpy() if want_xent else None)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: p[-10:-4])
+def test_gpu_matches_golden(path):
+    c = load_golden(path)
+    g, s = handles(c["den"], c["sup"])
+    res, d, _ = run_abi(g, s, c["y"], c["l2"], c["leaky"])
+    assert rel(res[0], c["objf"]) < OBJF_RTOL
+    assert abs(res[1] - c["l2_term"]) <= OBJF_RTOL * max(abs(c["l2_term"]), 1e-30)
+    assert res[2] == pytest.approx(c["weight"])
+    assert deriv_err(d, c["deriv"]) < DERIV_RTOL
+
+
+@pytest.mark.parametrize("seed", range(50))
+def test_gpu_matches_oracle_small(seed):
+    """cfg 1 of BASELINE.json: the reference's own CPU-runnable random case ranges."""
+    c = synth.small_case(seed)
+    oden, osup = ol.OracleDen(c["den"]), ol.OracleSup(c["sup"])
+    r = ol.chain(oden, osup, c["y"], l2=c["l2"], leaky=c["leaky"], mode="fp64")
+    g, s = handles(c["den"], c["sup"])
+    res, d, _ = run_abi(g, s, c["y"], c["l2"], c["leaky"], stride_pad=seed % 3)
+    assert rel(res[0], r["objf"]) < OBJF_RTOL
+    assert abs(res[1] - r["l2_term"]) <= OBJF_RTOL * max(abs(r["l2_term"]), 1e-30)
+    assert res[2] == pytest.approx(r["weight"])
+    assert deriv_err(d, r["deriv"]) < DERIV_RTOL
+    # property assertions of the reference's test (chain-supervision-test.hpp:267-285)
+    if c["l2"] == 0.0:
+        assert np.linalg.norm(d.astype(np.float64).sum(axis=1)) < 0.1
+        assert res[0] <= 0.0
+
+
+@pytest.mark.parametrize("B,T,N,P", [(33, 9, 300, 70), (64, 11, 500, 100), (100, 7, 400, 64),
+                                     (128, 6, 700, 130), (200, 5, 350, 90), (300, 4, 250, 50)])
+def test_gpu_matches_oracle_batch_shapes(B, T, N, P):
+    """Every vector width / chunking / multi-pass path of the kernel (padded batches)."""
+    den = synth.make_den_fst(B, N, P, mean_deg=6.0)
+    sup = synth.make_supervision(B + 1, den, B, T, num_paths=3, weight=1.0)
+    y = synth.make_nnet_output(B + 2, B, T, P, scale=1.5)
+    oden, osup = ol.OracleDen(den), ol.OracleSup(sup)
+    r = ol.chain(oden, osup, y, l2=5e-5, leaky=0.1, mode="fp64", threads=4)
+    g, s = handles(den, sup)
+    res, d, _ = run_abi(g, s, y, 5e-5, 0.1)
+    assert rel(res[0], r["objf"]) < OBJF_RTOL
+    assert rel(res[1], r["l2_term"]) < OBJF_RTOL
+    assert deriv_err(d, r["deriv"]) < DERIV_RTOL
+
+
+def test_gpu_xent_output_is_weighted_numerator_posterior():
+    c = synth.small_case(7)
+    oden, osup = ol.OracleDen(c["den"]), ol.OracleSup(c["sup"])
+    r = ol.chain(oden, osup, c["y"], l2=c["l2"], leaky=c["leaky"], mode="fp64", want_xent=True)
+    g, s = handles(c["den"], c["sup"])
+    res, d, x = run_abi(g, s, c["y"], c["l2"], c["leaky"], xent=0.1, want_xent=True)
+    assert deriv_err(x, r["xent"]) < DERIV_RTOL
+    assert deriv_err(d, r["deriv"]) < DERIV_RTOL
+    # every (t, s) row of the numerator posterior sums to supervision.weight
+    assert np.abs(x.astype(np.float64).sum(axis=1) - c["sup"].weight).max() < 1e-4
+
+
+def test_gpu_unsplit_supervision_fallback():
+    """A merged FST that does not factorise per sequence runs as one chain and still matches."""
+    den = synth.make_den_fst(3, 50, 12, mean_deg=3.0)
+    sup = synth.make_supervision(4, den, 3, 6, num_paths=3)
+    times = np.full(sup.num_states, -1)
+    times[0] = 0
+    for st in range(sup.num_states):
+        for a in range(sup.arc_begin[st], sup.arc_begin[st + 1]):
+            times[sup.arc_dst[a]] = times[st] + 1
+    boundary = np.where(times == 6)[0]
+    if len(boundary) < 2:
+        pytest.skip("needs two boundary states")
+    sup.arc_cost = sup.arc_cost.copy()
+    sup.arc_cost[sup.arc_begin[boundary[1]]] += 0.5
+    y = synth.make_nnet_output(5, 3, 6, 12)
+    r = ol.chain(ol.OracleDen(den), ol.OracleSup(sup), y, l2=0.0, leaky=0.1, mode="fp64")
+    g, s = handles(den, sup)
+    assert s.num_chains == 1
+    res, d, _ = run_abi(g, s, y, 0.0, 0.1)
+    assert rel(res[0], r["objf"]) < OBJF_RTOL
+    assert deriv_err(d, r["deriv"]) < DERIV_RTOL
+
+
+def test_gpu_guard_on_nan():
+    c = synth.small_case(1)
+    g, s = handles(c["den"], c["sup"])
+    y = c["y"].copy()
+    y[0, 0] = np.nan
+    res, d, _ = run_abi(g, s, y, 0.0, 0.1)
+    assert res[0] == pytest.approx(-10.0 * res[2])
+    assert np.all(d == 0.0)
+
+
+def test_gpu_error_paths():
+    import torch
+    lib = _lib.load()
+    c = synth.small_case(2)
+    g, s = handles(c["den"], c["sup"])
+    y = torch.from_numpy(c["y"]).cuda()
+    d = torch.empty_like(y)
+    res = np.zeros(3, dtype=np.float32)
+    args = lambda rows, leaky: (g.ptr, s.ptr, y.data_ptr(), rows, y.shape[1], y.stride(0),
+                                res.ctypes.data_as(ctypes.c_void_p), d.data_ptr(), d.stride(0), None, 0,
+                                0.0, leaky, 0.0, 0, None)
+    assert lib.my_lib_ComputeChainObjfAndDeriv(*args(y.shape[0] - 1, 0.1)) == 0
+    assert "rows" in _lib.last_error()
+    assert lib.my_lib_ComputeChainObjfAndDeriv(*args(y.shape[0], 0.0)) == 0
+    assert "leaky" in _lib.last_error()
+
+
+def test_python_chain_loss_autograd():
+    """torchain.functions.chain_loss semantics (reference functions.py:62-138)."""
+    import torch
+    from torchain_b200.functions import chain_loss
+    c = synth.small_case(9)
+    B, T, P = c["B"], c["T"], c["P"]
+    oden, osup = ol.OracleDen(c["den"]), ol.OracleSup(c["sup"])
+    r = ol.chain(oden, osup, c["y"], l2=0.01, leaky=0.1, mode="fp64", want_xent=True)
+    g, s = handles(c["den"], c["sup"])
+    # (B, P, T) input as the recipes pass it
+    y3 = torch.from_numpy(c["y"]).view(T, B, P).permute(1, 2, 0).contiguous().cuda().requires_grad_(True)
+    x3 = y3.detach().clone().requires_grad_(True)
+    loss, results = chain_loss(y3, g, s, l2_regularize=0.01, leaky_hmm_coefficient=0.1,
+                               xent_regularize=0.1, xent_input=x3, kaldi_way=True)
+    assert loss.is_cuda and loss.shape == (1,)
+    assert float(loss) == pytest.approx(-r["objf"] / r["weight"], rel=1e-5)
+    assert not results.data.is_cuda and results.data.dtype == torch.float32
+    assert float(results.data[0]) == pytest.approx(r["objf"], rel=1e-5)
+    assert float(results.data[1]) == pytest.approx(r["l2_term"], rel=1e-5)
+    (loss * 123.0).backward()   # grad_output is ignored by the reference's backward
+    gy = y3.grad.permute(2, 0, 1).reshape(T * B, P).cpu().numpy()
+    gx = x3.grad.permute(2, 0, 1).reshape(T * B, P).cpu().numpy()
+    assert deriv_err(gy, -r["deriv"]) < DERIV_RTOL
+    assert deriv_err(gx, -0.1 * r["xent"]) < DERIV_RTOL
+
+
+def test_host_buffer_entry():
+    lib = _lib.load()
+    c = load_golden(GOLDEN[2])
+    g, s = handles(c["den"], c["sup"])
+    y = np.ascontiguousarray(c["y"], dtype=np.float32)
+    d = np.full_like(y, np.nan)
+    res = np.zeros(3, dtype=np.float32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    ok = lib.torchain_ComputeChainObjfAndDeriv_host(g.ptr, s.ptr, p(y), y.shape[0], y.shape[1], y.shape[1], p(res),
+                                                    p(d), y.shape[1], None, 0, c["l2"], c["leaky"], 0.0, 0)
+    assert ok == 1, _lib.last_error()
+    assert rel(res[0], c["objf"]) < OBJF_RTOL
+    assert deriv_err(d, c["deriv"]) < DERIV_RTOL
+
+
+def test_large_config_properties():
+    """BASELINE.json cfg 2 at full size: size-independent properties (the oracle's fp64
+    pass is too slow for the GPU suite at this size; bench.py times a bounded sample)."""
+    import torch
+    c = synth.make_config("chime5", with_y=False)
+    g, s = handles(c["den"], c["sup"])
+    B, T, P = c["B"], c["T"], c["P"]
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    y = (torch.randn(T * B, P, device="cuda", generator=gen) * 2.0)
+    res, d, x = run_abi(g, s, y.cpu().numpy(), 0.0, 0.1, xent=0.1, want_xent=True)
+    d64 = d.astype(np.float64)
+    assert res[0] <= 0.0 and res[2] == B * T
+    assert np.abs(d64.sum(axis=1)).max() < 1e-3              # num and den posteriors both sum to 1 per row
+    assert np.abs(x.astype(np.float64).sum(axis=1) - 1.0).max() < 1e-4
+    den_post = x.astype(np.float64) - d64                     # = weight * gamma_den
+    assert den_post.min() > -1e-5 and abs(den_post.sum() - B * T) < 1e-2 * B * T / 100
+    # linearity in supervision.weight: objf and deriv scale, posterior structure does not
+    c["sup"].weight = 0.5
+    g2, s2 = handles(c["den"], c["sup"])
+    res2, d2, _ = run_abi(g2, s2, y.cpu().numpy(), 0.0, 0.1)
+    assert res2[0] == pytest.approx(0.5 * res[0], rel=1e-5)
+    assert deriv_err(d2, 0.5 * d64) < DERIV_RTOL

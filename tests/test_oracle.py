@@ -1,0 +1,154 @@
+"""CPU suite, part 1: the oracle (oracle/chain_oracle.cpp) against the golden
+fixtures, against the independent dense float64 formulation, and against the
+property assertions of the reference's own vendored Kaldi test
+(/root/reference/src/chain-supervision-test.hpp)."""
+import numpy as np
+import pytest
+
+import dense_ref
+import oracle_lib as ol
+from common import DERIV_RTOL, GOLDEN, OBJF_RTOL, deriv_err, load_golden, rel
+from torchain_b200 import synth
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: p[-10:-4])
+def test_oracle_fp64_matches_golden(path):
+    g = load_golden(path)
+    oden, osup = ol.OracleDen(g["den"]), ol.OracleSup(g["sup"])
+    r = ol.chain(oden, osup, g["y"], l2=g["l2"], leaky=g["leaky"], mode="fp64")
+    assert r["ok"]
+    assert rel(r["objf"], g["objf"]) < 1e-7
+    assert abs(r["l2_term"] - g["l2_term"]) <= 1e-9 * max(1.0, abs(g["l2_term"]))
+    assert r["weight"] == g["weight"]
+    assert deriv_err(r["deriv"], g["deriv"]) < 1e-7
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: p[-10:-4])
+def test_oracle_kaldi_fp32_within_stated_tolerance(path):
+    g = load_golden(path)
+    oden, osup = ol.OracleDen(g["den"]), ol.OracleSup(g["sup"])
+    r = ol.chain(oden, osup, g["y"], l2=g["l2"], leaky=g["leaky"], mode="kaldi_fp32")
+    assert rel(r["objf"], g["objf"]) < OBJF_RTOL
+    assert abs(r["l2_term"] - g["l2_term"]) <= OBJF_RTOL * max(1e-30, abs(g["l2_term"]))
+    assert deriv_err(r["deriv"], g["deriv"]) < DERIV_RTOL
+
+
+def test_initial_probs_match_vectorised_restatement():
+    for seed in range(5):
+        den = synth.make_den_fst(seed, 50 + 37 * seed, 11, mean_deg=3.0)
+        pi = ol.OracleDen(den).initial_probs()
+        ref = synth.initial_probs(den)
+        assert np.abs(pi - ref).max() < 1e-7
+        assert abs(pi.sum() - 1.0) < 1e-5
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_oracle_vs_dense_autograd(seed):
+    c = synth.small_case(seed)
+    if c["T"] > 25:  # the dense reference is a python loop; keep the CPU suite fast
+        c = dict(c)
+        c["T"] = T = 7
+        c["sup"] = synth.make_supervision(seed + 1, c["den"], c["B"], T, num_paths=3, weight=c["sup"].weight)
+        c["y"] = synth.make_nnet_output(seed + 2, c["B"], T, c["P"])
+    oden, osup = ol.OracleDen(c["den"]), ol.OracleSup(c["sup"])
+    r = ol.chain(oden, osup, c["y"], l2=c["l2"], leaky=c["leaky"], mode="fp64")
+    objf, l2_term, w, g = dense_ref.chain_objf(c["den"], oden.initial_probs(), c["sup"], c["y"], c["leaky"], c["l2"])
+    assert rel(r["objf"], objf) < 1e-7
+    assert abs(r["l2_term"] - l2_term) <= 1e-9 * max(1.0, abs(l2_term))
+    assert r["weight"] == pytest.approx(w)
+    assert deriv_err(r["deriv"], g) < 1e-7
+
+
+@pytest.mark.parametrize("seed", range(50))
+def test_chain_training_properties(seed):
+    """ChainTrainingTest assertions (chain-supervision-test.hpp:267-285)."""
+    c = synth.small_case(seed)
+    oden, osup = ol.OracleDen(c["den"]), ol.OracleSup(c["sup"])
+    r = ol.chain(oden, osup, c["y"], l2=0.0, leaky=c["leaky"], mode="kaldi_fp32")
+    assert r["ok"]
+    d = r["deriv"].astype(np.float64)
+    assert np.linalg.norm(d.sum(axis=1)) < 0.1      # :267-273 shift invariance
+    assert d.sum() < 0.2                            # :278-283
+    assert r["objf"] <= 0.0                         # :285
+    assert r["weight"] == pytest.approx(c["sup"].weight * c["B"] * c["T"])
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_chain_finite_difference(seed):
+    """chain-supervision-test.hpp:287-340: predicted vs observed objf change within 25 %."""
+    c = synth.small_case(seed)
+    if c["T"] <= 2:
+        pytest.skip("reference skips the comparison for very short sequences (:330)")
+    oden, osup = ol.OracleDen(c["den"]), ol.OracleSup(c["sup"])
+    r = ol.chain(oden, osup, c["y"], l2=0.0, leaky=c["leaky"], mode="fp64")
+    rng = np.random.default_rng(seed)
+    pred, obs = [], []
+    for _ in range(5):
+        delta = rng.standard_normal(c["y"].shape) * 1e-4
+        pred.append(float((r["deriv"] * delta).sum()))
+        r2 = ol.chain(oden, osup, c["y"].astype(np.float64) + delta, l2=0.0, leaky=c["leaky"], mode="fp64",
+                      want_deriv=False)
+        obs.append(r2["objf"] - r["objf"])
+    pred, obs = np.array(pred), np.array(obs)
+    if np.linalg.norm(pred) > 0.1 * 1e-4:
+        assert np.linalg.norm(pred - obs) <= 0.25 * np.linalg.norm(pred)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_denominator_properties(seed):
+    """ChainDenominatorTest (chain-supervision-test.hpp:388-463): occupancies sum to B*T,
+    finite differences of the forward log-prob agree with the derivative."""
+    c = synth.small_case(seed)
+    oden = ol.OracleDen(c["den"])
+    B, T = c["B"], c["T"]
+    lp, d, ok = ol.den_only(oden, B, T, c["y"], leaky=1e-5)
+    assert ok
+    assert abs(d.sum() - B * T) < 1e-6 * B * T
+    assert np.abs(d.reshape(T, B, -1).sum(axis=2) - 1.0).max() < 1e-9   # one unit of occupancy per (t, s)
+    rng = np.random.default_rng(seed)
+    for _ in range(3):
+        delta = rng.standard_normal(c["y"].shape) * 1e-4
+        lp2, _, _ = ol.den_only(oden, B, T, c["y"].astype(np.float64) + delta, leaky=1e-5, want_deriv=False)
+        pred = float((d * delta).sum())
+        if abs(pred) > 1e-7:
+            assert abs((lp2 - lp) - pred) < 0.05 * abs(pred) + 1e-9
+
+
+def test_numerator_shift_property():
+    """TestSupervisionNumerator (:139-149): adding r_row to every element of a row changes
+    the numerator log-prob by the sum of the r_row."""
+    c = synth.small_case(3)
+    oden, osup = ol.OracleDen(c["den"]), ol.OracleSup(c["sup"])
+    y = c["y"].astype(np.float64)
+    r0 = ol.chain(oden, osup, y, leaky=0.1, mode="fp64", want_deriv=False)
+    shift = np.random.default_rng(0).standard_normal(y.shape[0])
+    r1 = ol.chain(oden, osup, y + shift[:, None], leaky=0.1, mode="fp64", want_deriv=False)
+    assert abs((r1["num"] - r0["num"]) - c["sup"].weight * shift.sum()) < 1e-8 * max(1.0, abs(shift.sum()))
+
+
+def test_guard_on_nan_input():
+    """chain-training.cc guard: non-finite objf => objf = -10*weight, zero derivative (+ l2 part)."""
+    c = synth.small_case(1)
+    oden, osup = ol.OracleDen(c["den"]), ol.OracleSup(c["sup"])
+    y = c["y"].copy()
+    y[0, 0] = np.nan
+    r = ol.chain(oden, osup, y, l2=0.0, leaky=0.1, mode="kaldi_fp32")
+    assert r["objf"] == pytest.approx(-10.0 * r["weight"])
+    assert np.all(r["deriv"] == 0.0)
+
+
+def test_threaded_oracle_is_bit_identical():
+    c = synth.small_case(5)
+    oden, osup = ol.OracleDen(c["den"]), ol.OracleSup(c["sup"])
+    a = ol.chain(oden, osup, c["y"], l2=0.01, leaky=0.1, mode="kaldi_fp32", threads=1)
+    b = ol.chain(oden, osup, c["y"], l2=0.01, leaky=0.1, mode="kaldi_fp32", threads=4)
+    assert a["objf"] == b["objf"] and np.array_equal(a["deriv"], b["deriv"])
+
+
+def test_oracle_rejects_bad_inputs():
+    c = synth.small_case(2)
+    oden, osup = ol.OracleDen(c["den"]), ol.OracleSup(c["sup"])
+    with pytest.raises(ValueError):
+        ol.chain(oden, osup, c["y"][:-1], leaky=0.1)          # wrong number of rows
+    with pytest.raises(ValueError):
+        ol.chain(oden, osup, c["y"], leaky=0.0)               # Kaldi asserts 0 < leaky < 1

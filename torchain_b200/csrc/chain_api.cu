@@ -1,0 +1,1115 @@
+// chain_api.cu -- the C ABI of libtorchain_b200.so (include/torchain_b200.h):
+// handle types, host-side graph preparation, workspace management and the
+// ComputeChainObjfAndDeriv entry points.
+//
+// Mirrors, for the chain-loss path only, the reference's cffi surface
+// /root/reference/src/my_lib.h:19-48 and its glue
+// /root/reference/src/my_lib_chain.cpp:104-136, /root/reference/src/my_lib_example.cpp:71-95,129-138.
+// All arithmetic that Kaldi did underneath is in den_kernel.cu / num_kernel.cu;
+// the only host arithmetic here is the one-off DenominatorGraph preparation
+// (transition probabilities and initial-state probabilities).
+// There is no CPU implementation of the loss in this library.
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <limits>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <queue>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/torchain_b200.h"
+#include "chain_kernels.h"
+
+namespace {
+
+thread_local std::string g_error;
+std::atomic<int> g_profile{0};
+std::mutex g_prof_mu;
+double g_prof_den_ms = 0.0;
+int64_t g_prof_den_launches = 0;
+int fail(const std::string& msg) {
+  g_error = msg;
+  return 0;
+}
+void* fail_ptr(const std::string& msg) {
+  g_error = msg;
+  return nullptr;
+}
+#define CUDA_OK(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      return fail(std::string(#expr) + ": " + cudaGetErrorString(e__));                       \
+    }                                                                                         \
+  } while (0)
+
+const float kInf = std::numeric_limits<float>::infinity();
+
+// ---------------------------------------------------------------------------
+// device buffer helpers
+// ---------------------------------------------------------------------------
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() {
+    if (ptr) cudaFree(ptr);
+  }
+  cudaError_t reserve(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&ptr, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(ptr);
+  }
+};
+
+template <typename T>
+cudaError_t upload(DevBuf& b, const std::vector<T>& v) {
+  cudaError_t e = b.reserve(std::max<size_t>(sizeof(T) * v.size(), 16));
+  if (e != cudaSuccess) return e;
+  if (v.empty()) return cudaSuccess;
+  return cudaMemcpy(b.ptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice);
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+    if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Denominator graph handle
+// ---------------------------------------------------------------------------
+struct DirHost {  // one direction, partitioned
+  std::vector<int4> arcs, tasks;
+  std::vector<int> cta_arc_off, cta_task_off, warp_task_off;
+  int max_arcs_cta = 0, max_tasks_cta = 0;
+};
+
+struct DenDevice {  // per (device) copy
+  int grid = 0;
+  DevBuf arcs[2], tasks[2], cta_arc_off[2], cta_task_off[2], warp_task_off[2];
+  int max_arcs_cta[2] = {0, 0}, max_tasks_cta[2] = {0, 0};
+};
+
+struct Workspace {
+  DevBuf alpha, beta, tiles, zeroed, num_scratch, scratch_deriv;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  float* pinned = nullptr;  // 4 floats
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;  // around each denominator launch (profiling only)
+  ~Workspace() {
+    for (auto& pr : prof) {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    if (side) cudaStreamDestroy(side);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (pinned) cudaFreeHost(pinned);
+  }
+};
+
+struct DenGraph {
+  int N = 0, A = 0, P = 0, start = 0;
+  std::vector<int> src, dst, pdf;
+  std::vector<float> prob;
+  std::vector<float> pi;
+  double sum_pi = 0.0;
+  std::mutex mu;
+  std::map<int, std::unique_ptr<DenDevice>> dev;
+  std::map<std::pair<int, void*>, std::unique_ptr<Workspace>> ws;
+};
+
+// Longest-processing-time-first assignment of weighted items to `bins` bins.
+void lpt(const std::vector<int>& items, const std::vector<int>& cost, int bins, std::vector<std::vector<int>>* out) {
+  out->assign(bins, {});
+  std::vector<int> order(items);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+  typedef std::pair<long long, int> Load;  // (load, bin)
+  std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
+  for (int b = 0; b < bins; b++) heap.push({0, b});
+  for (int it : order) {
+    Load l = heap.top();
+    heap.pop();
+    (*out)[l.second].push_back(it);
+    l.first += cost[it];
+    heap.push(l);
+  }
+}
+
+// Partition one direction over grid CTAs x kDenMainWarps warps.
+//   dir 0: tasks = destination states with their in-arcs (other = source)
+//   dir 1: tasks = source states with their out-arcs     (other = destination)
+void build_dir(const DenGraph& g, int dir, int grid, DirHost* out) {
+  const int N = g.N, A = g.A;
+  std::vector<int> deg(N, 0), begin(N + 1, 0);
+  const std::vector<int>& key = dir == 0 ? g.dst : g.src;
+  const std::vector<int>& other = dir == 0 ? g.src : g.dst;
+  for (int a = 0; a < A; a++) deg[key[a]]++;
+  for (int s = 0; s < N; s++) begin[s + 1] = begin[s] + deg[s];
+  std::vector<int> arc_of(A), pos(begin.begin(), begin.end() - 1);
+  for (int a = 0; a < A; a++) arc_of[pos[key[a]]++] = a;  // stable: FST arc order within a state
+
+  const int kTaskOverhead = 3;  // fixed per-state cost in arc units (prologue, store, partial sums)
+  std::vector<int> cost(N), all(N);
+  for (int s = 0; s < N; s++) {
+    cost[s] = deg[s] + kTaskOverhead;
+    all[s] = s;
+  }
+  std::vector<std::vector<int>> by_cta;
+  lpt(all, cost, grid, &by_cta);
+
+  out->arcs.clear();
+  out->tasks.clear();
+  out->cta_arc_off.assign(1, 0);
+  out->cta_task_off.assign(1, 0);
+  out->warp_task_off.assign(1, 0);
+  out->max_arcs_cta = out->max_tasks_cta = 0;
+  for (int c = 0; c < grid; c++) {
+    std::vector<std::vector<int>> by_warp;
+    lpt(by_cta[c], cost, tb::kDenMainWarps, &by_warp);
+    const int arc0 = (int)out->arcs.size(), task0 = (int)out->tasks.size();
+    for (int w = 0; w < tb::kDenMainWarps; w++) {
+      for (int s : by_warp[w]) {
+        int4 tk;
+        tk.x = s;
+        tk.y = (int)out->arcs.size() - arc0;
+        tk.z = deg[s];
+        float pis = g.pi[s];
+        std::memcpy(&tk.w, &pis, 4);
+        out->tasks.push_back(tk);
+        for (int k = begin[s]; k < begin[s + 1]; k++) {
+          const int a = arc_of[k];
+          int4 ar;
+          ar.x = other[a];
+          ar.y = g.pdf[a];
+          float pr = g.prob[a], pio = g.pi[other[a]];
+          std::memcpy(&ar.z, &pr, 4);
+          std::memcpy(&ar.w, &pio, 4);
+          out->arcs.push_back(ar);
+        }
+      }
+      out->warp_task_off.push_back((int)out->tasks.size());
+    }
+    out->cta_arc_off.push_back((int)out->arcs.size());
+    out->cta_task_off.push_back((int)out->tasks.size());
+    out->max_arcs_cta = std::max(out->max_arcs_cta, (int)out->arcs.size() - arc0);
+    out->max_tasks_cta = std::max(out->max_tasks_cta, (int)out->tasks.size() - task0);
+  }
+}
+
+// Kaldi DenominatorGraph ctor: SetTransitions + SetInitialProbs.
+DenGraph* make_den_graph(int32_t N, int32_t A, const int32_t* src, const int32_t* dst, const int32_t* ilabel,
+                         const float* cost, int32_t start, const float* final_cost, int32_t num_pdfs) {
+  if (N <= 0 || A < 0 || num_pdfs <= 0 || start < 0 || start >= N) {
+    g_error = "denominator graph: bad sizes / start state";
+    return nullptr;
+  }
+  auto g = std::make_unique<DenGraph>();
+  g->N = N;
+  g->A = A;
+  g->P = num_pdfs;
+  g->start = start;
+  g->src.assign(src, src + A);
+  g->dst.assign(dst, dst + A);
+  g->pdf.resize(A);
+  g->prob.resize(A);
+  std::vector<double> tot(N);
+  for (int s = 0; s < N; s++) tot[s] = std::exp(-(double)final_cost[s]);
+  for (int a = 0; a < A; a++) {
+    if (src[a] < 0 || src[a] >= N || dst[a] < 0 || dst[a] >= N) {
+      g_error = "denominator graph: arc endpoint out of range";
+      return nullptr;
+    }
+    if (ilabel[a] < 1 || ilabel[a] > num_pdfs) {
+      g_error = "denominator graph: arc label not in [1, num_pdfs]";
+      return nullptr;
+    }
+    g->pdf[a] = ilabel[a] - 1;
+    g->prob[a] = std::exp(-cost[a]);
+    tot[src[a]] += std::exp(-(double)cost[a]);
+  }
+  for (int s = 0; s < N; s++) {
+    if (!(tot[s] > 0.0 && tot[s] < 100.0)) {
+      g_error = "denominator graph: a state's total outgoing probability is not in (0, 100)";
+      return nullptr;
+    }
+  }
+  // initial probabilities: average of 100 propagation steps from the start state
+  std::vector<int> begin(N + 1, 0);
+  for (int a = 0; a < A; a++) begin[src[a] + 1]++;
+  for (int s = 0; s < N; s++) begin[s + 1] += begin[s];
+  std::vector<int> by_src(A), pos(begin.begin(), begin.end() - 1);
+  for (int a = 0; a < A; a++) by_src[pos[src[a]]++] = a;
+  std::vector<double> w(A);
+  for (int a = 0; a < A; a++) w[a] = std::exp(-(double)cost[a]) / tot[src[a]];
+  std::vector<double> cur(N, 0.0), nxt(N, 0.0), avg(N, 0.0);
+  cur[start] = 1.0;
+  const int iters = 100;
+  for (int it = 0; it < iters; it++) {
+    for (int s = 0; s < N; s++) avg[s] += cur[s] / iters;
+    for (int s = 0; s < N; s++) {
+      if (cur[s] == 0.0) continue;
+      for (int k = begin[s]; k < begin[s + 1]; k++) nxt[dst[by_src[k]]] += cur[s] * w[by_src[k]];
+    }
+    double sum = 0.0;
+    for (int s = 0; s < N; s++) sum += nxt[s];
+    for (int s = 0; s < N; s++) {
+      cur[s] = nxt[s] / sum;
+      nxt[s] = 0.0;
+    }
+  }
+  g->pi.resize(N);
+  g->sum_pi = 0.0;
+  for (int s = 0; s < N; s++) {
+    g->pi[s] = (float)avg[s];
+    g->sum_pi += (double)g->pi[s];
+  }
+  return g.release();
+}
+
+// ---- FST file readers (OpenFst binary "vector"/"standard", or AT&T text) ----
+bool read_fst_file(const char* path, std::vector<int32_t>* src, std::vector<int32_t>* dst,
+                   std::vector<int32_t>* ilabel, std::vector<float>* cost, int32_t* start,
+                   std::vector<float>* final_cost) {
+  std::ifstream is(path, std::ios::binary);
+  if (!is) {
+    g_error = std::string("cannot open ") + path;
+    return false;
+  }
+  int32_t magic = 0;
+  is.read(reinterpret_cast<char*>(&magic), 4);
+  if (is && magic == 2125659606) {
+    auto read_str = [&](std::string* s) {
+      int32_t n = 0;
+      is.read(reinterpret_cast<char*>(&n), 4);
+      if (!is || n < 0 || n > 4096) return false;
+      s->resize(n);
+      is.read(&(*s)[0], n);
+      return (bool)is;
+    };
+    std::string fsttype, arctype;
+    int32_t version = 0, flags = 0;
+    uint64_t props = 0;
+    int64_t st = 0, nstates = 0, narcs = 0;
+    if (!read_str(&fsttype) || !read_str(&arctype)) {
+      g_error = "FST header truncated";
+      return false;
+    }
+    is.read(reinterpret_cast<char*>(&version), 4);
+    is.read(reinterpret_cast<char*>(&flags), 4);
+    is.read(reinterpret_cast<char*>(&props), 8);
+    is.read(reinterpret_cast<char*>(&st), 8);
+    is.read(reinterpret_cast<char*>(&nstates), 8);
+    is.read(reinterpret_cast<char*>(&narcs), 8);
+    if (!is || fsttype != "vector" || arctype != "standard") {
+      g_error = "FST must be a binary VectorFst<StdArc> (got fsttype='" + fsttype + "', arctype='" + arctype + "')";
+      return false;
+    }
+    if (flags & 3) {
+      g_error = "FST files with embedded symbol tables are not supported";
+      return false;
+    }
+    if (nstates <= 0 || nstates > (1 << 30)) {
+      g_error = "FST has an implausible number of states";
+      return false;
+    }
+    *start = (int32_t)st;
+    final_cost->resize(nstates);
+    for (int64_t s = 0; s < nstates; s++) {
+      float fw;
+      int64_t na;
+      is.read(reinterpret_cast<char*>(&fw), 4);
+      is.read(reinterpret_cast<char*>(&na), 8);
+      if (!is || na < 0) {
+        g_error = "FST body truncated";
+        return false;
+      }
+      (*final_cost)[s] = fw;
+      for (int64_t k = 0; k < na; k++) {
+        int32_t il, ol, ns;
+        float wt;
+        is.read(reinterpret_cast<char*>(&il), 4);
+        is.read(reinterpret_cast<char*>(&ol), 4);
+        is.read(reinterpret_cast<char*>(&wt), 4);
+        is.read(reinterpret_cast<char*>(&ns), 4);
+        if (!is) {
+          g_error = "FST body truncated";
+          return false;
+        }
+        src->push_back((int32_t)s);
+        dst->push_back(ns);
+        ilabel->push_back(il);
+        cost->push_back(wt);
+      }
+    }
+    return true;
+  }
+  // text: "src dst ilabel olabel [weight]" | "state [weight]"
+  is.clear();
+  is.seekg(0);
+  std::string line;
+  bool first = true;
+  int32_t max_state = -1;
+  std::vector<std::pair<int32_t, float>> finals;
+  while (std::getline(is, line)) {
+    std::istringstream ls(line);
+    std::vector<std::string> tok;
+    std::string t;
+    while (ls >> t) tok.push_back(t);
+    if (tok.empty()) continue;
+    try {
+      if (tok.size() >= 4) {
+        int32_t s = std::stoi(tok[0]), d = std::stoi(tok[1]), il = std::stoi(tok[2]);
+        float w = tok.size() >= 5 ? std::stof(tok[4]) : 0.f;
+        if (first) *start = s;
+        src->push_back(s);
+        dst->push_back(d);
+        ilabel->push_back(il);
+        cost->push_back(w);
+        max_state = std::max(max_state, std::max(s, d));
+      } else {
+        int32_t s = std::stoi(tok[0]);
+        float w = tok.size() >= 2 ? std::stof(tok[1]) : 0.f;
+        if (first) *start = s;
+        finals.emplace_back(s, w);
+        max_state = std::max(max_state, s);
+      }
+    } catch (...) {
+      g_error = std::string("cannot parse FST (neither OpenFst binary nor text): ") + path;
+      return false;
+    }
+    first = false;
+  }
+  if (max_state < 0) {
+    g_error = std::string("empty FST: ") + path;
+    return false;
+  }
+  final_cost->assign(max_state + 1, kInf);
+  for (auto& f : finals) (*final_cost)[f.first] = f.second;
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// Supervision handle
+// ---------------------------------------------------------------------------
+struct SupDevice {
+  DevBuf chain_level_off, level_state_off, chain_arc_off, in_off, in_arcs, out_off, out_arcs, final_cost, arc_row,
+      arc_pdf, arc_cost, uniq_row, uniq_pdf, uniq_arc_off, uniq_arcs;
+};
+
+struct Supervision {
+  float weight = 1.f;
+  int B = 0, T = 0, P = 0;
+  // split representation (host)
+  int num_chains = 0, S = 0, A = 0, num_uniq = 0;
+  std::vector<int> chain_level_off, level_state_off, chain_arc_off, in_off, out_off;
+  std::vector<int2> in_arcs, out_arcs;
+  std::vector<float> final_cost, arc_cost;
+  std::vector<int> arc_row, arc_pdf, uniq_row, uniq_pdf, uniq_arc_off, uniq_arcs;
+  std::mutex mu;
+  std::map<int, std::unique_ptr<SupDevice>> dev;
+};
+
+struct RawArc {
+  int src, dst, label;
+  float cost;
+};
+
+// Build the per-chain level structure from a list of chains; each chain is a
+// list of states (already in time order, first = its start) and arcs.
+Supervision* make_supervision(float weight, int32_t B, int32_t T, int32_t label_dim, int32_t S,
+                              const int32_t* arc_begin, const int32_t* arc_dst, const int32_t* arc_label,
+                              const float* arc_cost, const float* final_cost) {
+  if (B <= 0 || T <= 0 || label_dim <= 0 || S <= 0) {
+    g_error = "supervision: bad sizes";
+    return nullptr;
+  }
+  const int A = arc_begin[S];
+  // --- state times (Kaldi ComputeFstStateTimes): unique time per state, arcs advance by one
+  std::vector<int> time(S, -1);
+  time[0] = 0;
+  int total = -1;
+  for (int s = 0; s < S; s++) {
+    if (time[s] < 0) {
+      g_error = "supervision: FST not connected / not topologically sorted";
+      return nullptr;
+    }
+    if (s > 0 && time[s] < time[s - 1]) {
+      g_error = "supervision: states are not in time order";
+      return nullptr;
+    }
+    if (arc_begin[s + 1] < arc_begin[s]) {
+      g_error = "supervision: arc_begin not monotone";
+      return nullptr;
+    }
+    for (int a = arc_begin[s]; a < arc_begin[s + 1]; a++) {
+      const int d = arc_dst[a];
+      if (d <= s || d >= S) {
+        g_error = "supervision: arc destination out of range or not forward";
+        return nullptr;
+      }
+      if (arc_label[a] < 1 || arc_label[a] > label_dim) {
+        g_error = "supervision: arc label not in [1, label_dim]";
+        return nullptr;
+      }
+      if (time[d] == -1) time[d] = time[s] + 1;
+      else if (time[d] != time[s] + 1) {
+        g_error = "supervision: a state is reachable at two different times";
+        return nullptr;
+      }
+    }
+    if (final_cost[s] != kInf) {
+      if (total == -1) total = time[s];
+      else if (total != time[s]) {
+        g_error = "supervision: final states at different times";
+        return nullptr;
+      }
+    }
+  }
+  if (total != B * T) {
+    g_error = "supervision: FST length != num_sequences * frames_per_sequence";
+    return nullptr;
+  }
+  for (int s = 0; s < S; s++) {
+    if (time[s] == total && arc_begin[s + 1] != arc_begin[s]) {
+      g_error = "supervision: arcs leave a state at the final time";
+      return nullptr;
+    }
+    if (time[s] < total && final_cost[s] != kInf) {
+      g_error = "supervision: final state before the final time";
+      return nullptr;
+    }
+  }
+
+  // --- try to factorise per sequence: at each boundary time k*T the
+  // boundary states must carry identical out-arc sets up to a per-state constant.
+  std::vector<int> first_at(total + 2, S);  // first state index with time >= t
+  for (int s = S - 1; s >= 0; s--) first_at[time[s]] = s;
+  for (int t = total; t >= 0; t--)
+    if (first_at[t] == S) first_at[t] = (t == total) ? S : first_at[t + 1];
+  first_at[total + 1] = S;
+  auto states_at = [&](int t, int* lo, int* hi) {
+    *lo = first_at[t];
+    *hi = first_at[t + 1];
+  };
+
+  bool split = true;
+  std::vector<float> boundary_final(S, kInf);  // per-sequence final cost assigned to boundary states
+  if (B > 1) {
+    struct Key {
+      int dst, label;
+      float cost;
+    };
+    for (int k = 1; k < B && split; k++) {
+      int lo, hi;
+      states_at(k * T, &lo, &hi);
+      if (lo >= hi) {
+        split = false;
+        break;
+      }
+      auto arcs_of = [&](int s) {
+        std::vector<Key> v;
+        for (int a = arc_begin[s]; a < arc_begin[s + 1]; a++) v.push_back({arc_dst[a], arc_label[a], arc_cost[a]});
+        std::sort(v.begin(), v.end(), [](const Key& x, const Key& y) {
+          if (x.dst != y.dst) return x.dst < y.dst;
+          if (x.label != y.label) return x.label < y.label;
+          return x.cost < y.cost;
+        });
+        return v;
+      };
+      const std::vector<Key> ref = arcs_of(lo);
+      if (ref.empty()) {
+        split = false;
+        break;
+      }
+      boundary_final[lo] = 0.f;
+      for (int s = lo + 1; s < hi && split; s++) {
+        const std::vector<Key> v = arcs_of(s);
+        if (v.size() != ref.size()) {
+          split = false;
+          break;
+        }
+        const float delta = v[0].cost - ref[0].cost;
+        for (size_t i = 0; i < v.size(); i++) {
+          const float d = v[i].cost - ref[i].cost;
+          if (v[i].dst != ref[i].dst || v[i].label != ref[i].label ||
+              std::fabs(d - delta) > 1e-4f * std::max(1.f, std::fabs(delta))) {
+            split = false;
+            break;
+          }
+        }
+        boundary_final[s] = delta;
+      }
+    }
+  }
+
+  auto sup = std::make_unique<Supervision>();
+  sup->weight = weight;
+  sup->B = B;
+  sup->T = T;
+  sup->P = label_dim;
+
+  // New state numbering: chain by chain, level by level.
+  // split:   chain k = {virtual start (k>0) or state 0} + original states with time in (k*T, (k+1)*T]
+  // unsplit: one chain = all states.
+  std::vector<RawArc> arcs;      // in new state ids, grouped by chain
+  std::vector<int> arc_time;     // FST time of each new arc's source
+  std::vector<float> fin;        // per new state
+  sup->chain_level_off.assign(1, 0);
+  sup->chain_arc_off.assign(1, 0);
+  const int nchains = split ? B : 1;
+  const int levels_per_chain = split ? T : total;
+  std::vector<int> newid(S, -1);
+  int next_state = 0;
+  for (int c = 0; c < nchains; c++) {
+    const int t0 = c * levels_per_chain;
+    // level 0
+    int start_new = next_state++;
+    fin.push_back(kInf);
+    sup->level_state_off.push_back(start_new);
+    int start_orig;
+    if (c == 0) {
+      start_orig = 0;
+      newid[0] = start_new;
+    } else {
+      int lo, hi;
+      states_at(t0, &lo, &hi);
+      start_orig = lo;  // the reference boundary state f*: its out-arcs are this chain's start arcs
+    }
+    // levels 1..levels_per_chain
+    for (int l = 1; l <= levels_per_chain; l++) {
+      int lo, hi;
+      states_at(t0 + l, &lo, &hi);
+      sup->level_state_off.push_back(next_state);
+      for (int s = lo; s < hi; s++) {
+        newid[s] = next_state++;
+        float f = kInf;
+        if (l == levels_per_chain) f = (split && c + 1 < nchains) ? boundary_final[s] : final_cost[s];
+        fin.push_back(f);
+      }
+    }
+    sup->level_state_off.push_back(next_state);  // end of last level
+    sup->chain_level_off.push_back((int)sup->level_state_off.size());
+    // arcs: start arcs, then arcs of states at levels 1..levels_per_chain-1
+    for (int a = arc_begin[start_orig]; a < arc_begin[start_orig + 1]; a++) {
+      arcs.push_back({start_new, newid[arc_dst[a]], arc_label[a], arc_cost[a]});
+      arc_time.push_back(t0);
+    }
+    for (int l = 1; l < levels_per_chain; l++) {
+      int lo, hi;
+      states_at(t0 + l, &lo, &hi);
+      for (int s = lo; s < hi; s++)
+        for (int a = arc_begin[s]; a < arc_begin[s + 1]; a++) {
+          arcs.push_back({newid[s], newid[arc_dst[a]], arc_label[a], arc_cost[a]});
+          arc_time.push_back(t0 + l);
+        }
+    }
+    sup->chain_arc_off.push_back((int)arcs.size());
+  }
+  // level_state_off layout per chain: levels_per_chain+1 level starts + 1 end => nlevels+1 entries
+  const int NS = next_state, NA = (int)arcs.size();
+  (void)A;
+  sup->num_chains = nchains;
+  sup->S = NS;
+  sup->A = NA;
+  sup->final_cost = fin;
+  sup->arc_cost.resize(NA);
+  sup->arc_row.resize(NA);
+  sup->arc_pdf.resize(NA);
+  sup->in_off.assign(NS + 1, 0);
+  sup->out_off.assign(NS + 1, 0);
+  for (int a = 0; a < NA; a++) {
+    sup->arc_cost[a] = arcs[a].cost;
+    sup->arc_pdf[a] = arcs[a].label - 1;
+    const int seq = arc_time[a] / T, frame = arc_time[a] % T;
+    sup->arc_row[a] = frame * B + seq;  // Kaldi ComputeRowIndex
+    sup->in_off[arcs[a].dst + 1]++;
+    sup->out_off[arcs[a].src + 1]++;
+  }
+  for (int s = 0; s < NS; s++) {
+    sup->in_off[s + 1] += sup->in_off[s];
+    sup->out_off[s + 1] += sup->out_off[s];
+  }
+  sup->in_arcs.resize(NA);
+  sup->out_arcs.resize(NA);
+  {
+    std::vector<int> ip(sup->in_off.begin(), sup->in_off.end() - 1), op(sup->out_off.begin(), sup->out_off.end() - 1);
+    for (int a = 0; a < NA; a++) {
+      sup->in_arcs[ip[arcs[a].dst]++] = make_int2(arcs[a].src, a);
+      sup->out_arcs[op[arcs[a].src]++] = make_int2(arcs[a].dst, a);
+    }
+  }
+  // de-duplicate (row, pdf) so the derivative has one writer per element (Kaldi ComputeLookupIndexes)
+  {
+    std::vector<int> order(NA);
+    for (int a = 0; a < NA; a++) order[a] = a;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+      if (sup->arc_row[x] != sup->arc_row[y]) return sup->arc_row[x] < sup->arc_row[y];
+      return sup->arc_pdf[x] < sup->arc_pdf[y];
+    });
+    sup->uniq_arc_off.assign(1, 0);
+    for (int i = 0; i < NA; i++) {
+      const int a = order[i];
+      if (i == 0 || sup->arc_row[a] != sup->arc_row[order[i - 1]] || sup->arc_pdf[a] != sup->arc_pdf[order[i - 1]]) {
+        if (i > 0) sup->uniq_arc_off.push_back(i);
+        sup->uniq_row.push_back(sup->arc_row[a]);
+        sup->uniq_pdf.push_back(sup->arc_pdf[a]);
+      }
+      sup->uniq_arcs.push_back(a);
+    }
+    sup->uniq_arc_off.push_back(NA);
+    sup->num_uniq = (int)sup->uniq_row.size();
+    if (NA == 0) {
+      sup->uniq_arc_off.assign(1, 0);
+      sup->num_uniq = 0;
+    }
+  }
+  return sup.release();
+}
+
+// ---------------------------------------------------------------------------
+// per-device preparation
+// ---------------------------------------------------------------------------
+int get_den_device(DenGraph* g, int device, DenDevice** out) {
+  std::lock_guard<std::mutex> lock(g->mu);
+  auto it = g->dev.find(device);
+  if (it != g->dev.end()) {
+    *out = it->second.get();
+    return 1;
+  }
+  auto d = std::make_unique<DenDevice>();
+  d->grid = tb::den_max_grid(device);
+  if (d->grid <= 0) return fail("cannot query SM count");
+  for (int dir = 0; dir < 2; dir++) {
+    DirHost h;
+    build_dir(*g, dir, d->grid, &h);
+    CUDA_OK(upload(d->arcs[dir], h.arcs));
+    CUDA_OK(upload(d->tasks[dir], h.tasks));
+    CUDA_OK(upload(d->cta_arc_off[dir], h.cta_arc_off));
+    CUDA_OK(upload(d->cta_task_off[dir], h.cta_task_off));
+    CUDA_OK(upload(d->warp_task_off[dir], h.warp_task_off));
+    d->max_arcs_cta[dir] = h.max_arcs_cta;
+    d->max_tasks_cta[dir] = h.max_tasks_cta;
+  }
+  *out = d.get();
+  g->dev[device] = std::move(d);
+  return 1;
+}
+
+int get_sup_device(Supervision* s, int device, SupDevice** out) {
+  std::lock_guard<std::mutex> lock(s->mu);
+  auto it = s->dev.find(device);
+  if (it != s->dev.end()) {
+    *out = it->second.get();
+    return 1;
+  }
+  auto d = std::make_unique<SupDevice>();
+  CUDA_OK(upload(d->chain_level_off, s->chain_level_off));
+  CUDA_OK(upload(d->level_state_off, s->level_state_off));
+  CUDA_OK(upload(d->chain_arc_off, s->chain_arc_off));
+  CUDA_OK(upload(d->in_off, s->in_off));
+  CUDA_OK(upload(d->in_arcs, s->in_arcs));
+  CUDA_OK(upload(d->out_off, s->out_off));
+  CUDA_OK(upload(d->out_arcs, s->out_arcs));
+  CUDA_OK(upload(d->final_cost, s->final_cost));
+  CUDA_OK(upload(d->arc_row, s->arc_row));
+  CUDA_OK(upload(d->arc_pdf, s->arc_pdf));
+  CUDA_OK(upload(d->arc_cost, s->arc_cost));
+  CUDA_OK(upload(d->uniq_row, s->uniq_row));
+  CUDA_OK(upload(d->uniq_pdf, s->uniq_pdf));
+  CUDA_OK(upload(d->uniq_arc_off, s->uniq_arc_off));
+  CUDA_OK(upload(d->uniq_arcs, s->uniq_arcs));
+  *out = d.get();
+  s->dev[device] = std::move(d);
+  return 1;
+}
+
+int get_workspace(DenGraph* g, int device, void* stream, Workspace** out) {
+  std::lock_guard<std::mutex> lock(g->mu);
+  auto key = std::make_pair(device, stream);
+  auto it = g->ws.find(key);
+  if (it != g->ws.end()) {
+    *out = it->second.get();
+    return 1;
+  }
+  auto w = std::make_unique<Workspace>();
+  CUDA_OK(cudaStreamCreateWithFlags(&w->side, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming));
+  CUDA_OK(cudaMallocHost(&w->pinned, 4 * sizeof(float)));
+  *out = w.get();
+  g->ws[key] = std::move(w);
+  return 1;
+}
+
+// Resolve and clear the profiling events of every workspace of this graph.
+void harvest_profile(DenGraph* g) {
+  std::lock_guard<std::mutex> lock(g->mu);
+  for (auto& kv : g->ws) {
+    for (auto& pr : kv.second->prof) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+        std::lock_guard<std::mutex> l2(g_prof_mu);
+        g_prof_den_ms += ms;
+        g_prof_den_launches++;
+      }
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    kv.second->prof.clear();
+  }
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int pad_batch(int b) {
+  if (b <= 32) return 32;
+  if (b <= 64) return 64;
+  return (b + 127) / 128 * 128;
+}
+
+// The whole loss, enqueued on `stream`.  results_host may be null (no sync).
+int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t cols, int64_t ystride,
+            float* results_host, float* results_dev_user, float* deriv, int64_t dstride, float* xent,
+            int64_t xstride, float l2, float leaky, float xent_regularize, float deriv_scale, int device,
+            cudaStream_t stream) {
+  if (!g || !sup) return fail("null den_graph / supervision handle");
+  if (!y) return fail("null nnet_output");
+  const int B = sup->B, T = sup->T, P = g->P, N = g->N;
+  if (rows != (int64_t)B * T) return fail("nnet_output rows != num_sequences * frames_per_sequence");
+  if (cols != P) return fail("nnet_output cols != den_graph.NumPdfs()");
+  if (sup->P != P) return fail("supervision.label_dim != den_graph.NumPdfs()");
+  if (ystride < cols || (deriv && dstride < cols) || (xent && xstride < cols)) return fail("row stride < cols");
+  if (!(leaky > 0.f && leaky < 1.f)) return fail("leaky_hmm_coefficient must be in (0, 1)");
+  if ((int64_t)N * tb::kMaxBP >= (1ll << 31) || (int64_t)P * tb::kMaxBP >= (1ll << 31))
+    return fail("graph too large for 32-bit tile offsets");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail("cannot select CUDA device");
+
+  DenDevice* dd;
+  SupDevice* sd;
+  Workspace* ws;
+  if (!get_den_device(g, device, &dd)) return 0;
+  if (!get_sup_device(sup, device, &sd)) return 0;
+  if (!get_workspace(g, device, (void*)stream, &ws)) return 0;
+  const bool want_xent = xent != nullptr && xent_regularize != 0.f;
+
+  if (!deriv) {  // objective only: derivatives go to scratch
+    CUDA_OK(ws->scratch_deriv.reserve(sizeof(float) * (size_t)rows * cols));
+    deriv = ws->scratch_deriv.as<float>();
+    dstride = cols;
+  }
+
+  // ---- numerator on the side stream
+  const size_t nA = (size_t)sup->A, nS = (size_t)sup->S;
+  size_t off_arcval = 0, off_la = align_up(off_arcval + 8 * nA, 256), off_lb = align_up(off_la + 8 * nS, 256),
+         off_post = align_up(off_lb + 8 * nS, 256), off_clp = align_up(off_post + 4 * nA, 256),
+         num_total = align_up(off_clp + 8 * (size_t)sup->num_chains, 256);
+  CUDA_OK(ws->num_scratch.reserve(num_total));
+  char* nb = ws->num_scratch.as<char>();
+  tb::NumParams np;
+  np.num_chains = sup->num_chains;
+  np.chain_level_off = sd->chain_level_off.as<int>();
+  np.level_state_off = sd->level_state_off.as<int>();
+  np.chain_arc_off = sd->chain_arc_off.as<int>();
+  np.in_off = sd->in_off.as<int>();
+  np.in_arcs = sd->in_arcs.as<int2>();
+  np.out_off = sd->out_off.as<int>();
+  np.out_arcs = sd->out_arcs.as<int2>();
+  np.final_cost = sd->final_cost.as<float>();
+  np.arc_row = sd->arc_row.as<int>();
+  np.arc_pdf = sd->arc_pdf.as<int>();
+  np.arc_cost = sd->arc_cost.as<float>();
+  np.y = y;
+  np.ystride = ystride;
+  np.arc_val = reinterpret_cast<double*>(nb + off_arcval);
+  np.log_alpha = reinterpret_cast<double*>(nb + off_la);
+  np.log_beta = reinterpret_cast<double*>(nb + off_lb);
+  np.arc_post = reinterpret_cast<float*>(nb + off_post);
+  np.chain_logprob = reinterpret_cast<double*>(nb + off_clp);
+  CUDA_OK(cudaEventRecord(ws->ev_fork, stream));
+  CUDA_OK(cudaStreamWaitEvent(ws->side, ws->ev_fork, 0));
+  CUDA_OK(tb::launch_numerator(np, ws->side));
+  CUDA_OK(cudaEventRecord(ws->ev_join, ws->side));
+
+  // ---- denominator passes of at most kMaxBP sequences
+  const int maxBP = pad_batch(std::min(B, tb::kMaxBP));
+  CUDA_OK(ws->alpha.reserve(sizeof(float) * (size_t)(T + 1) * N * maxBP));
+  CUDA_OK(ws->beta.reserve(sizeof(float) * (size_t)2 * N * maxBP));
+  const size_t tile_floats = (size_t)2 * P * maxBP;
+  CUDA_OK(ws->tiles.reserve(sizeof(float) * tile_floats));  // etile
+  // zeroed block: gtile | Ssum | Bsum | barrier(+pad) ;  scalars + results live after it
+  const size_t z_gtile = 0, z_S = align_up(z_gtile + 4 * tile_floats, 256),
+               z_B = align_up(z_S + 8 * (size_t)(T + 1) * maxBP, 256),
+               z_bar = align_up(z_B + 8 * (size_t)(T + 1) * maxBP, 256), z_end = z_bar + 256,
+               z_scal = z_end, z_res = z_scal + 64, z_total = z_res + 64;
+  CUDA_OK(ws->zeroed.reserve(z_total));
+  char* zb = ws->zeroed.as<char>();
+  CUDA_OK(cudaMemsetAsync(zb + z_scal, 0, 128, stream));
+
+  tb::DenParams dp;
+  for (int dir = 0; dir < 2; dir++) {
+    dp.dir[dir].arcs = dd->arcs[dir].as<int4>();
+    dp.dir[dir].tasks = dd->tasks[dir].as<int4>();
+    dp.dir[dir].cta_arc_off = dd->cta_arc_off[dir].as<int>();
+    dp.dir[dir].cta_task_off = dd->cta_task_off[dir].as<int>();
+    dp.dir[dir].warp_task_off = dd->warp_task_off[dir].as<int>();
+    dp.dir[dir].max_arcs_cta = dd->max_arcs_cta[dir];
+    dp.dir[dir].max_tasks_cta = dd->max_tasks_cta[dir];
+  }
+  dp.N = N;
+  dp.P = P;
+  dp.Btot = B;
+  dp.T = T;
+  dp.y = y;
+  dp.ystride = ystride;
+  dp.deriv = deriv;
+  dp.dstride = dstride;
+  dp.alpha = ws->alpha.as<float>();
+  dp.beta = ws->beta.as<float>();
+  dp.etile = ws->tiles.as<float>();
+  dp.gtile = reinterpret_cast<float*>(zb + z_gtile);
+  dp.Ssum = reinterpret_cast<double*>(zb + z_S);
+  dp.Bsum = reinterpret_cast<double*>(zb + z_B);
+  dp.barrier = reinterpret_cast<unsigned*>(zb + z_bar);
+  dp.scalars = reinterpret_cast<double*>(zb + z_scal);
+  dp.leaky = leaky;
+  dp.sum_pi = (float)g->sum_pi;
+  dp.scale_gamma = deriv_scale * (-sup->weight);
+  dp.scale_y = deriv_scale * (-sup->weight * l2);
+  for (int seq0 = 0; seq0 < B; seq0 += tb::kMaxBP) {
+    dp.seq0 = seq0;
+    dp.B = std::min(B - seq0, tb::kMaxBP);
+    dp.BP = pad_batch(dp.B);
+    dp.arcs_in_smem = 1;
+    if (tb::den_smem_bytes(dp) > 200 * 1024) dp.arcs_in_smem = 0;
+    CUDA_OK(cudaMemsetAsync(zb, 0, z_end, stream));
+    if (g_profile.load()) {
+      cudaEvent_t e0, e1;
+      CUDA_OK(cudaEventCreate(&e0));
+      CUDA_OK(cudaEventCreate(&e1));
+      CUDA_OK(cudaEventRecord(e0, stream));
+      CUDA_OK(tb::launch_den(dp, dd->grid, stream));
+      CUDA_OK(cudaEventRecord(e1, stream));
+      std::lock_guard<std::mutex> lock(g->mu);
+      ws->prof.emplace_back(e0, e1);
+    } else {
+      CUDA_OK(tb::launch_den(dp, dd->grid, stream));
+    }
+  }
+
+  // ---- final pass
+  float* res_dev = reinterpret_cast<float*>(zb + z_res);
+  if (want_xent) CUDA_OK(cudaMemset2DAsync(xent, sizeof(float) * xstride, 0, sizeof(float) * cols, rows, stream));
+  CUDA_OK(cudaStreamWaitEvent(stream, ws->ev_join, 0));
+  tb::FinalParams fp;
+  fp.den_scalars = dp.scalars;
+  fp.chain_logprob = np.chain_logprob;
+  fp.num_chains = sup->num_chains;
+  fp.B = B;
+  fp.T = T;
+  fp.sup_weight = sup->weight;
+  fp.l2 = l2;
+  fp.deriv_scale = deriv_scale;
+  fp.results_dev = res_dev;
+  fp.deriv = deriv;
+  fp.dstride = dstride;
+  fp.xent = want_xent ? xent : nullptr;
+  fp.xstride = xstride;
+  fp.y = y;
+  fp.ystride = ystride;
+  fp.rows = rows;
+  fp.cols = cols;
+  fp.num_uniq = sup->num_uniq;
+  fp.uniq_row = sd->uniq_row.as<int>();
+  fp.uniq_pdf = sd->uniq_pdf.as<int>();
+  fp.uniq_arc_off = sd->uniq_arc_off.as<int>();
+  fp.uniq_arcs = sd->uniq_arcs.as<int>();
+  fp.arc_post = np.arc_post;
+  CUDA_OK(tb::launch_final(fp, stream));
+  if (results_dev_user)
+    CUDA_OK(cudaMemcpyAsync(results_dev_user, res_dev, 3 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  if (results_host) {
+    CUDA_OK(cudaMemcpyAsync(ws->pinned, res_dev, 4 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaStreamSynchronize(stream));
+    results_host[0] = ws->pinned[0];
+    results_host[1] = ws->pinned[1];
+    results_host[2] = ws->pinned[2];
+  }
+  return 1;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+const char* torchain_last_error(void) { return g_error.c_str(); }
+int torchain_abi_version(void) { return 1; }
+int64_t torchain_kernel_launch_count(void) { return tb::launch_count(); }
+
+int my_lib_set_kaldi_device(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return fail("no CUDA driver / device");
+  if (device < 0 || device >= n) return fail("CUDA device index out of range");
+  return 1;
+}
+
+void* torchain_denominator_graph_from_arrays(int32_t num_states, int32_t num_arcs, const int32_t* src,
+                                             const int32_t* dst, const int32_t* ilabel, const float* cost,
+                                             int32_t start, const float* final_cost, int32_t num_pdfs) {
+  if (num_arcs > 0 && (!src || !dst || !ilabel || !cost)) return fail_ptr("denominator graph: null arc arrays");
+  if (!final_cost) return fail_ptr("denominator graph: null final_cost");
+  return make_den_graph(num_states, num_arcs, src, dst, ilabel, cost, start, final_cost, num_pdfs);
+}
+
+void* my_lib_denominator_graph_new(const char* rxfilename, int num_pdf) {
+  if (!rxfilename) return fail_ptr("null rxfilename");
+  std::vector<int32_t> src, dst, il;
+  std::vector<float> cost, fin;
+  int32_t start = 0;
+  if (!read_fst_file(rxfilename, &src, &dst, &il, &cost, &start, &fin)) return nullptr;
+  return make_den_graph((int32_t)fin.size(), (int32_t)src.size(), src.data(), dst.data(), il.data(), cost.data(),
+                        start, fin.data(), num_pdf);
+}
+
+void my_lib_denominator_graph_free(void* p) { delete static_cast<DenGraph*>(p); }
+int torchain_denominator_graph_num_states(void* p) { return p ? static_cast<DenGraph*>(p)->N : 0; }
+int torchain_denominator_graph_num_arcs(void* p) { return p ? static_cast<DenGraph*>(p)->A : 0; }
+int torchain_denominator_graph_num_pdfs(void* p) { return p ? static_cast<DenGraph*>(p)->P : 0; }
+int torchain_denominator_graph_initial_probs(void* p, float* out) {
+  if (!p || !out) return fail("null argument");
+  auto* g = static_cast<DenGraph*>(p);
+  std::memcpy(out, g->pi.data(), sizeof(float) * g->N);
+  return 1;
+}
+
+void* torchain_supervision_from_arrays(float weight, int32_t num_sequences, int32_t frames_per_sequence,
+                                       int32_t label_dim, int32_t num_states, const int32_t* arc_begin,
+                                       const int32_t* arc_dst, const int32_t* arc_label, const float* arc_cost,
+                                       const float* final_cost) {
+  if (!arc_begin || !final_cost) return fail_ptr("supervision: null arrays");
+  if (arc_begin[num_states > 0 ? num_states : 0] > 0 && (!arc_dst || !arc_label || !arc_cost))
+    return fail_ptr("supervision: null arc arrays");
+  return make_supervision(weight, num_sequences, frames_per_sequence, label_dim, num_states, arc_begin, arc_dst,
+                          arc_label, arc_cost, final_cost);
+}
+
+void* my_lib_supervision_new(void*) {
+  return fail_ptr("Kaldi egs readers are outside the chain-loss hot path; use torchain_supervision_from_arrays");
+}
+void* my_lib_supervision_rand_new(void*) {
+  return fail_ptr("Kaldi egs readers are outside the chain-loss hot path; use torchain_supervision_from_arrays");
+}
+void my_lib_supervision_free(void* p) { delete static_cast<Supervision*>(p); }
+int my_lib_supervision_num_pdf(void* p) { return p ? static_cast<Supervision*>(p)->P : 0; }
+int my_lib_supervision_num_sequence(void* p) { return p ? static_cast<Supervision*>(p)->B : 0; }
+int my_lib_supervision_num_frame(void* p) { return p ? static_cast<Supervision*>(p)->T : 0; }
+int torchain_supervision_num_chains(void* p) { return p ? static_cast<Supervision*>(p)->num_chains : 0; }
+
+int torchain_ComputeChainObjfAndDeriv_ex(void* den, void* sup, const float* y, int64_t rows, int64_t cols,
+                                         int64_t ystride, float* results, float* results_dev, float* deriv,
+                                         int64_t dstride, float* xent, int64_t xstride, float l2, float leaky,
+                                         float xent_regularize, float deriv_scale, int device, void* stream) {
+  return compute(static_cast<DenGraph*>(den), static_cast<Supervision*>(sup), y, rows, cols, ystride, results,
+                 results_dev, deriv, dstride, xent, xstride, l2, leaky, xent_regularize, deriv_scale, device,
+                 static_cast<cudaStream_t>(stream));
+}
+
+int my_lib_ComputeChainObjfAndDeriv(void* den, void* sup, const float* y, int64_t rows, int64_t cols,
+                                    int64_t ystride, float* results, float* deriv, int64_t dstride, float* xent,
+                                    int64_t xstride, float l2, float leaky, float xent_regularize, int device,
+                                    void* stream) {
+  if (!results) return fail("null results");
+  return compute(static_cast<DenGraph*>(den), static_cast<Supervision*>(sup), y, rows, cols, ystride, results,
+                 nullptr, deriv, dstride, xent, xstride, l2, leaky, xent_regularize, 1.0f, device,
+                 static_cast<cudaStream_t>(stream));
+}
+
+int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_host, int64_t rows, int64_t cols,
+                                           int64_t ystride, float* results, float* deriv_host, int64_t dstride,
+                                           float* xent_host, int64_t xstride, float l2, float leaky,
+                                           float xent_regularize, int device) {
+  if (!den || !sup) return fail("null den_graph / supervision handle");
+  if (!y_host || !results) return fail("null nnet_output / results");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail("cannot select CUDA device");
+  auto* g = static_cast<DenGraph*>(den);
+  // staging buffers live in a workspace keyed by a private stream tag
+  static thread_local cudaStream_t hstream = nullptr;
+  static thread_local int hdev = -1;
+  if (hstream == nullptr || hdev != device) {
+    CUDA_OK(cudaStreamCreateWithFlags(&hstream, cudaStreamNonBlocking));
+    hdev = device;
+  }
+  static thread_local DevBuf dy, dd, dx;
+  const size_t bytes = sizeof(float) * (size_t)rows * cols;
+  CUDA_OK(dy.reserve(bytes));
+  CUDA_OK(dd.reserve(bytes));
+  const bool want_xent = xent_host != nullptr && xent_regularize != 0.f;
+  if (want_xent) CUDA_OK(dx.reserve(bytes));
+  CUDA_OK(cudaMemcpy2DAsync(dy.ptr, sizeof(float) * cols, y_host, sizeof(float) * ystride, sizeof(float) * cols, rows,
+                            cudaMemcpyHostToDevice, hstream));
+  // compute() synchronises hstream once to deliver `results`; the derivative
+  // copies below are ordered after it on the same stream.
+  if (!compute(g, static_cast<Supervision*>(sup), dy.as<float>(), rows, cols, cols, results, nullptr,
+               dd.as<float>(), cols, want_xent ? dx.as<float>() : nullptr, cols, l2, leaky, xent_regularize, 1.0f,
+               device, hstream))
+    return 0;
+  if (deriv_host)
+    CUDA_OK(cudaMemcpy2DAsync(deriv_host, sizeof(float) * dstride, dd.ptr, sizeof(float) * cols, sizeof(float) * cols,
+                              rows, cudaMemcpyDeviceToHost, hstream));
+  if (want_xent)
+    CUDA_OK(cudaMemcpy2DAsync(xent_host, sizeof(float) * xstride, dx.ptr, sizeof(float) * cols, sizeof(float) * cols,
+                              rows, cudaMemcpyDeviceToHost, hstream));
+  CUDA_OK(cudaStreamSynchronize(hstream));
+  return 1;
+}
+
+void torchain_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
+int torchain_profile_read(void* den_graph_ptr, double* den_kernel_ms, int64_t* den_kernel_launches, int reset) {
+  if (!den_graph_ptr) return fail("null den_graph handle");
+  harvest_profile(static_cast<DenGraph*>(den_graph_ptr));
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  if (den_kernel_ms) *den_kernel_ms = g_prof_den_ms;
+  if (den_kernel_launches) *den_kernel_launches = g_prof_den_launches;
+  if (reset) {
+    g_prof_den_ms = 0.0;
+    g_prof_den_launches = 0;
+  }
+  return 1;
+}
+
+double torchain_microbench_l2_gather(int device, int64_t table_bytes, int row_bytes, int iters) {
+  return tb::microbench_l2_gather(device, table_bytes, row_bytes, iters);
+}
+double torchain_microbench_l2_red(int device, int64_t table_bytes, int row_bytes, int iters) {
+  return tb::microbench_l2_red(device, table_bytes, row_bytes, iters);
+}
+double torchain_microbench_grid_barrier(int device, int iters) { return tb::microbench_grid_barrier(device, iters); }
+
+}  // extern "C"

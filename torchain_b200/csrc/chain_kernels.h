@@ -1,0 +1,126 @@
+// chain_kernels.h -- host-visible launch interface of the sm_100a kernels.
+// Internal to libtorchain_b200.so (the public boundary is include/torchain_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tb {
+
+// ---------------------------------------------------------------------------
+// Denominator (persistent alpha / beta+derivative kernel)
+// ---------------------------------------------------------------------------
+constexpr int kDenThreads = 512;               // threads per CTA (one CTA per SM)
+constexpr int kDenWarps = kDenThreads / 32;
+constexpr int kDenAuxWarps = 2;                // staging (transpose+exp) / derivative write-out warps
+constexpr int kDenMainWarps = kDenWarps - kDenAuxWarps;
+constexpr int kMaxBP = 256;                    // padded sequences per kernel pass
+
+// One direction of the graph, partitioned over `grid` CTAs x kDenMainWarps warps.
+//   dir 0 ("alpha"): tasks are destination states, arcs are their in-arcs
+//   dir 1 ("beta") : tasks are source states,      arcs are their out-arcs
+struct DenDir {
+  const int4* arcs;          // {other_state, pdf, float_bits(prob), float_bits(pi[other_state])}
+  const int4* tasks;         // {state, arc_begin (relative to the CTA's slice), arc_count, float_bits(pi[state])}
+  const int* cta_arc_off;    // [grid+1]
+  const int* cta_task_off;   // [grid+1]
+  const int* warp_task_off;  // [grid*kDenMainWarps+1] absolute task indices
+  int max_arcs_cta;
+  int max_tasks_cta;
+};
+
+struct DenParams {
+  DenDir dir[2];
+  int N, P;
+  int B;        // sequences in this pass
+  int BP;       // padded to 32*V*chunks
+  int Btot;     // sequences in the whole minibatch (row = frame*Btot + seq0 + s)
+  int seq0;     // first sequence of this pass
+  int T;
+  const float* y;
+  int64_t ystride;
+  float* deriv;
+  int64_t dstride;
+  float* alpha;      // (T+1) x N x BP   un-mixed alphas (Kaldi stores alpha-dash; we mix on the fly)
+  float* beta;       // 2 x N x BP       beta-dash ping-pong
+  float* etile;      // 2 x P x BP       exp(y) of one frame, sequence-innermost
+  float* gtile;      // 2 x P x BP       occupancies of one frame, sequence-innermost (zero on entry)
+  double* Ssum;      // (T+1) x BP       sum_h alpha_t(h,s)      (zero on entry)
+  double* Bsum;      // (T+1) x BP       sum_h pi(h) beta'_t(h,s) (zero on entry)
+  double* scalars;   // [0] alpha.beta at t=0, [1] sum gamma_0, [2] den logprob, [3] sum y^2  (accumulated)
+  unsigned* barrier; // zero on entry
+  float leaky;
+  float sum_pi;
+  float scale_gamma;  // deriv_scale * (-supervision.weight)
+  float scale_y;      // deriv_scale * (-supervision.weight * l2_regularize)
+  int arcs_in_smem;   // 1: arc slices staged in shared memory
+};
+
+size_t den_smem_bytes(const DenParams& p);
+// Enqueues the persistent kernel with a cooperative launch of `grid` CTAs.
+cudaError_t launch_den(const DenParams& p, int grid, cudaStream_t stream);
+int den_max_grid(int device);  // co-resident CTAs (one per SM)
+
+// ---------------------------------------------------------------------------
+// Numerator (batched supervision-FST forward-backward) + final pass
+// ---------------------------------------------------------------------------
+struct NumParams {
+  int num_chains;
+  const int* chain_level_off;   // [num_chains+1] into level_state_off
+  const int* level_state_off;   // per level: first state (global state index); one extra entry per chain
+  const int* chain_arc_off;     // [num_chains+1] arc-id range of each chain
+  const int* in_off;            // [S+1]  in-arc CSR per state
+  const int2* in_arcs;          // {src_state, arc_id}
+  const int* out_off;           // [S+1]  out-arc CSR per state
+  const int2* out_arcs;         // {dst_state, arc_id}
+  const float* final_cost;      // [S]
+  const int* arc_row;           // [A] row of nnet_output (frame*B + seq)
+  const int* arc_pdf;           // [A]
+  const float* arc_cost;        // [A]
+  const float* y;
+  int64_t ystride;
+  double* arc_val;              // [A] scratch: y - cost
+  double* log_alpha;            // [S]
+  double* log_beta;             // [S]
+  float* arc_post;              // [A] occupancy of each arc
+  double* chain_logprob;        // [num_chains]
+};
+cudaError_t launch_numerator(const NumParams& p, cudaStream_t stream);
+
+struct FinalParams {
+  // scalars
+  const double* den_scalars;    // [4] from the denominator kernel
+  const double* chain_logprob;  // [num_chains]
+  int num_chains;
+  int B, T;
+  float sup_weight;
+  float l2;
+  float deriv_scale;
+  float* results_dev;           // [4]: objf, l2_term, weight, ok
+  // derivative fix-up
+  float* deriv;
+  int64_t dstride;
+  float* xent;                  // may be null
+  int64_t xstride;
+  const float* y;
+  int64_t ystride;
+  int64_t rows, cols;
+  // numerator posteriors, de-duplicated by (row, pdf)
+  int num_uniq;
+  const int* uniq_row;
+  const int* uniq_pdf;
+  const int* uniq_arc_off;      // [num_uniq+1]
+  const int* uniq_arcs;         // arc ids
+  const float* arc_post;
+};
+cudaError_t launch_final(const FinalParams& p, cudaStream_t stream);
+
+// kernels launched by this library so far (process-wide)
+void count_launch(int n = 1);
+int64_t launch_count();
+
+// micro-benchmarks
+double microbench_l2_gather(int device, int64_t table_bytes, int row_bytes, int iters);
+double microbench_l2_red(int device, int64_t table_bytes, int row_bytes, int iters);
+double microbench_grid_barrier(int device, int iters);
+
+}  // namespace tb

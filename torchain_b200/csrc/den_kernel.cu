@@ -1,0 +1,520 @@
+// den_kernel.cu -- persistent denominator forward (alpha) and backward
+// (beta + derivative) recurrences of the LF-MMI loss for sm_100a.
+//
+// Replaces, for the hot path only, Kaldi's DenominatorComputation
+// (kaldi@22fbdd:src/chain/chain-denominator.cc: AlphaFirstFrame, AlphaDash,
+// AlphaGeneralFrame, ComputeTotLogLike, BetaDashLastFrame, Beta,
+// BetaDashGeneralFrame, BetaGeneralFrameDebug) and its two per-frame kernels
+// in chain-kernels.cu, which the reference reaches through
+// /root/reference/src/my_lib_chain.cpp:129-131.  Algorithm restated in
+// SURVEY.md Appendix A.2; nothing here is derived from Kaldi's CUDA code.
+//
+// Design (DESIGN.md "Kernels"):
+//  * ONE launch for all 2T+3 phases; one CTA per SM; phases separated by a
+//    software grid barrier (cooperative launch guarantees co-residency).
+//  * HMM states are partitioned over CTAs x warps by a host-side LPT schedule
+//    (balanced by arc count); each CTA keeps its arc/task slice in shared memory.
+//  * Sequences are innermost: a warp handles one state for 32*V sequences, so
+//    every gather of alpha / beta / exp(y) is one coalesced 128*V-byte row.
+//  * exp(y) is produced on the fly, one frame ahead, by "aux" warps that
+//    transpose frame t of nnet_output into an L2-resident [pdf][seq] tile;
+//    the same warps transpose the finished occupancy tile of frame t+1 out to
+//    nnet_output_deriv (scaled, with the l2 term) during the backward pass.
+//  * Leaky-HMM mixing is applied by the consumer (alpha' = alpha + leaky*pi*S),
+//    so a frame needs ONE grid barrier; the per-frame normalisers S_t and the
+//    leaky beta sums are CTA-reduced and then accumulated with fp64 atomics.
+//  * Occupancies are accumulated with vectorised red.global.add.f32 into the
+//    L2-resident tile: no separate scatter kernel, no transposed deriv copy.
+
+#include "chain_kernels.h"
+
+#include <cstdio>
+
+namespace tb {
+namespace {
+
+// ------------------------------------------------------------------ helpers
+template <int V>
+__device__ __forceinline__ void ld_cg(const float* ptr, float (&v)[V]) {
+  if constexpr (V == 4) {
+    float4 t = __ldcg(reinterpret_cast<const float4*>(ptr));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if constexpr (V == 2) {
+    float2 t = __ldcg(reinterpret_cast<const float2*>(ptr));
+    v[0] = t.x; v[1] = t.y;
+  } else {
+    v[0] = __ldcg(ptr);
+  }
+}
+
+template <int V>
+__device__ __forceinline__ void ld_cs(const float* ptr, float (&v)[V]) {
+  if constexpr (V == 4) {
+    float4 t = __ldcs(reinterpret_cast<const float4*>(ptr));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else if constexpr (V == 2) {
+    float2 t = __ldcs(reinterpret_cast<const float2*>(ptr));
+    v[0] = t.x; v[1] = t.y;
+  } else {
+    v[0] = __ldcs(ptr);
+  }
+}
+
+template <int V>
+__device__ __forceinline__ void st_vec(float* ptr, const float (&v)[V]) {
+  if constexpr (V == 4) {
+    *reinterpret_cast<float4*>(ptr) = make_float4(v[0], v[1], v[2], v[3]);
+  } else if constexpr (V == 2) {
+    *reinterpret_cast<float2*>(ptr) = make_float2(v[0], v[1]);
+  } else {
+    *ptr = v[0];
+  }
+}
+
+// Fire-and-forget fp32 reduction at L2 (no return value): RED.E.ADD.F32[.vN]
+template <int V>
+__device__ __forceinline__ void red_add(float* ptr, const float (&v)[V]) {
+  if constexpr (V == 4) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3])
+                 : "memory");
+  } else if constexpr (V == 2) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(ptr), "f"(v[0]), "f"(v[1]) : "memory");
+  } else {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(ptr), "f"(v[0]) : "memory");
+  }
+}
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* ptr) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+
+// All CTAs of the (co-resident) grid meet here.  `epoch` lives in thread 0.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += gridDim.x;
+    __threadfence();  // release everything this CTA wrote (cumulative over the bar.sync above)
+    atomicAdd(counter, 1u);
+    while (ld_acquire(counter) < epoch) {
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+struct Smem {
+  float* red;     // [kDenMainWarps][BP]
+  float* tile;    // [kDenAuxWarps][32][33]
+  int4* tasks;    // [max_tasks_cta]   (only if staged)
+  int4* arcs;     // [max_arcs_cta]    (only if staged)
+};
+
+__device__ __forceinline__ Smem carve(unsigned char* base, const DenParams& p) {
+  Smem s;
+  s.red = reinterpret_cast<float*>(base);
+  size_t off = sizeof(float) * kDenMainWarps * p.BP;
+  s.tile = reinterpret_cast<float*>(base + off);
+  off += sizeof(float) * kDenAuxWarps * 32 * 33;
+  off = (off + 15) & ~size_t(15);
+  int max_tasks = max(p.dir[0].max_tasks_cta, p.dir[1].max_tasks_cta);
+  s.tasks = reinterpret_cast<int4*>(base + off);
+  off += sizeof(int4) * max_tasks;
+  s.arcs = reinterpret_cast<int4*>(base + off);
+  return s;
+}
+
+// CTA-level reduction of the main warps' per-sequence partial sums followed by
+// one fp64 atomic per sequence (148-way contention per address per frame).
+__device__ __forceinline__ void cta_reduce_to(const float* red, int BP, double* dst) {
+  __syncthreads();
+  for (int c = threadIdx.x; c < BP; c += kDenThreads) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < kDenMainWarps; w++) acc += red[w * BP + c];
+    atomicAdd(dst + c, (double)acc);
+  }
+}
+
+// ------------------------------------------------- aux-warp work: staging
+// Transpose frame t of nnet_output (rows frame*Btot+seq, pdf innermost) into
+// etile[pdf][seq] = exp(y); 32x32 tiles, one warp each, through padded smem.
+__device__ __forceinline__ void stage_exp(const DenParams& p, int t, float* etile, float* tile, int auxw, int lane,
+                                          bool want_sq, double& sumsq) {
+  const int BP = p.BP;
+  const int nts = BP >> 5, ntp = (p.P + 31) >> 5, ntiles = nts * ntp;
+  const float* yrow0 = p.y + ((int64_t)t * p.Btot + p.seq0) * p.ystride;
+  for (int i = blockIdx.x + gridDim.x * auxw; i < ntiles; i += gridDim.x * kDenAuxWarps) {
+    const int s0 = (i % nts) << 5, p0 = (i / nts) << 5;
+    const int pdf = p0 + lane;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      const int s = s0 + j;
+      v[j] = (s < p.B && pdf < p.P) ? __ldg(yrow0 + (int64_t)s * p.ystride + pdf) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      if (want_sq) sumsq += (double)v[j] * (double)v[j];
+      tile[j * 33 + lane] = expf(v[j]);  // padded sequences / pdfs: exp(0) = 1, never read back out
+    }
+    __syncwarp();
+#pragma unroll 8
+    for (int k = 0; k < 32; k++) {
+      const int pd = p0 + k;
+      if (pd < p.P) etile[(size_t)pd * BP + s0 + lane] = tile[lane * 33 + k];
+    }
+    __syncwarp();
+  }
+}
+
+// Transpose the finished occupancy tile of `frame` out to nnet_output_deriv:
+//   deriv(row, pdf) = scale_gamma * gamma(pdf, seq) + scale_y * y(row, pdf)
+// and reset the tile to zero for reuse two frames later.
+__device__ __forceinline__ void flush_gamma(const DenParams& p, int frame, float* gtile, float* tile, int auxw,
+                                            int lane, bool want_sum, double& gsum) {
+  const int BP = p.BP;
+  const int nts = BP >> 5, ntp = (p.P + 31) >> 5, ntiles = nts * ntp;
+  const int64_t row0 = (int64_t)frame * p.Btot + p.seq0;
+  for (int i = blockIdx.x + gridDim.x * auxw; i < ntiles; i += gridDim.x * kDenAuxWarps) {
+    const int s0 = (i % nts) << 5, p0 = (i / nts) << 5;
+#pragma unroll 8
+    for (int k = 0; k < 32; k++) {
+      const int pd = p0 + k;
+      float g = 0.f;
+      if (pd < p.P) {
+        float* ptr = gtile + (size_t)pd * BP + s0 + lane;
+        g = __ldcg(ptr);
+        *ptr = 0.f;
+      }
+      tile[k * 33 + lane] = g;
+    }
+    __syncwarp();
+    const int pdf = p0 + lane;
+#pragma unroll 8
+    for (int j = 0; j < 32; j++) {
+      const int s = s0 + j;
+      if (s < p.B && pdf < p.P) {
+        const float g = tile[lane * 33 + j];
+        float out = p.scale_gamma * g;
+        if (p.scale_y != 0.f) out = fmaf(p.scale_y, __ldg(p.y + (row0 + s) * p.ystride + pdf), out);
+        __stcs(p.deriv + (row0 + s) * p.dstride + pdf, out);
+        if (want_sum) gsum += (double)g;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------- main-warp work: recursions
+// alpha_t(h,s) = (1/S_{t-1}(s)) * sum_{arcs i->h} (alpha_{t-1}(i,s) + leaky*pi(i)*S_{t-1}(s)) * p * e_{t-1}(pdf,s)
+template <int V>
+__device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __restrict__ arcs,
+                                           const int4* __restrict__ tasks, int tb, int te, int t, float* red,
+                                           int warp, int lane) {
+  const int BP = p.BP;
+  const float* __restrict__ alpha_prev = p.alpha + (size_t)(t - 1) * p.N * BP;
+  float* __restrict__ alpha_cur = p.alpha + (size_t)t * p.N * BP;
+  const float* __restrict__ et = p.etile + (size_t)((t - 1) & 1) * p.P * BP;
+  const double* Sprev = p.Ssum + (size_t)(t - 1) * BP;
+  for (int col = lane * V; col < BP; col += 32 * V) {
+    float lamS[V], invS[V], part[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      const float S = (float)__ldcg(Sprev + col + v);
+      lamS[v] = p.leaky * S;
+      invS[v] = 1.0f / S;
+      part[v] = 0.f;
+    }
+    for (int task = tb; task < te; task++) {
+      const int4 tk = tasks[task];
+      const int4* __restrict__ a = arcs + tk.y;
+      const int n = tk.z;
+      float acc[V];
+#pragma unroll
+      for (int v = 0; v < V; v++) acc[v] = 0.f;
+#pragma unroll 4
+      for (int k = 0; k < n; k++) {
+        const int4 ar = a[k];
+        float al[V], e[V];
+        ld_cg<V>(alpha_prev + ar.x * BP + col, al);
+        ld_cg<V>(et + ar.y * BP + col, e);
+        const float pr = __int_as_float(ar.z), pi = __int_as_float(ar.w);
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          const float ad = fmaf(pi, lamS[v], al[v]);
+          acc[v] = fmaf(ad * pr, e[v], acc[v]);
+        }
+      }
+      float out[V];
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        out[v] = acc[v] * invS[v];
+        part[v] += out[v];
+      }
+      st_vec<V>(alpha_cur + tk.x * BP + col, out);
+    }
+#pragma unroll
+    for (int v = 0; v < V; v++) red[warp * BP + col + v] = part[v];
+  }
+}
+
+// beta'_t(h,s) = (1/S_t(s)) * sum_{arcs h->j} p * e_t(pdf,s) * (beta'_{t+1}(j,s) + b_{t+1}(s))
+// gamma_t(pdf,s) += that term * alpha'_t(h,s) / S_t(s)
+template <int V>
+__device__ __forceinline__ void beta_step(const DenParams& p, const int4* __restrict__ arcs,
+                                          const int4* __restrict__ tasks, int tb, int te, int t, float* red,
+                                          int warp, int lane, double& ab) {
+  const int BP = p.BP;
+  const float* __restrict__ alpha_t = p.alpha + (size_t)t * p.N * BP;
+  const float* __restrict__ beta_next = p.beta + (size_t)((t + 1) & 1) * p.N * BP;
+  float* __restrict__ beta_cur = p.beta + (size_t)(t & 1) * p.N * BP;
+  const float* __restrict__ et = p.etile + (size_t)(t & 1) * p.P * BP;
+  float* __restrict__ gt = p.gtile + (size_t)(t & 1) * p.P * BP;
+  const double* St = p.Ssum + (size_t)t * BP;
+  const double* Bn = p.Bsum + (size_t)(t + 1) * BP;
+  for (int col = lane * V; col < BP; col += 32 * V) {
+    float lamS[V], invS[V], bv[V], part[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      const float S = (float)__ldcg(St + col + v);
+      lamS[v] = p.leaky * S;
+      invS[v] = 1.0f / S;
+      bv[v] = p.leaky * (float)__ldcg(Bn + col + v);
+      part[v] = 0.f;
+    }
+    for (int task = tb; task < te; task++) {
+      const int4 tk = tasks[task];
+      const int4* __restrict__ a = arcs + tk.y;
+      const int n = tk.z;
+      const float pi_h = __int_as_float(tk.w);
+      float al[V], adash[V], occ[V], X[V];
+      ld_cs<V>(alpha_t + tk.x * BP + col, al);
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        adash[v] = fmaf(pi_h, lamS[v], al[v]);
+        occ[v] = adash[v] * invS[v];
+        X[v] = 0.f;
+      }
+#pragma unroll 4
+      for (int k = 0; k < n; k++) {
+        const int4 ar = a[k];
+        float be[V], e[V], g[V];
+        ld_cg<V>(beta_next + ar.x * BP + col, be);
+        ld_cg<V>(et + ar.y * BP + col, e);
+        const float pr = __int_as_float(ar.z);
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          const float vf = pr * (be[v] + bv[v]) * e[v];
+          X[v] += vf;
+          g[v] = vf * occ[v];
+        }
+        red_add<V>(gt + ar.y * BP + col, g);
+      }
+      float bd[V];
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        bd[v] = X[v] * invS[v];
+        part[v] = fmaf(pi_h, bd[v], part[v]);
+        if (t == 0 && col + v < p.B) ab += (double)adash[v] * (double)bd[v];
+      }
+      st_vec<V>(beta_cur + tk.x * BP + col, bd);
+    }
+#pragma unroll
+    for (int v = 0; v < V; v++) red[warp * BP + col + v] = part[v];
+  }
+}
+
+template <bool STAGED>
+__device__ __forceinline__ void load_dir(const DenParams& p, int d, const Smem& sm, const int4*& arcs,
+                                         const int4*& tasks, int& tb, int& te, int warp) {
+  const DenDir& D = p.dir[d];
+  const int task0 = D.cta_task_off[blockIdx.x], ntask = D.cta_task_off[blockIdx.x + 1] - task0;
+  const int arc0 = D.cta_arc_off[blockIdx.x], narc = D.cta_arc_off[blockIdx.x + 1] - arc0;
+  tb = 0;
+  te = 0;
+  if (warp < kDenMainWarps) {
+    tb = D.warp_task_off[blockIdx.x * kDenMainWarps + warp] - task0;
+    te = D.warp_task_off[blockIdx.x * kDenMainWarps + warp + 1] - task0;
+  }
+  if constexpr (STAGED) {
+    for (int i = threadIdx.x; i < ntask; i += kDenThreads) sm.tasks[i] = D.tasks[task0 + i];
+    for (int i = threadIdx.x; i < narc; i += kDenThreads) sm.arcs[i] = D.arcs[arc0 + i];
+    arcs = sm.arcs;
+    tasks = sm.tasks;
+    __syncthreads();
+  } else {
+    arcs = D.arcs + arc0;
+    tasks = D.tasks + task0;
+  }
+}
+
+// ------------------------------------------------------------------ kernel
+template <int V, bool STAGED>
+__global__ void __launch_bounds__(kDenThreads, 1) den_chain_kernel(const __grid_constant__ DenParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const Smem sm = carve(smem_raw, p);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_aux = warp >= kDenMainWarps;
+  const int auxw = warp - kDenMainWarps;
+  float* tile = sm.tile + (is_aux ? auxw : 0) * 32 * 33;
+  const int BP = p.BP, T = p.T;
+  unsigned epoch = 0;
+  double sumsq = 0.0, ab = 0.0, gsum = 0.0;
+
+  const int4* arcs;
+  const int4* tasks;
+  int tb, te;
+  load_dir<STAGED>(p, 0, sm, arcs, tasks, tb, te, warp);
+
+  // ---- prologue: alpha_0 = pi, S_0; stage exp(y_0)
+  if (is_aux) {
+    stage_exp(p, 0, p.etile, tile, auxw, lane, true, sumsq);
+  } else {
+    for (int col = lane * V; col < BP; col += 32 * V) {
+      float part = 0.f;
+      for (int task = tb; task < te; task++) {
+        const int4 tk = tasks[task];
+        const float pi_h = __int_as_float(tk.w);
+        float out[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) out[v] = pi_h;
+        st_vec<V>(p.alpha + tk.x * BP + col, out);
+        part += pi_h;
+      }
+#pragma unroll
+      for (int v = 0; v < V; v++) sm.red[warp * BP + col + v] = part;
+    }
+  }
+  cta_reduce_to(sm.red, BP, p.Ssum);
+  grid_barrier(p.barrier, epoch);
+
+  // ---- forward
+  for (int t = 1; t <= T; t++) {
+    if (is_aux) {
+      if (t < T) stage_exp(p, t, p.etile + (size_t)(t & 1) * p.P * BP, tile, auxw, lane, true, sumsq);
+    } else {
+      alpha_step<V>(p, arcs, tasks, tb, te, t, sm.red, warp, lane);
+    }
+    cta_reduce_to(sm.red, BP, p.Ssum + (size_t)t * BP);
+    grid_barrier(p.barrier, epoch);
+  }
+
+  // ---- backward prologue: beta'_T(h,s) = 1 / sum_h alpha'_T(h,s) = 1 / (S_T (1 + leaky*sum_pi))
+  load_dir<STAGED>(p, 1, sm, arcs, tasks, tb, te, warp);
+  if (is_aux) {
+    sumsq = warp_sum(sumsq);
+    if (lane == 0 && sumsq != 0.0) atomicAdd(p.scalars + 3, sumsq);
+  } else {
+    const double* ST = p.Ssum + (size_t)T * BP;
+    float* betaT = p.beta + (size_t)(T & 1) * p.N * BP;
+    for (int col = lane * V; col < BP; col += 32 * V) {
+      float inv[V], part[V];
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        const float S = (float)__ldcg(ST + col + v);
+        inv[v] = 1.0f / (S * (1.0f + p.leaky * p.sum_pi));
+        part[v] = 0.f;
+      }
+      for (int task = tb; task < te; task++) {
+        const int4 tk = tasks[task];
+        const float pi_h = __int_as_float(tk.w);
+        st_vec<V>(betaT + tk.x * BP + col, inv);
+#pragma unroll
+        for (int v = 0; v < V; v++) part[v] = fmaf(pi_h, inv[v], part[v]);
+      }
+#pragma unroll
+      for (int v = 0; v < V; v++) sm.red[warp * BP + col + v] = part[v];
+    }
+  }
+  cta_reduce_to(sm.red, BP, p.Bsum + (size_t)T * BP);
+  grid_barrier(p.barrier, epoch);
+
+  // ---- backward
+  for (int t = T - 1; t >= 0; t--) {
+    if (is_aux) {
+      if (t + 1 < T) flush_gamma(p, t + 1, p.gtile + (size_t)((t + 1) & 1) * p.P * BP, tile, auxw, lane, false, gsum);
+      if (t > 0) stage_exp(p, t - 1, p.etile + (size_t)((t - 1) & 1) * p.P * BP, tile, auxw, lane, false, sumsq);
+    } else {
+      beta_step<V>(p, arcs, tasks, tb, te, t, sm.red, warp, lane, ab);
+    }
+    cta_reduce_to(sm.red, BP, p.Bsum + (size_t)t * BP);
+    grid_barrier(p.barrier, epoch);
+  }
+
+  // ---- epilogue: frame 0's derivative rows, sanity sums, total log-likelihood
+  if (is_aux) {
+    flush_gamma(p, 0, p.gtile, tile, auxw, lane, true, gsum);
+    gsum = warp_sum(gsum);
+    if (lane == 0 && gsum != 0.0) atomicAdd(p.scalars + 1, gsum);
+  } else {
+    ab = warp_sum(ab);
+    if (lane == 0 && ab != 0.0) atomicAdd(p.scalars + 0, ab);
+  }
+  if (blockIdx.x == 0) {
+    // ComputeTotLogLike: sum_s log(sum_h alpha'_T(h,s)) + sum_{t<T} sum_s log S_t(s)
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < (T + 1) * BP; i += kDenThreads) {
+      const int t = i / BP, s = i - t * BP;
+      if (s < p.B) {
+        float S = (float)__ldcg(p.Ssum + i);
+        if (t == T) S = S * (1.0f + p.leaky * p.sum_pi);
+        acc += log((double)S);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) atomicAdd(p.scalars + 2, acc);
+  }
+}
+
+template <int V, bool STAGED>
+cudaError_t launch_t(const DenParams& p, int grid, size_t smem, cudaStream_t stream) {
+  auto kern = den_chain_kernel<V, STAGED>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  void* args[] = {const_cast<DenParams*>(&p)};
+  e = cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(kDenThreads), args, smem, stream);
+  if (e == cudaSuccess) count_launch();
+  return e;
+}
+
+}  // namespace
+
+size_t den_smem_bytes(const DenParams& p) {
+  size_t off = sizeof(float) * kDenMainWarps * p.BP;
+  off += sizeof(float) * kDenAuxWarps * 32 * 33;
+  off = (off + 15) & ~size_t(15);
+  if (p.arcs_in_smem) {
+    off += sizeof(int4) * (size_t)std::max(p.dir[0].max_tasks_cta, p.dir[1].max_tasks_cta);
+    off += sizeof(int4) * (size_t)std::max(p.dir[0].max_arcs_cta, p.dir[1].max_arcs_cta);
+  }
+  return off;
+}
+
+int den_max_grid(int device) {
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  return sms;
+}
+
+cudaError_t launch_den(const DenParams& p, int grid, cudaStream_t stream) {
+  const size_t smem = den_smem_bytes(p);
+  const int vec = p.BP >= 128 ? 4 : (p.BP >= 64 ? 2 : 1);
+  if (p.arcs_in_smem) {
+    if (vec == 4) return launch_t<4, true>(p, grid, smem, stream);
+    if (vec == 2) return launch_t<2, true>(p, grid, smem, stream);
+    return launch_t<1, true>(p, grid, smem, stream);
+  }
+  if (vec == 4) return launch_t<4, false>(p, grid, smem, stream);
+  if (vec == 2) return launch_t<2, false>(p, grid, smem, stream);
+  return launch_t<1, false>(p, grid, smem, stream);
+}
+
+}  // namespace tb

@@ -1,0 +1,190 @@
+// num_kernel.cu -- batched numerator (supervision FST) forward-backward and the
+// final pass (objf / l2 / weight, numeric guard, numerator derivative) for sm_100a.
+//
+// Replaces, for the hot path only, Kaldi's host-side NumeratorComputation
+// (kaldi@22fbdd:src/chain/chain-numerator.cc: Forward / Backward, with its
+// Lookup D2H gather and AddElements H2D scatter) and the tail of
+// ComputeChainObjfAndDeriv (kaldi@22fbdd:src/chain/chain-training.cc), which
+// the reference reaches through /root/reference/src/my_lib_chain.cpp:129-131.
+// Algorithm restated in SURVEY.md Appendix A.3 / A.5.
+//
+// One warp per numerator chain (one chain per sequence when the merged FST
+// factorises, see supervision splitting in chain_api.cu); states are walked
+// level by level (all arcs advance time by one frame), lanes over the states
+// of a level, log-domain fp64 as Kaldi.  All nnet_output values a chain touches
+// are gathered up front with full memory-level parallelism, so the serial
+// level loop only touches L1/L2-resident scratch.
+
+#include "chain_kernels.h"
+
+#include <atomic>
+#include <cmath>
+
+namespace tb {
+namespace {
+
+std::atomic<int64_t> g_launches{0};
+
+__device__ __forceinline__ double log_add(double x, double y) {
+  // kaldi@22fbdd:src/base/kaldi-math.h LogAdd(double, double)
+  double diff;
+  if (x < y) {
+    diff = x - y;
+    x = y;
+  } else {
+    diff = y - x;
+  }
+  if (diff >= -36.04365338911715) return x + log1p(exp(diff));
+  return x;  // includes -inf/-inf (diff = NaN)
+}
+
+constexpr int kNumThreads = 128;  // 4 chains per CTA
+
+__global__ void __launch_bounds__(kNumThreads) num_fb_kernel(const __grid_constant__ NumParams p) {
+  const int chain = (blockIdx.x * kNumThreads + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (chain >= p.num_chains) return;
+  const double kNegInf = -INFINITY;
+
+  // 1. gather y - cost for every arc of the chain
+  const int a0 = p.chain_arc_off[chain], a1 = p.chain_arc_off[chain + 1];
+  for (int a = a0 + lane; a < a1; a += 32) {
+    const float yv = __ldg(p.y + (int64_t)p.arc_row[a] * p.ystride + p.arc_pdf[a]);
+    p.arc_val[a] = (double)yv - (double)p.arc_cost[a];
+  }
+  __syncwarp();
+
+  const int lb = p.chain_level_off[chain];
+  const int nlevels = p.chain_level_off[chain + 1] - lb - 1;
+  const int* lso = p.level_state_off + lb;
+
+  // 2. forward
+  for (int st = lso[0] + lane; st < lso[1]; st += 32) p.log_alpha[st] = 0.0;  // the start state
+  __syncwarp();
+  for (int lev = 1; lev < nlevels; lev++) {
+    for (int st = lso[lev] + lane; st < lso[lev + 1]; st += 32) {
+      double acc = kNegInf;
+      for (int k = p.in_off[st]; k < p.in_off[st + 1]; k++) {
+        const int2 ia = p.in_arcs[k];
+        acc = log_add(acc, p.log_alpha[ia.x] + p.arc_val[ia.y]);
+      }
+      p.log_alpha[st] = acc;
+    }
+    __syncwarp();
+  }
+  // total over final states (all sit on the last level)
+  double tot = kNegInf;
+  for (int st = lso[nlevels - 1] + lane; st < lso[nlevels]; st += 32) {
+    const float fc = p.final_cost[st];
+    if (fc != INFINITY) tot = log_add(tot, p.log_alpha[st] - (double)fc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot = log_add(tot, __shfl_xor_sync(0xffffffffu, tot, o));
+  if (lane == 0) p.chain_logprob[chain] = tot;
+
+  // 3. backward + arc occupancies
+  for (int lev = nlevels - 1; lev >= 0; lev--) {
+    for (int st = lso[lev] + lane; st < lso[lev + 1]; st += 32) {
+      const float fc = p.final_cost[st];
+      double acc = (fc != INFINITY) ? -(double)fc : kNegInf;
+      const double la = p.log_alpha[st];
+      for (int k = p.out_off[st]; k < p.out_off[st + 1]; k++) {
+        const int2 oa = p.out_arcs[k];
+        const double v = p.arc_val[oa.y] + p.log_beta[oa.x];
+        acc = log_add(acc, v);
+        p.arc_post[oa.y] = (float)exp(la + v - tot);
+      }
+      p.log_beta[st] = acc;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- final pass, part 1: the three result scalars and the numeric guard
+__global__ void final_scalars_kernel(const __grid_constant__ FinalParams p) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int c = threadIdx.x; c < p.num_chains; c += blockDim.x) acc += p.chain_logprob[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double num = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) num += sh[w];
+    const double ab = p.den_scalars[0], gsum = p.den_scalars[1], den = p.den_scalars[2], sq = p.den_scalars[3];
+    // BetaGeneralFrameDebug at t = 0
+    bool ok = (fabs(ab - (double)p.B) <= 2.0) && (fabs(gsum - (double)p.B) <= 2.0);
+    const double w = (double)p.sup_weight;
+    float objf = (float)(w * num - w * den);
+    const float weight = (float)(w * (double)p.B * (double)p.T);
+    if (!(objf - objf == 0.0f) || !ok) {
+      ok = false;
+      objf = -10.0f * weight;
+    }
+    float l2_term = 0.f;
+    if (p.l2 != 0.f) {
+      const float scale = p.sup_weight * p.l2;
+      l2_term = (float)(-0.5 * (double)scale * sq);
+    }
+    p.results_dev[0] = objf;
+    p.results_dev[1] = l2_term;
+    p.results_dev[2] = weight;
+    p.results_dev[3] = ok ? 1.f : 0.f;
+  }
+}
+
+// ---- final pass, part 2: numerator occupancies into the derivative(s); on a
+// tripped guard the derivative is reset to the l2 part only (Kaldi: SetZero,
+// then AddMat(-scale, nnet_output)).
+__global__ void __launch_bounds__(256) final_deriv_kernel(const __grid_constant__ FinalParams p) {
+  const bool ok = p.results_dev[3] != 0.f;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  if (ok) {
+    const float wscale = p.deriv_scale * p.sup_weight;
+    for (int64_t u = tid; u < p.num_uniq; u += nthreads) {
+      float acc = 0.f;
+      for (int k = p.uniq_arc_off[u]; k < p.uniq_arc_off[u + 1]; k++) acc += p.arc_post[p.uniq_arcs[k]];
+      const int64_t r = p.uniq_row[u];
+      const int c = p.uniq_pdf[u];
+      if (p.deriv) p.deriv[r * p.dstride + c] += wscale * acc;
+      if (p.xent) p.xent[r * p.xstride + c] = wscale * acc;
+    }
+  } else {
+    const float sy = -p.deriv_scale * p.sup_weight * p.l2;
+    const int64_t total = p.rows * p.cols;
+    for (int64_t i = tid; i < total; i += nthreads) {
+      const int64_t r = i / p.cols, c = i - r * p.cols;
+      if (p.deriv) p.deriv[r * p.dstride + c] = (p.l2 != 0.f) ? sy * p.y[r * p.ystride + c] : 0.f;
+      if (p.xent) p.xent[r * p.xstride + c] = 0.f;
+    }
+  }
+}
+
+}  // namespace
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+cudaError_t launch_numerator(const NumParams& p, cudaStream_t stream) {
+  if (p.num_chains <= 0) return cudaSuccess;
+  const int chains_per_cta = kNumThreads / 32;
+  const int grid = (p.num_chains + chains_per_cta - 1) / chains_per_cta;
+  num_fb_kernel<<<grid, kNumThreads, 0, stream>>>(p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_final(const FinalParams& p, cudaStream_t stream) {
+  final_scalars_kernel<<<1, 256, 0, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  int blocks = (int)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (p.num_uniq + 255) / 256));
+  if (blocks < 148) blocks = 148;  // the (rare) guard path walks the whole matrix
+  final_deriv_kernel<<<blocks, 256, 0, stream>>>(p);
+  count_launch(2);
+  return cudaGetLastError();
+}
+
+}  // namespace tb

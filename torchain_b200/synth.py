@@ -1,0 +1,249 @@
+"""Synthetic inputs for the chain loss: denominator graphs, supervisions, nnet outputs.
+
+The reference has no runnable fixtures for this path (its tests need private
+CHiME-5 egs, /root/reference/test/test.py:36-38,83-86, or Kaldi's random
+TransitionModel machinery, /root/reference/src/my_lib_chain.cpp:138-213), so the
+configurations of BASELINE.json are generated here:
+
+* den graph: N states, out-degree ~ Poisson(mean_deg) plus a self-loop and a
+  ring arc (keeps the graph strongly connected), pdfs uniform, probabilities
+  Dirichlet-normalised per source state and scaled by (1 - final_prob).
+* supervision for each sequence: the union of K random T-step walks through the
+  den graph, merged into a lattice keyed by (frame, den state); arc label =
+  that den arc's pdf + 1, arc cost = -log(transition prob); the first arc also
+  carries -log(initial prob of the walk's first state).  This is what composing
+  a supervision with Kaldi's normalization FST produces
+  (/root/reference/src/my_lib_chain.cpp:200-204) and makes ``objf <= 0`` hold
+  (/root/reference/src/chain-supervision-test.hpp:285).  The per-sequence FSTs
+  are then concatenated the way Kaldi's MergeChainExamples/AppendSupervision
+  does (Concat + RmEpsilon): the final states of sequence k-1 carry copies of
+  sequence k's start arcs.
+
+Pure numpy; no dependency on the CUDA library or on oracle/.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class DenFst:
+    num_states: int
+    num_pdfs: int
+    start: int
+    src: np.ndarray      # int32 [A]
+    dst: np.ndarray      # int32 [A]
+    ilabel: np.ndarray   # int32 [A]  (pdf + 1)
+    cost: np.ndarray     # float32 [A]
+    final_cost: np.ndarray  # float32 [N], inf = non-final
+
+    @property
+    def num_arcs(self):
+        return int(self.src.shape[0])
+
+
+@dataclass
+class SupFst:
+    weight: float
+    num_sequences: int
+    frames_per_sequence: int
+    label_dim: int
+    arc_begin: np.ndarray   # int32 [S+1]
+    arc_dst: np.ndarray     # int32 [A]
+    arc_label: np.ndarray   # int32 [A]
+    arc_cost: np.ndarray    # float32 [A]
+    final_cost: np.ndarray  # float32 [S]
+
+    @property
+    def num_states(self):
+        return int(self.final_cost.shape[0])
+
+    @property
+    def num_arcs(self):
+        return int(self.arc_dst.shape[0])
+
+
+def make_den_fst(seed, num_states, num_pdfs, mean_deg=28.0, final_prob=0.05, max_deg=None):
+    """Random strongly-connected HMM graph (arcs grouped by source state)."""
+    rng = np.random.default_rng(seed)
+    N = int(num_states)
+    extra = rng.poisson(mean_deg, size=N).astype(np.int64)
+    if max_deg is not None:
+        extra = np.minimum(extra, max_deg)
+    deg = extra + 2  # + self-loop + ring arc
+    A = int(deg.sum())
+    begin = np.zeros(N + 1, dtype=np.int64)
+    np.cumsum(deg, out=begin[1:])
+    src = np.repeat(np.arange(N, dtype=np.int64), deg)
+    dst = rng.integers(0, N, size=A, dtype=np.int64)
+    dst[begin[:-1]] = np.arange(N)                 # self-loop
+    dst[begin[:-1] + 1] = (np.arange(N) + 1) % N   # ring
+    pdf = rng.integers(0, num_pdfs, size=A, dtype=np.int64)
+    g = rng.gamma(1.0, size=A)                     # Dirichlet(1) per source after normalisation
+    tot = np.add.reduceat(g, begin[:-1])
+    prob = g / np.repeat(tot, deg) * (1.0 - final_prob)
+    prob = np.maximum(prob, 1e-6)
+    cost = (-np.log(prob)).astype(np.float32)
+    final_cost = np.full(N, -np.log(final_prob) if final_prob > 0 else np.inf, dtype=np.float32)
+    return DenFst(N, int(num_pdfs), 0, src.astype(np.int32), dst.astype(np.int32),
+                  (pdf + 1).astype(np.int32), cost, final_cost)
+
+
+def initial_probs(den):
+    """Kaldi DenominatorGraph::SetInitialProbs, vectorised; float64."""
+    N = den.num_states
+    w = np.exp(-den.cost.astype(np.float64))
+    tot = np.exp(-den.final_cost.astype(np.float64))
+    tot = tot + np.bincount(den.src, weights=w, minlength=N)
+    wn = w / tot[den.src]
+    cur = np.zeros(N)
+    cur[den.start] = 1.0
+    avg = np.zeros(N)
+    for _ in range(100):
+        avg += cur / 100.0
+        nxt = np.bincount(den.dst, weights=cur[den.src] * wn, minlength=N)
+        cur = nxt / nxt.sum()
+    return avg
+
+
+def make_supervision(seed, den, num_sequences, frames_per_sequence, num_paths=4, weight=1.0,
+                     boundary_final_costs=False):
+    """Merged supervision FST over num_sequences * frames_per_sequence frames."""
+    rng = np.random.default_rng(seed)
+    B, T, K = int(num_sequences), int(frames_per_sequence), int(num_paths)
+    N = den.num_states
+    order = np.argsort(den.src, kind="stable")
+    begin = np.zeros(N + 1, dtype=np.int64)
+    np.cumsum(np.bincount(den.src, minlength=N), out=begin[1:])
+    outdeg = begin[1:] - begin[:-1]
+    pi = initial_probs(den)
+    cdf = np.cumsum(pi / pi.sum())
+
+    # K walks per sequence, vectorised over (B, K)
+    q = np.searchsorted(cdf, rng.random((B, K))).clip(0, N - 1)          # den state at frame 0
+    q0 = q.copy()
+    arc = np.empty((B, K, T), dtype=np.int64)                             # den arc taken at frame t
+    for t in range(T):
+        pick = (rng.random((B, K)) * outdeg[q]).astype(np.int64)
+        a = order[begin[q] + np.minimum(pick, outdeg[q] - 1)]
+        arc[:, :, t] = a
+        q = den.dst[a].astype(np.int64)
+
+    den_cost = den.cost.astype(np.float64)
+    states_final = []   # merged FST, built sequence by sequence
+    arc_src, arc_dst, arc_lab, arc_cost = [], [], [], []
+    n_states = 1        # state 0 = global start
+    prev_finals = None  # merged ids of the previous sequence's last-level states
+    prev_final_cost = None
+    for b in range(B):
+        # level-1 arcs: keyed by (q0, den arc)
+        a0 = arc[b, :, 0]
+        key0 = np.unique(np.stack([q0[b], a0], axis=1), axis=0)
+        # states per level l = 1..T keyed by den state
+        level_ids = []
+        level_states = []
+        for l in range(1, T + 1):
+            ds = np.unique(den.dst[arc[b, :, l - 1]].astype(np.int64))
+            ids = n_states + np.arange(ds.shape[0])
+            n_states += ds.shape[0]
+            level_states.append(ds)
+            level_ids.append(ids)
+        # start arcs of this sequence: (dst merged id, label, cost)
+        d1 = den.dst[key0[:, 1]].astype(np.int64)
+        st_dst = level_ids[0][np.searchsorted(level_states[0], d1)]
+        st_lab = den.ilabel[key0[:, 1]].astype(np.int64)
+        st_cost = den_cost[key0[:, 1]] - np.log(pi[key0[:, 0]])
+        if b == 0:
+            for j in range(st_dst.shape[0]):
+                arc_src.append(0)
+                arc_dst.append(int(st_dst[j]))
+                arc_lab.append(int(st_lab[j]))
+                arc_cost.append(float(st_cost[j]))
+        else:
+            # Concat + RmEpsilon: every final state f of the previous sequence gets the start arcs,
+            # with cost final(f) (x) arc cost
+            for f, fc in zip(prev_finals, prev_final_cost):
+                for j in range(st_dst.shape[0]):
+                    arc_src.append(int(f))
+                    arc_dst.append(int(st_dst[j]))
+                    arc_lab.append(int(st_lab[j]))
+                    arc_cost.append(float(st_cost[j] + fc))
+        # inner arcs, level l -> l+1 keyed by den arc id
+        for l in range(1, T):
+            au = np.unique(arc[b, :, l])
+            s_ids = level_ids[l - 1][np.searchsorted(level_states[l - 1], den.src[au].astype(np.int64))]
+            d_ids = level_ids[l][np.searchsorted(level_states[l], den.dst[au].astype(np.int64))]
+            o = np.argsort(s_ids, kind="stable")
+            for j in o:
+                arc_src.append(int(s_ids[j]))
+                arc_dst.append(int(d_ids[j]))
+                arc_lab.append(int(den.ilabel[au[j]]))
+                arc_cost.append(float(den_cost[au[j]]))
+        prev_finals = level_ids[T - 1]
+        if boundary_final_costs:
+            prev_final_cost = rng.random(prev_finals.shape[0]) * 2.0
+        else:
+            prev_final_cost = np.zeros(prev_finals.shape[0])
+    S = n_states
+    final_cost = np.full(S, np.inf, dtype=np.float32)
+    final_cost[prev_finals] = prev_final_cost.astype(np.float32)
+    arc_src = np.asarray(arc_src, dtype=np.int64)
+    o = np.argsort(arc_src, kind="stable")
+    arc_begin = np.zeros(S + 1, dtype=np.int64)
+    np.cumsum(np.bincount(arc_src, minlength=S), out=arc_begin[1:])
+    return SupFst(float(weight), B, T, den.num_pdfs, arc_begin.astype(np.int32),
+                  np.asarray(arc_dst, dtype=np.int32)[o], np.asarray(arc_lab, dtype=np.int32)[o],
+                  np.asarray(arc_cost, dtype=np.float32)[o], final_cost)
+
+
+def make_nnet_output(seed, num_sequences, frames_per_sequence, num_pdfs, scale=1.0, zero=False):
+    """(T*B, P) float32, rows frame-major (row = t*B + b)."""
+    rows = int(num_sequences) * int(frames_per_sequence)
+    if zero:
+        return np.zeros((rows, int(num_pdfs)), dtype=np.float32)
+    rng = np.random.default_rng(seed)
+    return (rng.standard_normal((rows, int(num_pdfs))) * scale).astype(np.float32)
+
+
+# --- BASELINE.json configurations -------------------------------------------
+def small_case(seed):
+    """cfg 1: mirrors the ranges of the reference's native test
+    (/root/reference/src/chain-supervision-test.hpp:390-399, my_lib_chain.cpp:198-199)."""
+    rng = np.random.default_rng(10_000 + seed)
+    P = int(rng.integers(5, 61))
+    N = int(rng.integers(5, 201))
+    B = int(rng.integers(1, 6))
+    T = int(rng.integers(2, 21))
+    if rng.integers(0, 4) == 0:
+        T *= 30
+    zero = bool(rng.integers(0, 4) == 0)
+    leaky = float([1e-5, 0.2, 0.1][int(rng.integers(0, 3))])
+    weight = float([1.0, 0.5][int(rng.integers(0, 2))])
+    l2 = float([0.0, 0.01][int(rng.integers(0, 2))])
+    K = int(rng.integers(1, 5))
+    den = make_den_fst(seed, N, P, mean_deg=float(rng.uniform(0.0, 4.0)), max_deg=4)
+    sup = make_supervision(seed + 1, den, B, T, num_paths=K, weight=weight,
+                           boundary_final_costs=bool(rng.integers(0, 2)))
+    y = make_nnet_output(seed + 2, B, T, P, zero=zero)
+    return dict(den=den, sup=sup, y=y, leaky=leaky, l2=l2, B=B, T=T, P=P, N=N)
+
+
+CONFIGS = {
+    # name: (P, N, mean_deg, B, T, leaky, l2)
+    "chime5": dict(P=2928, N=10_000, mean_deg=28.0, B=128, T=50, leaky=0.1, l2=5e-5),
+    "chime5_b512": dict(P=2928, N=10_000, mean_deg=28.0, B=512, T=50, leaky=0.1, l2=5e-5),
+    "large_tree": dict(P=6000, N=20_000, mean_deg=28.0, B=256, T=50, leaky=0.1, l2=5e-5),
+}
+
+
+def make_config(name, seed=1234, B=None, T=None, y_scale=2.0, with_y=True):
+    c = dict(CONFIGS[name])
+    if B is not None:
+        c["B"] = int(B)
+    if T is not None:
+        c["T"] = int(T)
+    den = make_den_fst(seed, c["N"], c["P"], mean_deg=c["mean_deg"])
+    sup = make_supervision(seed + 1, den, c["B"], c["T"], num_paths=4, weight=1.0)
+    y = make_nnet_output(seed + 2, c["B"], c["T"], c["P"], scale=y_scale) if with_y else None
+    c.update(den=den, sup=sup, y=y)
+    return c
