@@ -173,6 +173,11 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den_graph_ptr, void* supervisio
 void torchain_profile_enable(int on);
 int torchain_profile_read(void* den_graph_ptr, double* den_kernel_ms, int64_t* den_kernel_launches, int reset);
 
+/* With profiling enabled the kernel also stamps %globaltimer (ns) at every phase
+ * boundary of its last launch: [start, prologue, T forward frames, backward
+ * prologue, T backward frames, end].  Copies up to max_entries; returns the count. */
+int torchain_profile_timeline(void* den_graph_ptr, int64_t* out_ns, int max_entries);
+
 /* L2-resident random 512-byte-row gather: the measured denominator of the
  * gather roofline.  Returns achieved GB/s, <0 on error. */
 double torchain_microbench_l2_gather(int device, int64_t table_bytes, int row_bytes, int iters);

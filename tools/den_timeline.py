@@ -1,0 +1,71 @@
+"""Per-phase timeline of the persistent denominator kernel (globaltimer stamps).
+
+    python tools/den_timeline.py [--config chime5] [--batch B] [--frames T]
+Prints the mean forward / backward frame time and the slowest frames.
+"""
+import argparse
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import bench
+    from torchain_b200 import _lib, io
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="chime5")
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--frames", type=int, default=0)
+    args = ap.parse_args()
+    lib = _lib.load()
+    c = bench.make_workload(args.config, args.batch, args.frames, 0)
+    den, sup = c["den"], c["sup"]
+    B, T, P = c["B"], c["T"], c["P"]
+    g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
+                                        den.final_cost, den.num_pdfs)
+    s = io.Supervision.from_arrays(sup.weight, B, T, sup.label_dim, sup.arc_begin, sup.arc_dst, sup.arc_label,
+                                   sup.arc_cost, sup.final_cost)
+    y = torch.randn(T * B, P, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)) * 2.0
+    d = torch.empty_like(y)
+    res = np.zeros(3, dtype=np.float32)
+
+    def step():
+        ok = lib.my_lib_ComputeChainObjfAndDeriv(g.ptr, s.ptr, y.data_ptr(), T * B, P, P,
+                                                 res.ctypes.data_as(ctypes.c_void_p), d.data_ptr(), P, None, 0,
+                                                 c["l2"], c["leaky"], 0.0, 0,
+                                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert ok == 1, _lib.last_error()
+
+    for _ in range(3):
+        step()
+    lib.torchain_profile_enable(1)
+    step()
+    torch.cuda.synchronize()
+    n = 2 * T + 4
+    tl = np.zeros(n, dtype=np.int64)
+    got = lib.torchain_profile_timeline(g.ptr, tl.ctypes.data_as(ctypes.c_void_p), n)
+    lib.torchain_profile_enable(0)
+    assert got == n, got
+    dt = np.diff(tl) / 1e3  # us
+    # [start->prologue, T fwd frames, bwd prologue, T bwd frames, epilogue]
+    pro, fwd, bpro, bwd, epi = dt[0], dt[1:1 + T], dt[1 + T], dt[2 + T:2 + 2 * T], dt[2 + 2 * T]
+    print("config %s B=%d T=%d: total %.1f us" % (args.config, B, T, (tl[-1] - tl[0]) / 1e3))
+    print("prologue %.1f us | fwd frames mean %.2f min %.2f max %.2f (sum %.1f) | bwd prologue %.1f |"
+          " bwd frames mean %.2f min %.2f max %.2f (sum %.1f) | epilogue %.1f" %
+          (pro, fwd.mean(), fwd.min(), fwd.max(), fwd.sum(), bpro, bwd.mean(), bwd.min(), bwd.max(), bwd.sum(), epi))
+    A = den.num_arcs
+    print("ideal @14.5 TB/s L2 gather: fwd frame %.2f us (A*B*8 B), bwd frame gathers %.2f us + red A*B*4 B" %
+          (A * B * 8 / 14.5e6, A * B * 8 / 14.5e6))
+    if os.environ.get("TL_VERBOSE"):
+        print("fwd frames:", np.round(fwd, 1).tolist())
+        print("bwd frames:", np.round(bwd, 1).tolist())
+
+
+if __name__ == "__main__":
+    main()

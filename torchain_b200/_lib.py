@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtorchain_b200.so")
+LIB_PATH = os.environ.get("TORCHAIN_B200_LIB", os.path.join(_HERE, "libtorchain_b200.so"))
 
 _c_f = ctypes.c_float
 _c_i = ctypes.c_int
@@ -53,6 +53,7 @@ SIGNATURES = {
                _c_f, _c_f, _c_f, _c_i]),
     "torchain_profile_enable": (None, [_c_i]),
     "torchain_profile_read": (_c_i, [_c_p, _c_p, _c_p, _c_i]),
+    "torchain_profile_timeline": (_c_i, [_c_p, _c_p, _c_i]),
     "torchain_microbench_l2_gather": (_c_d, [_c_i, _c_i64, _c_i, _c_i]),
     "torchain_microbench_l2_red": (_c_d, [_c_i, _c_i64, _c_i, _c_i]),
     "torchain_microbench_grid_barrier": (_c_d, [_c_i, _c_i]),

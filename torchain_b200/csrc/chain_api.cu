@@ -102,13 +102,13 @@ struct DeviceGuard {
 // ---------------------------------------------------------------------------
 struct DirHost {  // one direction, partitioned
   std::vector<int4> arcs, tasks;
-  std::vector<int> cta_arc_off, cta_task_off, warp_task_off;
+  std::vector<int> cta_arc_off, cta_task_off, warp_task_off, warp_arc_off;
   int max_arcs_cta = 0, max_tasks_cta = 0;
 };
 
 struct DenDevice {  // per (device) copy
   int grid = 0;
-  DevBuf arcs[2], tasks[2], cta_arc_off[2], cta_task_off[2], warp_task_off[2];
+  DevBuf arcs[2], tasks[2], cta_arc_off[2], cta_task_off[2], warp_task_off[2], warp_arc_off[2];
   int max_arcs_cta[2] = {0, 0}, max_tasks_cta[2] = {0, 0};
 };
 
@@ -117,6 +117,8 @@ struct Workspace {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float* pinned = nullptr;  // 4 floats
+  char* timeline_dev = nullptr;
+  int timeline_len = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;  // around each denominator launch (profiling only)
   ~Workspace() {
     for (auto& pr : prof) {
@@ -185,6 +187,7 @@ void build_dir(const DenGraph& g, int dir, int grid, DirHost* out) {
   out->cta_arc_off.assign(1, 0);
   out->cta_task_off.assign(1, 0);
   out->warp_task_off.assign(1, 0);
+  out->warp_arc_off.assign(1, 0);
   out->max_arcs_cta = out->max_tasks_cta = 0;
   for (int c = 0; c < grid; c++) {
     std::vector<std::vector<int>> by_warp;
@@ -195,7 +198,7 @@ void build_dir(const DenGraph& g, int dir, int grid, DirHost* out) {
         int4 tk;
         tk.x = s;
         tk.y = (int)out->arcs.size() - arc0;
-        tk.z = deg[s];
+        tk.z = std::max(deg[s], 1);
         float pis = g.pi[s];
         std::memcpy(&tk.w, &pis, 4);
         out->tasks.push_back(tk);
@@ -209,8 +212,18 @@ void build_dir(const DenGraph& g, int dir, int grid, DirHost* out) {
           std::memcpy(&ar.w, &pio, 4);
           out->arcs.push_back(ar);
         }
+        if (deg[s] == 0) {  // a state without arcs still needs its end-of-state marker
+          int4 ar;
+          ar.x = s;
+          ar.y = 0;
+          ar.z = 0;  // probability 0.0f
+          ar.w = 0;
+          out->arcs.push_back(ar);
+        }
+        out->arcs.back().y |= (int)0x80000000u;
       }
       out->warp_task_off.push_back((int)out->tasks.size());
+      out->warp_arc_off.push_back((int)out->arcs.size());
     }
     out->cta_arc_off.push_back((int)out->arcs.size());
     out->cta_task_off.push_back((int)out->tasks.size());
@@ -710,6 +723,7 @@ int get_den_device(DenGraph* g, int device, DenDevice** out) {
     CUDA_OK(upload(d->cta_arc_off[dir], h.cta_arc_off));
     CUDA_OK(upload(d->cta_task_off[dir], h.cta_task_off));
     CUDA_OK(upload(d->warp_task_off[dir], h.warp_task_off));
+    CUDA_OK(upload(d->warp_arc_off[dir], h.warp_arc_off));
     d->max_arcs_cta[dir] = h.max_arcs_cta;
     d->max_tasks_cta[dir] = h.max_tasks_cta;
   }
@@ -863,7 +877,8 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   // zeroed block: gtile | Ssum | Bsum | barrier(+pad) ;  scalars + results live after it
   const size_t z_gtile = 0, z_S = align_up(z_gtile + 4 * tile_floats, 256),
                z_B = align_up(z_S + 8 * (size_t)(T + 1) * maxBP, 256),
-               z_bar = align_up(z_B + 8 * (size_t)(T + 1) * maxBP, 256), z_end = z_bar + 256,
+               z_bar = align_up(z_B + 8 * (size_t)(T + 1) * maxBP, 256),
+               z_tl = z_bar + 256, z_end = align_up(z_tl + 8 * (size_t)(2 * T + 8), 256),
                z_scal = z_end, z_res = z_scal + 64, z_total = z_res + 64;
   CUDA_OK(ws->zeroed.reserve(z_total));
   char* zb = ws->zeroed.as<char>();
@@ -876,6 +891,7 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
     dp.dir[dir].cta_arc_off = dd->cta_arc_off[dir].as<int>();
     dp.dir[dir].cta_task_off = dd->cta_task_off[dir].as<int>();
     dp.dir[dir].warp_task_off = dd->warp_task_off[dir].as<int>();
+    dp.dir[dir].warp_arc_off = dd->warp_arc_off[dir].as<int>();
     dp.dir[dir].max_arcs_cta = dd->max_arcs_cta[dir];
     dp.dir[dir].max_tasks_cta = dd->max_tasks_cta[dir];
   }
@@ -899,6 +915,13 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   dp.sum_pi = (float)g->sum_pi;
   dp.scale_gamma = deriv_scale * (-sup->weight);
   dp.scale_y = deriv_scale * (-sup->weight * l2);
+  {
+    const char* dbg = getenv("TORCHAIN_DEBUG_FLAGS");
+    dp.debug_flags = dbg ? atoi(dbg) : 0;
+  }
+  dp.timeline = g_profile.load() ? reinterpret_cast<unsigned long long*>(zb + z_tl) : nullptr;
+  ws->timeline_dev = zb + z_tl;
+  ws->timeline_len = 2 * T + 4;
   for (int seq0 = 0; seq0 < B; seq0 += tb::kMaxBP) {
     dp.seq0 = seq0;
     dp.B = std::min(B - seq0, tb::kMaxBP);
@@ -1102,6 +1125,21 @@ int torchain_profile_read(void* den_graph_ptr, double* den_kernel_ms, int64_t* d
     g_prof_den_launches = 0;
   }
   return 1;
+}
+
+int torchain_profile_timeline(void* den_graph_ptr, int64_t* out_ns, int max_entries) {
+  if (!den_graph_ptr || !out_ns) return 0;
+  auto* g = static_cast<DenGraph*>(den_graph_ptr);
+  std::lock_guard<std::mutex> lock(g->mu);
+  for (auto& kv : g->ws) {
+    Workspace* w = kv.second.get();
+    if (!w->timeline_dev || w->timeline_len <= 0) continue;
+    const int n = std::min(max_entries, w->timeline_len);
+    cudaSetDevice(kv.first.first);
+    if (cudaMemcpy(out_ns, w->timeline_dev, sizeof(int64_t) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return n;
+  }
+  return 0;
 }
 
 double torchain_microbench_l2_gather(int device, int64_t table_bytes, int row_bytes, int iters) {

@@ -9,9 +9,15 @@ namespace tb {
 // ---------------------------------------------------------------------------
 // Denominator (persistent alpha / beta+derivative kernel)
 // ---------------------------------------------------------------------------
-constexpr int kDenThreads = 512;               // threads per CTA (one CTA per SM)
+#ifndef DEN_THREADS
+#define DEN_THREADS 512
+#endif
+#ifndef DEN_AUX_WARPS
+#define DEN_AUX_WARPS 2
+#endif
+constexpr int kDenThreads = DEN_THREADS;       // threads per CTA (one CTA per SM)
 constexpr int kDenWarps = kDenThreads / 32;
-constexpr int kDenAuxWarps = 2;                // staging (transpose+exp) / derivative write-out warps
+constexpr int kDenAuxWarps = DEN_AUX_WARPS;                // staging (transpose+exp) / derivative write-out warps
 constexpr int kDenMainWarps = kDenWarps - kDenAuxWarps;
 constexpr int kMaxBP = 256;                    // padded sequences per kernel pass
 
@@ -19,11 +25,12 @@ constexpr int kMaxBP = 256;                    // padded sequences per kernel pa
 //   dir 0 ("alpha"): tasks are destination states, arcs are their in-arcs
 //   dir 1 ("beta") : tasks are source states,      arcs are their out-arcs
 struct DenDir {
-  const int4* arcs;          // {other_state, pdf, float_bits(prob), float_bits(pi[other_state])}
+  const int4* arcs;          // {other_state, pdf | end-of-state flag (bit 31), float_bits(prob), float_bits(pi[other_state])}
   const int4* tasks;         // {state, arc_begin (relative to the CTA's slice), arc_count, float_bits(pi[state])}
   const int* cta_arc_off;    // [grid+1]
   const int* cta_task_off;   // [grid+1]
   const int* warp_task_off;  // [grid*kDenMainWarps+1] absolute task indices
+  const int* warp_arc_off;   // [grid*kDenMainWarps+1] absolute arc indices
   int max_arcs_cta;
   int max_tasks_cta;
 };
@@ -53,6 +60,8 @@ struct DenParams {
   float scale_gamma;  // deriv_scale * (-supervision.weight)
   float scale_y;      // deriv_scale * (-supervision.weight * l2_regularize)
   int arcs_in_smem;   // 1: arc slices staged in shared memory
+  int debug_flags;    // timing experiments only (TORCHAIN_DEBUG_FLAGS): 1 = skip aux work in backward, 2 = skip REDs
+  unsigned long long* timeline;  // optional: globaltimer at every phase boundary (2T+5 entries), or null
 };
 
 size_t den_smem_bytes(const DenParams& p);

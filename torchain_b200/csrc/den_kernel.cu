@@ -144,122 +144,177 @@ __device__ __forceinline__ void cta_reduce_to(const float* red, int BP, double* 
 }
 
 // ------------------------------------------------- aux-warp work: staging
+// Both jobs work on 32 (sequences) x 32 (pdfs) tiles, one warp per tile, with all 32
+// (or 64) global loads of a tile in flight at once: the aux warps are latency-bound,
+// and they must finish inside the frame time of the main warps.
+
 // Transpose frame t of nnet_output (rows frame*Btot+seq, pdf innermost) into
-// etile[pdf][seq] = exp(y); 32x32 tiles, one warp each, through padded smem.
-__device__ __forceinline__ void stage_exp(const DenParams& p, int t, float* etile, float* tile, int auxw, int lane,
-                                          bool want_sq, double& sumsq) {
+// etile[pdf][seq] = exp(y) through padded shared memory.
+__device__ __forceinline__ void stage_exp_tile(const DenParams& p, int t, float* etile, float* tile, int i, int lane,
+                                               bool want_sq, double& sumsq) {
   const int BP = p.BP;
-  const int nts = BP >> 5, ntp = (p.P + 31) >> 5, ntiles = nts * ntp;
+  const int nts = BP >> 5;
   const float* yrow0 = p.y + ((int64_t)t * p.Btot + p.seq0) * p.ystride;
-  for (int i = blockIdx.x + gridDim.x * auxw; i < ntiles; i += gridDim.x * kDenAuxWarps) {
-    const int s0 = (i % nts) << 5, p0 = (i / nts) << 5;
-    const int pdf = p0 + lane;
-    float v[32];
+  const int s0 = (i % nts) << 5, p0 = (i / nts) << 5;
+  const int pdf = p0 + lane;
+  float v[32];
 #pragma unroll
-    for (int j = 0; j < 32; j++) {
-      const int s = s0 + j;
-      v[j] = (s < p.B && pdf < p.P) ? __ldg(yrow0 + (int64_t)s * p.ystride + pdf) : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-      if (want_sq) sumsq += (double)v[j] * (double)v[j];
-      tile[j * 33 + lane] = expf(v[j]);  // padded sequences / pdfs: exp(0) = 1, never read back out
-    }
-    __syncwarp();
-#pragma unroll 8
-    for (int k = 0; k < 32; k++) {
-      const int pd = p0 + k;
-      if (pd < p.P) etile[(size_t)pd * BP + s0 + lane] = tile[lane * 33 + k];
-    }
-    __syncwarp();
+  for (int j = 0; j < 32; j++) {
+    const int s = s0 + j;
+    v[j] = (s < p.B && pdf < p.P) ? __ldg(yrow0 + (int64_t)s * p.ystride + pdf) : 0.f;
   }
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    if (want_sq) sumsq += (double)v[j] * (double)v[j];
+    tile[j * 33 + lane] = expf(v[j]);  // padded sequences / pdfs: exp(0) = 1, never read back out
+  }
+  __syncwarp();
+#pragma unroll 8
+  for (int k = 0; k < 32; k++) {
+    const int pd = p0 + k;
+    if (pd < p.P) etile[(size_t)pd * BP + s0 + lane] = tile[lane * 33 + k];
+  }
+  __syncwarp();
 }
 
 // Transpose the finished occupancy tile of `frame` out to nnet_output_deriv:
 //   deriv(row, pdf) = scale_gamma * gamma(pdf, seq) + scale_y * y(row, pdf)
 // and reset the tile to zero for reuse two frames later.
-__device__ __forceinline__ void flush_gamma(const DenParams& p, int frame, float* gtile, float* tile, int auxw,
-                                            int lane, bool want_sum, double& gsum) {
+__device__ __forceinline__ void flush_gamma_tile(const DenParams& p, int frame, float* gtile, float* tile, int i,
+                                                 int lane, bool want_sum, double& gsum) {
   const int BP = p.BP;
-  const int nts = BP >> 5, ntp = (p.P + 31) >> 5, ntiles = nts * ntp;
+  const int nts = BP >> 5;
   const int64_t row0 = (int64_t)frame * p.Btot + p.seq0;
-  for (int i = blockIdx.x + gridDim.x * auxw; i < ntiles; i += gridDim.x * kDenAuxWarps) {
-    const int s0 = (i % nts) << 5, p0 = (i / nts) << 5;
-#pragma unroll 8
-    for (int k = 0; k < 32; k++) {
-      const int pd = p0 + k;
-      float g = 0.f;
-      if (pd < p.P) {
-        float* ptr = gtile + (size_t)pd * BP + s0 + lane;
-        g = __ldcg(ptr);
-        *ptr = 0.f;
-      }
-      tile[k * 33 + lane] = g;
+  const int s0 = (i % nts) << 5, p0 = (i / nts) << 5;
+  const int pdf = p0 + lane;
+  float g[32], yv[32];
+#pragma unroll
+  for (int k = 0; k < 32; k++) g[k] = (p0 + k < p.P) ? __ldcg(gtile + (size_t)(p0 + k) * BP + s0 + lane) : 0.f;
+  const bool want_y = p.scale_y != 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j++)
+    yv[j] = (want_y && s0 + j < p.B && pdf < p.P) ? __ldg(p.y + (row0 + s0 + j) * p.ystride + pdf) : 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; k++) {
+    if (p0 + k < p.P) gtile[(size_t)(p0 + k) * BP + s0 + lane] = 0.f;
+    tile[k * 33 + lane] = g[k];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    const int s = s0 + j;
+    if (s < p.B && pdf < p.P) {
+      const float gg = tile[lane * 33 + j];
+      __stcs(p.deriv + (row0 + s) * p.dstride + pdf, fmaf(p.scale_y, yv[j], p.scale_gamma * gg));
+      if (want_sum) gsum += (double)gg;
     }
-    __syncwarp();
-    const int pdf = p0 + lane;
-#pragma unroll 8
-    for (int j = 0; j < 32; j++) {
-      const int s = s0 + j;
-      if (s < p.B && pdf < p.P) {
-        const float g = tile[lane * 33 + j];
-        float out = p.scale_gamma * g;
-        if (p.scale_y != 0.f) out = fmaf(p.scale_y, __ldg(p.y + (row0 + s) * p.ystride + pdf), out);
-        __stcs(p.deriv + (row0 + s) * p.dstride + pdf, out);
-        if (want_sum) gsum += (double)g;
-      }
-    }
-    __syncwarp();
+  }
+  __syncwarp();
+}
+
+// One frame's aux work: flush occupancies of `flush_frame` (if >= 0) and stage exp(y) of
+// `stage_frame` (if >= 0), as ONE list of tile jobs dealt round-robin to all aux warps.
+// forceinline on purpose: as a real call (ABI stack frame, by-reference doubles in local
+// memory) the aux warps became the critical path of the backward pass (+25 us/frame).
+__device__ __forceinline__ void aux_work(const DenParams& p, int flush_frame, int stage_frame, float* tile, int auxw,
+                                         int lane, bool want_sq, double& sumsq, bool want_gsum, double& gsum) {
+  const int BP = p.BP;
+  const int ntiles = (BP >> 5) * ((p.P + 31) >> 5);
+  const int nflush = flush_frame >= 0 ? ntiles : 0, nstage = stage_frame >= 0 ? ntiles : 0;
+  for (int j = blockIdx.x + gridDim.x * auxw; j < nflush + nstage; j += gridDim.x * kDenAuxWarps) {
+    if (j < nflush)
+      flush_gamma_tile(p, flush_frame, p.gtile + (size_t)(flush_frame & 1) * p.P * BP, tile, j, lane, want_gsum, gsum);
+    else
+      stage_exp_tile(p, stage_frame, p.etile + (size_t)(stage_frame & 1) * p.P * BP, tile, j - nflush, lane, want_sq,
+                     sumsq);
   }
 }
 
 // ------------------------------------------------- main-warp work: recursions
+// A warp walks its contiguous arc list as ONE stream, kU arcs (2*kU row gathers) per
+// batch; the last arc of every state carries the end-of-state flag (bit 31 of its pdf
+// field), states without arcs get one zero-probability arc.  Measured on B200
+// (profiles/r01_variants.txt): kU = 4 is the sweet spot; deeper prefetch (kU >= 6, or
+// a second register buffer) does not speed the forward pass up and slows the
+// backward pass down, where gathers share the memory pipe with the REDs.
+#ifndef DEN_KU
+#define DEN_KU 4
+#endif
+constexpr int kU = DEN_KU;
+
+template <int V>
+struct GatherBuf {
+  float a[kU][V];  // alpha_{t-1}(src) / beta'_{t+1}(dst)
+  float e[kU][V];  // exp(y)(pdf)
+};
+
 // alpha_t(h,s) = (1/S_{t-1}(s)) * sum_{arcs i->h} (alpha_{t-1}(i,s) + leaky*pi(i)*S_{t-1}(s)) * p * e_{t-1}(pdf,s)
 template <int V>
 __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __restrict__ arcs,
-                                           const int4* __restrict__ tasks, int tb, int te, int t, float* red,
-                                           int warp, int lane) {
+                                           const int4* __restrict__ tasks, int abeg, int aend, int tb, int t,
+                                           float* red, int warp, int lane) {
   const int BP = p.BP;
   const float* __restrict__ alpha_prev = p.alpha + (size_t)(t - 1) * p.N * BP;
   float* __restrict__ alpha_cur = p.alpha + (size_t)t * p.N * BP;
   const float* __restrict__ et = p.etile + (size_t)((t - 1) & 1) * p.P * BP;
   const double* Sprev = p.Ssum + (size_t)(t - 1) * BP;
+  const int4* __restrict__ a = arcs + abeg;
+  const int n = aend - abeg;
   for (int col = lane * V; col < BP; col += 32 * V) {
-    float lamS[V], invS[V], part[V];
+    float lamS[V], invS[V], part[V], acc[V];
+    double Sd[V];
+#pragma unroll
+    for (int v = 0; v < V; v++) Sd[v] = __ldcg(Sprev + col + v);
+    int task = tb;
+    GatherBuf<V> b0;
+    auto load = [&](GatherBuf<V>& buf, int k) {
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        if (k + u < n) {
+          const int4 ar = a[k + u];
+          ld_cg<V>(alpha_prev + ar.x * BP + col, buf.a[u]);
+          ld_cg<V>(et + (ar.y & 0x7fffffff) * BP + col, buf.e[u]);
+        }
+      }
+    };
+    auto consume = [&](GatherBuf<V>& buf, int k) {
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        if (k + u < n) {
+          const int4 ar = a[k + u];
+          const float pr = __int_as_float(ar.z), pi = __int_as_float(ar.w);
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            const float ad = fmaf(pi, lamS[v], buf.a[u][v]);
+            acc[v] = fmaf(ad * pr, buf.e[u][v], acc[v]);
+          }
+          if (ar.y < 0) {  // last arc of this state (warp-uniform branch)
+            const int4 tk = tasks[task++];
+            float out[V];
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+              out[v] = acc[v] * invS[v];
+              part[v] += out[v];
+              acc[v] = 0.f;
+            }
+            st_vec<V>(alpha_cur + tk.x * BP + col, out);
+          }
+        }
+      }
+    };
+    load(b0, 0);  // first gathers are in flight before the normalisers are consumed
 #pragma unroll
     for (int v = 0; v < V; v++) {
-      const float S = (float)__ldcg(Sprev + col + v);
+      const float S = (float)Sd[v];
       lamS[v] = p.leaky * S;
       invS[v] = 1.0f / S;
       part[v] = 0.f;
+      acc[v] = 0.f;
     }
-    for (int task = tb; task < te; task++) {
-      const int4 tk = tasks[task];
-      const int4* __restrict__ a = arcs + tk.y;
-      const int n = tk.z;
-      float acc[V];
-#pragma unroll
-      for (int v = 0; v < V; v++) acc[v] = 0.f;
-#pragma unroll 4
-      for (int k = 0; k < n; k++) {
-        const int4 ar = a[k];
-        float al[V], e[V];
-        ld_cg<V>(alpha_prev + ar.x * BP + col, al);
-        ld_cg<V>(et + ar.y * BP + col, e);
-        const float pr = __int_as_float(ar.z), pi = __int_as_float(ar.w);
-#pragma unroll
-        for (int v = 0; v < V; v++) {
-          const float ad = fmaf(pi, lamS[v], al[v]);
-          acc[v] = fmaf(ad * pr, e[v], acc[v]);
-        }
-      }
-      float out[V];
-#pragma unroll
-      for (int v = 0; v < V; v++) {
-        out[v] = acc[v] * invS[v];
-        part[v] += out[v];
-      }
-      st_vec<V>(alpha_cur + tk.x * BP + col, out);
+    for (int k = 0; k < n;) {
+      consume(b0, k);
+      k += kU;
+      load(b0, k);
     }
 #pragma unroll
     for (int v = 0; v < V; v++) red[warp * BP + col + v] = part[v];
@@ -270,8 +325,8 @@ __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __res
 // gamma_t(pdf,s) += that term * alpha'_t(h,s) / S_t(s)
 template <int V>
 __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __restrict__ arcs,
-                                          const int4* __restrict__ tasks, int tb, int te, int t, float* red,
-                                          int warp, int lane, double& ab) {
+                                          const int4* __restrict__ tasks, int abeg, int aend, int tb, int te, int t,
+                                          float* red, int warp, int lane, double& ab) {
   const int BP = p.BP;
   const float* __restrict__ alpha_t = p.alpha + (size_t)t * p.N * BP;
   const float* __restrict__ beta_next = p.beta + (size_t)((t + 1) & 1) * p.N * BP;
@@ -280,52 +335,89 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
   float* __restrict__ gt = p.gtile + (size_t)(t & 1) * p.P * BP;
   const double* St = p.Ssum + (size_t)t * BP;
   const double* Bn = p.Bsum + (size_t)(t + 1) * BP;
+  const int4* __restrict__ a = arcs + abeg;
+  const int n = aend - abeg;
   for (int col = lane * V; col < BP; col += 32 * V) {
-    float lamS[V], invS[V], bv[V], part[V];
+    float lamS[V], invS[V], bv[V], part[V], X[V], occ[V], aln[V], al0[V];
+    double Sd[V], Bd[V];
 #pragma unroll
     for (int v = 0; v < V; v++) {
-      const float S = (float)__ldcg(St + col + v);
+      Sd[v] = __ldcg(St + col + v);
+      Bd[v] = __ldcg(Bn + col + v);
+      aln[v] = 0.f;
+      al0[v] = 0.f;
+    }
+    int task = tb;
+    float pi_h = 0.f;
+    GatherBuf<V> b0;
+    auto load = [&](GatherBuf<V>& buf, int k) {
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        if (k + u < n) {
+          const int4 ar = a[k + u];
+          ld_cg<V>(beta_next + ar.x * BP + col, buf.a[u]);
+          ld_cg<V>(et + (ar.y & 0x7fffffff) * BP + col, buf.e[u]);
+        }
+      }
+    };
+    auto consume = [&](GatherBuf<V>& buf, int k) {
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        if (k + u < n) {
+          const int4 ar = a[k + u];
+          const float pr = __int_as_float(ar.z);
+          float g[V];
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            const float vf = pr * (buf.a[u][v] + bv[v]) * buf.e[u][v];
+            X[v] += vf;
+            g[v] = vf * occ[v];
+          }
+          if (!(p.debug_flags & 2)) red_add<V>(gt + (ar.y & 0x7fffffff) * BP + col, g);
+          if (ar.y < 0) {  // last arc of this state: finish it, set up the next one
+            const int4 tk = tasks[task];
+            float bd[V];
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+              bd[v] = X[v] * invS[v];
+              part[v] = fmaf(pi_h, bd[v], part[v]);
+              if (t == 0 && col + v < p.B) ab += (double)(occ[v] * (lamS[v] / p.leaky)) * (double)bd[v];
+              X[v] = 0.f;
+            }
+            st_vec<V>(beta_cur + tk.x * BP + col, bd);
+            task++;
+            if (task < te) {
+              pi_h = __int_as_float(tasks[task].w);
+#pragma unroll
+              for (int v = 0; v < V; v++) occ[v] = fmaf(pi_h, lamS[v], aln[v]) * invS[v];
+              if (task + 1 < te) ld_cs<V>(alpha_t + tasks[task + 1].x * BP + col, aln);
+            }
+          }
+        }
+      }
+    };
+    // everything the first arcs need is requested before anything is consumed
+    if (tb < te) {
+      const int4 tk0 = tasks[tb];
+      pi_h = __int_as_float(tk0.w);
+      ld_cs<V>(alpha_t + tk0.x * BP + col, al0);
+    }
+    load(b0, 0);
+    if (tb + 1 < te) ld_cs<V>(alpha_t + tasks[tb + 1].x * BP + col, aln);
+#pragma unroll
+    for (int v = 0; v < V; v++) {
+      const float S = (float)Sd[v];
       lamS[v] = p.leaky * S;
       invS[v] = 1.0f / S;
-      bv[v] = p.leaky * (float)__ldcg(Bn + col + v);
+      bv[v] = p.leaky * (float)Bd[v];
       part[v] = 0.f;
+      X[v] = 0.f;
+      occ[v] = fmaf(pi_h, lamS[v], al0[v]) * invS[v];
     }
-    for (int task = tb; task < te; task++) {
-      const int4 tk = tasks[task];
-      const int4* __restrict__ a = arcs + tk.y;
-      const int n = tk.z;
-      const float pi_h = __int_as_float(tk.w);
-      float al[V], adash[V], occ[V], X[V];
-      ld_cs<V>(alpha_t + tk.x * BP + col, al);
-#pragma unroll
-      for (int v = 0; v < V; v++) {
-        adash[v] = fmaf(pi_h, lamS[v], al[v]);
-        occ[v] = adash[v] * invS[v];
-        X[v] = 0.f;
-      }
-#pragma unroll 4
-      for (int k = 0; k < n; k++) {
-        const int4 ar = a[k];
-        float be[V], e[V], g[V];
-        ld_cg<V>(beta_next + ar.x * BP + col, be);
-        ld_cg<V>(et + ar.y * BP + col, e);
-        const float pr = __int_as_float(ar.z);
-#pragma unroll
-        for (int v = 0; v < V; v++) {
-          const float vf = pr * (be[v] + bv[v]) * e[v];
-          X[v] += vf;
-          g[v] = vf * occ[v];
-        }
-        red_add<V>(gt + ar.y * BP + col, g);
-      }
-      float bd[V];
-#pragma unroll
-      for (int v = 0; v < V; v++) {
-        bd[v] = X[v] * invS[v];
-        part[v] = fmaf(pi_h, bd[v], part[v]);
-        if (t == 0 && col + v < p.B) ab += (double)adash[v] * (double)bd[v];
-      }
-      st_vec<V>(beta_cur + tk.x * BP + col, bd);
+    for (int k = 0; k < n;) {
+      consume(b0, k);
+      k += kU;
+      load(b0, k);
     }
 #pragma unroll
     for (int v = 0; v < V; v++) red[warp * BP + col + v] = part[v];
@@ -334,15 +426,16 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
 
 template <bool STAGED>
 __device__ __forceinline__ void load_dir(const DenParams& p, int d, const Smem& sm, const int4*& arcs,
-                                         const int4*& tasks, int& tb, int& te, int warp) {
+                                         const int4*& tasks, int& tb, int& te, int& abeg, int& aend, int warp) {
   const DenDir& D = p.dir[d];
   const int task0 = D.cta_task_off[blockIdx.x], ntask = D.cta_task_off[blockIdx.x + 1] - task0;
   const int arc0 = D.cta_arc_off[blockIdx.x], narc = D.cta_arc_off[blockIdx.x + 1] - arc0;
-  tb = 0;
-  te = 0;
+  tb = te = abeg = aend = 0;
   if (warp < kDenMainWarps) {
     tb = D.warp_task_off[blockIdx.x * kDenMainWarps + warp] - task0;
     te = D.warp_task_off[blockIdx.x * kDenMainWarps + warp + 1] - task0;
+    abeg = D.warp_arc_off[blockIdx.x * kDenMainWarps + warp] - arc0;
+    aend = D.warp_arc_off[blockIdx.x * kDenMainWarps + warp + 1] - arc0;
   }
   if constexpr (STAGED) {
     for (int i = threadIdx.x; i < ntask; i += kDenThreads) sm.tasks[i] = D.tasks[task0 + i];
@@ -371,12 +464,22 @@ __global__ void __launch_bounds__(kDenThreads, 1) den_chain_kernel(const __grid_
 
   const int4* arcs;
   const int4* tasks;
-  int tb, te;
-  load_dir<STAGED>(p, 0, sm, arcs, tasks, tb, te, warp);
+  int tb, te, abeg, aend;
+  unsigned long long* tl = (p.timeline && blockIdx.x == 0 && threadIdx.x == 0) ? p.timeline : nullptr;
+  int tli = 0;
+  auto stamp = [&]() {
+    if (tl) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      tl[tli++] = ns;
+    }
+  };
+  stamp();
+  load_dir<STAGED>(p, 0, sm, arcs, tasks, tb, te, abeg, aend, warp);
 
   // ---- prologue: alpha_0 = pi, S_0; stage exp(y_0)
   if (is_aux) {
-    stage_exp(p, 0, p.etile, tile, auxw, lane, true, sumsq);
+    aux_work(p, -1, 0, tile, auxw, lane, true, sumsq, false, gsum);
   } else {
     for (int col = lane * V; col < BP; col += 32 * V) {
       float part = 0.f;
@@ -395,20 +498,22 @@ __global__ void __launch_bounds__(kDenThreads, 1) den_chain_kernel(const __grid_
   }
   cta_reduce_to(sm.red, BP, p.Ssum);
   grid_barrier(p.barrier, epoch);
+  stamp();
 
   // ---- forward
   for (int t = 1; t <= T; t++) {
     if (is_aux) {
-      if (t < T) stage_exp(p, t, p.etile + (size_t)(t & 1) * p.P * BP, tile, auxw, lane, true, sumsq);
+      if (t < T) aux_work(p, -1, t, tile, auxw, lane, true, sumsq, false, gsum);
     } else {
-      alpha_step<V>(p, arcs, tasks, tb, te, t, sm.red, warp, lane);
+      alpha_step<V>(p, arcs, tasks, abeg, aend, tb, t, sm.red, warp, lane);
     }
     cta_reduce_to(sm.red, BP, p.Ssum + (size_t)t * BP);
     grid_barrier(p.barrier, epoch);
+    stamp();
   }
 
   // ---- backward prologue: beta'_T(h,s) = 1 / sum_h alpha'_T(h,s) = 1 / (S_T (1 + leaky*sum_pi))
-  load_dir<STAGED>(p, 1, sm, arcs, tasks, tb, te, warp);
+  load_dir<STAGED>(p, 1, sm, arcs, tasks, tb, te, abeg, aend, warp);
   if (is_aux) {
     sumsq = warp_sum(sumsq);
     if (lane == 0 && sumsq != 0.0) atomicAdd(p.scalars + 3, sumsq);
@@ -436,22 +541,23 @@ __global__ void __launch_bounds__(kDenThreads, 1) den_chain_kernel(const __grid_
   }
   cta_reduce_to(sm.red, BP, p.Bsum + (size_t)T * BP);
   grid_barrier(p.barrier, epoch);
+  stamp();
 
   // ---- backward
   for (int t = T - 1; t >= 0; t--) {
     if (is_aux) {
-      if (t + 1 < T) flush_gamma(p, t + 1, p.gtile + (size_t)((t + 1) & 1) * p.P * BP, tile, auxw, lane, false, gsum);
-      if (t > 0) stage_exp(p, t - 1, p.etile + (size_t)((t - 1) & 1) * p.P * BP, tile, auxw, lane, false, sumsq);
+      if (!(p.debug_flags & 1)) aux_work(p, t + 1 < T ? t + 1 : -1, t - 1, tile, auxw, lane, false, sumsq, false, gsum);
     } else {
-      beta_step<V>(p, arcs, tasks, tb, te, t, sm.red, warp, lane, ab);
+      beta_step<V>(p, arcs, tasks, abeg, aend, tb, te, t, sm.red, warp, lane, ab);
     }
     cta_reduce_to(sm.red, BP, p.Bsum + (size_t)t * BP);
     grid_barrier(p.barrier, epoch);
+    stamp();
   }
 
   // ---- epilogue: frame 0's derivative rows, sanity sums, total log-likelihood
   if (is_aux) {
-    flush_gamma(p, 0, p.gtile, tile, auxw, lane, true, gsum);
+    aux_work(p, 0, -1, tile, auxw, lane, false, sumsq, true, gsum);
     gsum = warp_sum(gsum);
     if (lane == 0 && gsum != 0.0) atomicAdd(p.scalars + 1, gsum);
   } else {
@@ -472,6 +578,8 @@ __global__ void __launch_bounds__(kDenThreads, 1) den_chain_kernel(const __grid_
     acc = warp_sum(acc);
     if (lane == 0) atomicAdd(p.scalars + 2, acc);
   }
+  __syncthreads();
+  stamp();
 }
 
 template <int V, bool STAGED>
