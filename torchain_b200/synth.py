@@ -196,6 +196,52 @@ def make_supervision(seed, den, num_sequences, frames_per_sequence, num_paths=4,
                   np.asarray(arc_cost, dtype=np.float32)[o], final_cost)
 
 
+def append_supervisions(sups):
+    """Kaldi AppendSupervision/MergeChainExamples on per-sequence (or multi-sequence)
+    supervisions: fst::Concat + RmEpsilon.  The final states of part k get copies of the
+    start arcs of part k+1 with cost final(f) (x) arc cost; part k+1's start state vanishes."""
+    assert len(sups) >= 1
+    T, P, w = sups[0].frames_per_sequence, sups[0].label_dim, sups[0].weight
+    src, dst, lab, cost = [], [], [], []
+    offset = 0           # merged id of the current part's state 0 (only part 0 keeps it)
+    prev_finals = None   # [(merged id, final cost)]
+    n_states = 0
+    for k, sp in enumerate(sups):
+        assert sp.frames_per_sequence == T and sp.label_dim == P
+        S = sp.num_states
+        # part k's state i>0 maps to base + i; its state 0 maps to merged 0 (k == 0) or disappears
+        base = n_states if k == 0 else n_states - 1
+        for st in range(S):
+            for a in range(sp.arc_begin[st], sp.arc_begin[st + 1]):
+                d = base + int(sp.arc_dst[a])
+                if st == 0 and k > 0:
+                    for f, fc in prev_finals:
+                        src.append(f); dst.append(d); lab.append(int(sp.arc_label[a]))
+                        cost.append(float(sp.arc_cost[a]) + fc)
+                else:
+                    src.append(base + st); dst.append(d); lab.append(int(sp.arc_label[a]))
+                    cost.append(float(sp.arc_cost[a]))
+        prev_finals = [(base + st, float(sp.final_cost[st])) for st in range(S) if np.isfinite(sp.final_cost[st])]
+        n_states = base + S
+    final_cost = np.full(n_states, np.inf, dtype=np.float32)
+    for f, fc in prev_finals:
+        final_cost[f] = fc
+    src = np.asarray(src, dtype=np.int64)
+    o = np.argsort(src, kind="stable")
+    arc_begin = np.zeros(n_states + 1, dtype=np.int64)
+    np.cumsum(np.bincount(src, minlength=n_states), out=arc_begin[1:])
+    B = sum(sp.num_sequences for sp in sups)
+    return SupFst(float(w), B, T, P, arc_begin.astype(np.int32), np.asarray(dst, dtype=np.int32)[o],
+                  np.asarray(lab, dtype=np.int32)[o], np.asarray(cost, dtype=np.float32)[o], final_cost)
+
+
+def interleave_rows(ys, Bs):
+    """Frame-major nnet outputs of consecutive sequence groups -> one frame-major matrix."""
+    T = ys[0].shape[0] // Bs[0]
+    parts = [y.reshape(T, b, -1) for y, b in zip(ys, Bs)]
+    return np.concatenate(parts, axis=1).reshape(T * sum(Bs), -1)
+
+
 def make_nnet_output(seed, num_sequences, frames_per_sequence, num_pdfs, scale=1.0, zero=False):
     """(T*B, P) float32, rows frame-major (row = t*B + b)."""
     rows = int(num_sequences) * int(frames_per_sequence)
