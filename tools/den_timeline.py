@@ -47,18 +47,21 @@ def main():
     lib.torchain_profile_enable(1)
     step()
     torch.cuda.synchronize()
-    n = 2 * T + 4
+    n = 2 * T + 6
     tl = np.zeros(n, dtype=np.int64)
     got = lib.torchain_profile_timeline(g.ptr, tl.ctypes.data_as(ctypes.c_void_p), n)
     lib.torchain_profile_enable(0)
     assert got == n, got
-    dt = np.diff(tl) / 1e3  # us
-    # [start->prologue, T fwd frames, bwd prologue, T bwd frames, epilogue]
-    pro, fwd, bpro, bwd, epi = dt[0], dt[1:1 + T], dt[1 + T], dt[2 + T:2 + 2 * T], dt[2 + 2 * T]
-    print("config %s B=%d T=%d: total %.1f us" % (args.config, B, T, (tl[-1] - tl[0]) / 1e3))
-    print("prologue %.1f us | fwd frames mean %.2f min %.2f max %.2f (sum %.1f) | bwd prologue %.1f |"
+    # forward launch: [start, prologue, T frames, end]; backward launch: [start, prologue, T frames, end]
+    f, b = tl[:T + 3], tl[T + 3:]
+    df, db = np.diff(f) / 1e3, np.diff(b) / 1e3
+    fwd, bwd = df[1:1 + T], db[1:1 + T]
+    print("config %s B=%d T=%d: forward launch %.1f us, gap %.1f us (numerator), backward launch %.1f us, total %.1f us" %
+          (args.config, B, T, (f[-1] - f[0]) / 1e3, (b[0] - f[-1]) / 1e3, (b[-1] - b[0]) / 1e3, (b[-1] - f[0]) / 1e3))
+    print("prologue %.1f us | fwd frames mean %.2f min %.2f max %.2f (sum %.1f) | fwd tail %.1f | bwd prologue %.1f |"
           " bwd frames mean %.2f min %.2f max %.2f (sum %.1f) | epilogue %.1f" %
-          (pro, fwd.mean(), fwd.min(), fwd.max(), fwd.sum(), bpro, bwd.mean(), bwd.min(), bwd.max(), bwd.sum(), epi))
+          (df[0], fwd.mean(), fwd.min(), fwd.max(), fwd.sum(), df[-1], db[0], bwd.mean(), bwd.min(), bwd.max(),
+           bwd.sum(), db[-1]))
     A = den.num_arcs
     print("ideal @14.5 TB/s L2 gather: fwd frame %.2f us (A*B*8 B), bwd frame gathers %.2f us + red A*B*4 B" %
           (A * B * 8 / 14.5e6, A * B * 8 / 14.5e6))

@@ -429,18 +429,18 @@ bool read_fst_file(const char* path, std::vector<int32_t>* src, std::vector<int3
 // ---------------------------------------------------------------------------
 struct SupDevice {
   DevBuf chain_level_off, level_state_off, chain_arc_off, in_off, in_arcs, out_off, out_arcs, final_cost, arc_row,
-      arc_pdf, arc_cost, uniq_row, uniq_pdf, uniq_arc_off, uniq_arcs;
+      arc_pdf, arc_cost, arc_seq, frame_off, frame_arcs;
 };
 
 struct Supervision {
   float weight = 1.f;
   int B = 0, T = 0, P = 0;
   // split representation (host)
-  int num_chains = 0, S = 0, A = 0, num_uniq = 0;
+  int num_chains = 0, S = 0, A = 0;
   std::vector<int> chain_level_off, level_state_off, chain_arc_off, in_off, out_off;
   std::vector<int2> in_arcs, out_arcs;
   std::vector<float> final_cost, arc_cost;
-  std::vector<int> arc_row, arc_pdf, uniq_row, uniq_pdf, uniq_arc_off, uniq_arcs;
+  std::vector<int> arc_row, arc_pdf, arc_seq, frame_off, frame_arcs;  // frame_*: arc ids ordered by frame
   std::mutex mu;
   std::map<int, std::unique_ptr<SupDevice>> dev;
 };
@@ -674,30 +674,18 @@ Supervision* make_supervision(float weight, int32_t B, int32_t T, int32_t label_
       sup->out_arcs[op[arcs[a].src]++] = make_int2(arcs[a].dst, a);
     }
   }
-  // de-duplicate (row, pdf) so the derivative has one writer per element (Kaldi ComputeLookupIndexes)
+  // arcs ordered by frame, for the backward launch's per-frame numerator scatter
   {
-    std::vector<int> order(NA);
-    for (int a = 0; a < NA; a++) order[a] = a;
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-      if (sup->arc_row[x] != sup->arc_row[y]) return sup->arc_row[x] < sup->arc_row[y];
-      return sup->arc_pdf[x] < sup->arc_pdf[y];
-    });
-    sup->uniq_arc_off.assign(1, 0);
-    for (int i = 0; i < NA; i++) {
-      const int a = order[i];
-      if (i == 0 || sup->arc_row[a] != sup->arc_row[order[i - 1]] || sup->arc_pdf[a] != sup->arc_pdf[order[i - 1]]) {
-        if (i > 0) sup->uniq_arc_off.push_back(i);
-        sup->uniq_row.push_back(sup->arc_row[a]);
-        sup->uniq_pdf.push_back(sup->arc_pdf[a]);
-      }
-      sup->uniq_arcs.push_back(a);
+    sup->arc_seq.resize(NA);
+    sup->frame_off.assign(T + 1, 0);
+    for (int a = 0; a < NA; a++) {
+      sup->arc_seq[a] = arc_time[a] / T;
+      sup->frame_off[arc_time[a] % T + 1]++;
     }
-    sup->uniq_arc_off.push_back(NA);
-    sup->num_uniq = (int)sup->uniq_row.size();
-    if (NA == 0) {
-      sup->uniq_arc_off.assign(1, 0);
-      sup->num_uniq = 0;
-    }
+    for (int t = 0; t < T; t++) sup->frame_off[t + 1] += sup->frame_off[t];
+    sup->frame_arcs.resize(NA);
+    std::vector<int> pos(sup->frame_off.begin(), sup->frame_off.end() - 1);
+    for (int a = 0; a < NA; a++) sup->frame_arcs[pos[arc_time[a] % T]++] = a;
   }
   return sup.release();
 }
@@ -751,10 +739,9 @@ int get_sup_device(Supervision* s, int device, SupDevice** out) {
   CUDA_OK(upload(d->arc_row, s->arc_row));
   CUDA_OK(upload(d->arc_pdf, s->arc_pdf));
   CUDA_OK(upload(d->arc_cost, s->arc_cost));
-  CUDA_OK(upload(d->uniq_row, s->uniq_row));
-  CUDA_OK(upload(d->uniq_pdf, s->uniq_pdf));
-  CUDA_OK(upload(d->uniq_arc_off, s->uniq_arc_off));
-  CUDA_OK(upload(d->uniq_arcs, s->uniq_arcs));
+  CUDA_OK(upload(d->arc_seq, s->arc_seq));
+  CUDA_OK(upload(d->frame_off, s->frame_off));
+  CUDA_OK(upload(d->frame_arcs, s->frame_arcs));
   *out = d.get();
   s->dev[device] = std::move(d);
   return 1;
@@ -804,11 +791,20 @@ int pad_batch(int b) {
   return (b + 127) / 128 * 128;
 }
 
-// The whole loss, enqueued on `stream`.  results_host may be null (no sync).
+// Optional chunked arrival of nnet_output (host-buffer entry): flags[k] != 0 once the rows of
+// frames [k*chunk_frames, (k+1)*chunk_frames) have landed in device memory.
+struct ChunkedInput {
+  const unsigned* flags = nullptr;
+  int chunk_frames = 0;
+  cudaEvent_t all_landed = nullptr;  // recorded on the copy stream after the last chunk
+};
+
+// The whole loss, enqueued on `stream`: forward launch -> numerator -> backward launch ->
+// final scalars.  results_host may be null (then nothing synchronises).
 int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t cols, int64_t ystride,
             float* results_host, float* results_dev_user, float* deriv, int64_t dstride, float* xent,
             int64_t xstride, float l2, float leaky, float xent_regularize, float deriv_scale, int device,
-            cudaStream_t stream) {
+            cudaStream_t stream, ChunkedInput chunked = ChunkedInput()) {
   if (!g || !sup) return fail("null den_graph / supervision handle");
   if (!y) return fail("null nnet_output");
   const int B = sup->B, T = sup->T, P = g->P, N = g->N;
@@ -836,7 +832,7 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
     dstride = cols;
   }
 
-  // ---- numerator on the side stream
+  // ---- numerator scratch
   const size_t nA = (size_t)sup->A, nS = (size_t)sup->S;
   size_t off_arcval = 0, off_la = align_up(off_arcval + 8 * nA, 256), off_lb = align_up(off_la + 8 * nS, 256),
          off_post = align_up(off_lb + 8 * nS, 256), off_clp = align_up(off_post + 4 * nA, 256),
@@ -863,18 +859,14 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   np.log_beta = reinterpret_cast<double*>(nb + off_lb);
   np.arc_post = reinterpret_cast<float*>(nb + off_post);
   np.chain_logprob = reinterpret_cast<double*>(nb + off_clp);
-  CUDA_OK(cudaEventRecord(ws->ev_fork, stream));
-  CUDA_OK(cudaStreamWaitEvent(ws->side, ws->ev_fork, 0));
-  CUDA_OK(tb::launch_numerator(np, ws->side));
-  CUDA_OK(cudaEventRecord(ws->ev_join, ws->side));
 
-  // ---- denominator passes of at most kMaxBP sequences
+  // ---- denominator workspace; passes of at most kMaxBP sequences
   const int maxBP = pad_batch(std::min(B, tb::kMaxBP));
   CUDA_OK(ws->alpha.reserve(sizeof(float) * (size_t)(T + 1) * N * maxBP));
   CUDA_OK(ws->beta.reserve(sizeof(float) * (size_t)2 * N * maxBP));
   const size_t tile_floats = (size_t)2 * P * maxBP;
   CUDA_OK(ws->tiles.reserve(sizeof(float) * tile_floats));  // etile
-  // zeroed block: gtile | Ssum | Bsum | barrier(+pad) ;  scalars + results live after it
+  // zeroed block: gtile | Ssum | Bsum | barriers | timeline ;  scalars + results live after it
   const size_t z_gtile = 0, z_S = align_up(z_gtile + 4 * tile_floats, 256),
                z_B = align_up(z_S + 8 * (size_t)(T + 1) * maxBP, 256),
                z_bar = align_up(z_B + 8 * (size_t)(T + 1) * maxBP, 256),
@@ -915,13 +907,21 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   dp.sum_pi = (float)g->sum_pi;
   dp.scale_gamma = deriv_scale * (-sup->weight);
   dp.scale_y = deriv_scale * (-sup->weight * l2);
+  dp.num_frame_off = sd->frame_off.as<int>();
+  dp.num_frame_arcs = sd->frame_arcs.as<int>();
+  dp.num_arc_pdf = sd->arc_pdf.as<int>();
+  dp.num_arc_seq = sd->arc_seq.as<int>();
+  dp.num_arc_post = np.arc_post;
+  dp.y_ready = chunked.flags;
+  dp.y_chunk_frames = chunked.chunk_frames;
   {
     const char* dbg = getenv("TORCHAIN_DEBUG_FLAGS");
     dp.debug_flags = dbg ? atoi(dbg) : 0;
   }
   dp.timeline = g_profile.load() ? reinterpret_cast<unsigned long long*>(zb + z_tl) : nullptr;
   ws->timeline_dev = zb + z_tl;
-  ws->timeline_len = 2 * T + 4;
+  ws->timeline_len = 2 * T + 6;
+  bool numerator_done = false;
   for (int seq0 = 0; seq0 < B; seq0 += tb::kMaxBP) {
     dp.seq0 = seq0;
     dp.B = std::min(B - seq0, tb::kMaxBP);
@@ -929,24 +929,41 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
     dp.arcs_in_smem = 1;
     if (tb::den_smem_bytes(dp) > 200 * 1024) dp.arcs_in_smem = 0;
     CUDA_OK(cudaMemsetAsync(zb, 0, z_end, stream));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_profile.load()) {
-      cudaEvent_t e0, e1;
       CUDA_OK(cudaEventCreate(&e0));
       CUDA_OK(cudaEventCreate(&e1));
       CUDA_OK(cudaEventRecord(e0, stream));
-      CUDA_OK(tb::launch_den(dp, dd->grid, stream));
+    }
+    if (!numerator_done) {
+      // The numerator runs on a side stream, on the registers the forward launch leaves free.
+      // It needs all of nnet_output: resident from the start in the device entry, after the
+      // last chunk has landed in the host-buffer entry (event recorded on the copy stream).
+      if (chunked.all_landed) {
+        CUDA_OK(cudaStreamWaitEvent(ws->side, chunked.all_landed, 0));
+      } else {
+        CUDA_OK(cudaEventRecord(ws->ev_fork, stream));
+        CUDA_OK(cudaStreamWaitEvent(ws->side, ws->ev_fork, 0));
+      }
+      CUDA_OK(tb::launch_numerator(np, ws->side));
+      CUDA_OK(cudaEventRecord(ws->ev_join, ws->side));
+    }
+    CUDA_OK(tb::launch_den(dp, 0, dd->grid, stream));
+    if (!numerator_done) {
+      CUDA_OK(cudaStreamWaitEvent(stream, ws->ev_join, 0));
+      numerator_done = true;
+    }
+    CUDA_OK(tb::launch_den(dp, 1, dd->grid, stream));
+    if (e0) {
       CUDA_OK(cudaEventRecord(e1, stream));
       std::lock_guard<std::mutex> lock(g->mu);
       ws->prof.emplace_back(e0, e1);
-    } else {
-      CUDA_OK(tb::launch_den(dp, dd->grid, stream));
     }
   }
 
   // ---- final pass
   float* res_dev = reinterpret_cast<float*>(zb + z_res);
   if (want_xent) CUDA_OK(cudaMemset2DAsync(xent, sizeof(float) * xstride, 0, sizeof(float) * cols, rows, stream));
-  CUDA_OK(cudaStreamWaitEvent(stream, ws->ev_join, 0));
   tb::FinalParams fp;
   fp.den_scalars = dp.scalars;
   fp.chain_logprob = np.chain_logprob;
@@ -965,11 +982,9 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   fp.ystride = ystride;
   fp.rows = rows;
   fp.cols = cols;
-  fp.num_uniq = sup->num_uniq;
-  fp.uniq_row = sd->uniq_row.as<int>();
-  fp.uniq_pdf = sd->uniq_pdf.as<int>();
-  fp.uniq_arc_off = sd->uniq_arc_off.as<int>();
-  fp.uniq_arcs = sd->uniq_arcs.as<int>();
+  fp.num_arcs = sup->A;
+  fp.arc_row = sd->arc_row.as<int>();
+  fp.arc_pdf = sd->arc_pdf.as<int>();
   fp.arc_post = np.arc_post;
   CUDA_OK(tb::launch_final(fp, stream));
   if (results_dev_user)
@@ -983,6 +998,16 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   }
   return 1;
 }
+
+// Per-thread resources of the host-buffer entry.
+struct HostPath {
+  int device = -1;
+  cudaStream_t compute = nullptr, copy = nullptr;
+  cudaEvent_t ready = nullptr, landed = nullptr;
+  DevBuf y, deriv, xent, flags;
+  unsigned* one = nullptr;  // pinned constant 1
+};
+thread_local HostPath g_host;
 
 }  // namespace
 
@@ -1082,34 +1107,83 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
   DeviceGuard guard(device);
   if (!guard.ok) return fail("cannot select CUDA device");
   auto* g = static_cast<DenGraph*>(den);
-  // staging buffers live in a workspace keyed by a private stream tag
-  static thread_local cudaStream_t hstream = nullptr;
-  static thread_local int hdev = -1;
-  if (hstream == nullptr || hdev != device) {
-    CUDA_OK(cudaStreamCreateWithFlags(&hstream, cudaStreamNonBlocking));
-    hdev = device;
+  auto* sp = static_cast<Supervision*>(sup);
+  if (rows != (int64_t)sp->B * sp->T) return fail("nnet_output rows != num_sequences * frames_per_sequence");
+  if (cols != g->P) return fail("nnet_output cols != den_graph.NumPdfs()");
+  HostPath& h = g_host;
+  if (h.device != device) {
+    if (h.compute) cudaStreamDestroy(h.compute);
+    if (h.copy) cudaStreamDestroy(h.copy);
+    if (h.ready) cudaEventDestroy(h.ready);
+    if (h.landed) cudaEventDestroy(h.landed);
+    if (h.one) cudaFreeHost(h.one);
+    h = HostPath();
+    CUDA_OK(cudaStreamCreateWithFlags(&h.compute, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&h.copy, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&h.ready, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&h.landed, cudaEventDisableTiming));
+    CUDA_OK(cudaMallocHost(&h.one, sizeof(unsigned)));
+    *h.one = 1u;
+    h.device = device;
   }
-  static thread_local DevBuf dy, dd, dx;
   const size_t bytes = sizeof(float) * (size_t)rows * cols;
-  CUDA_OK(dy.reserve(bytes));
-  CUDA_OK(dd.reserve(bytes));
+  CUDA_OK(h.y.reserve(bytes));
   const bool want_xent = xent_host != nullptr && xent_regularize != 0.f;
-  if (want_xent) CUDA_OK(dx.reserve(bytes));
-  CUDA_OK(cudaMemcpy2DAsync(dy.ptr, sizeof(float) * cols, y_host, sizeof(float) * ystride, sizeof(float) * cols, rows,
-                            cudaMemcpyHostToDevice, hstream));
-  // compute() synchronises hstream once to deliver `results`; the derivative
-  // copies below are ordered after it on the same stream.
-  if (!compute(g, static_cast<Supervision*>(sup), dy.as<float>(), rows, cols, cols, results, nullptr,
-               dd.as<float>(), cols, want_xent ? dx.as<float>() : nullptr, cols, l2, leaky, xent_regularize, 1.0f,
-               device, hstream))
+  if (want_xent) CUDA_OK(h.xent.reserve(bytes));
+
+  // The derivative is written straight into the caller's buffer when that buffer is pinned
+  // (device-mapped under UVA): the backward launch streams its 128-byte row segments over
+  // PCIe while it runs, instead of a separate device-to-host copy afterwards.
+  float* deriv_dev = nullptr;
+  int64_t deriv_dev_stride = cols;
+  bool zero_copy = false;
+  if (deriv_host) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, deriv_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+        attr.devicePointer != nullptr) {
+      deriv_dev = static_cast<float*>(attr.devicePointer);
+      deriv_dev_stride = dstride;
+      zero_copy = true;
+    } else {
+      cudaGetLastError();  // clear the "not registered" error of pageable memory
+      CUDA_OK(h.deriv.reserve(bytes));
+      deriv_dev = h.deriv.as<float>();
+    }
+  }
+
+  // nnet_output goes up in chunks of whole frames; the forward launch starts as soon as the
+  // first chunk has landed and waits (per frame) on the flag of the chunk it needs next.
+  const int T = sp->T, B = sp->B;
+  const int chunk_frames = std::max(1, (T + 7) / 8);
+  const int nchunks = (T + chunk_frames - 1) / chunk_frames;
+  CUDA_OK(h.flags.reserve(sizeof(unsigned) * (size_t)nchunks));
+  CUDA_OK(cudaMemsetAsync(h.flags.ptr, 0, sizeof(unsigned) * nchunks, h.compute));
+  CUDA_OK(cudaEventRecord(h.ready, h.compute));
+  CUDA_OK(cudaStreamWaitEvent(h.copy, h.ready, 0));
+  for (int k = 0; k < nchunks; k++) {
+    const int64_t r0 = (int64_t)k * chunk_frames * B;
+    const int64_t nr = std::min<int64_t>((int64_t)chunk_frames * B, rows - r0);
+    CUDA_OK(cudaMemcpy2DAsync(h.y.as<float>() + r0 * cols, sizeof(float) * cols, y_host + r0 * ystride,
+                              sizeof(float) * ystride, sizeof(float) * cols, nr, cudaMemcpyHostToDevice, h.copy));
+    CUDA_OK(cudaMemcpyAsync(h.flags.as<unsigned>() + k, h.one, sizeof(unsigned), cudaMemcpyHostToDevice, h.copy));
+  }
+  CUDA_OK(cudaEventRecord(h.landed, h.copy));
+  ChunkedInput ci;
+  ci.flags = h.flags.as<unsigned>();
+  ci.chunk_frames = chunk_frames;
+  ci.all_landed = h.landed;
+  // compute() synchronises the compute stream once to deliver `results`
+  if (!compute(g, sp, h.y.as<float>(), rows, cols, cols, results, nullptr, deriv_dev, deriv_dev_stride,
+               want_xent ? h.xent.as<float>() : nullptr, cols, l2, leaky, xent_regularize, 1.0f, device, h.compute,
+               ci))
     return 0;
-  if (deriv_host)
-    CUDA_OK(cudaMemcpy2DAsync(deriv_host, sizeof(float) * dstride, dd.ptr, sizeof(float) * cols, sizeof(float) * cols,
-                              rows, cudaMemcpyDeviceToHost, hstream));
+  if (deriv_host && !zero_copy)
+    CUDA_OK(cudaMemcpy2DAsync(deriv_host, sizeof(float) * dstride, deriv_dev, sizeof(float) * cols,
+                              sizeof(float) * cols, rows, cudaMemcpyDeviceToHost, h.compute));
   if (want_xent)
-    CUDA_OK(cudaMemcpy2DAsync(xent_host, sizeof(float) * xstride, dx.ptr, sizeof(float) * cols, sizeof(float) * cols,
-                              rows, cudaMemcpyDeviceToHost, hstream));
-  CUDA_OK(cudaStreamSynchronize(hstream));
+    CUDA_OK(cudaMemcpy2DAsync(xent_host, sizeof(float) * xstride, h.xent.ptr, sizeof(float) * cols,
+                              sizeof(float) * cols, rows, cudaMemcpyDeviceToHost, h.compute));
+  CUDA_OK(cudaStreamSynchronize(h.compute));
   return 1;
 }
 

@@ -54,19 +54,31 @@ struct DenParams {
   double* Ssum;      // (T+1) x BP       sum_h alpha_t(h,s)      (zero on entry)
   double* Bsum;      // (T+1) x BP       sum_h pi(h) beta'_t(h,s) (zero on entry)
   double* scalars;   // [0] alpha.beta at t=0, [1] sum gamma_0, [2] den logprob, [3] sum y^2  (accumulated)
-  unsigned* barrier; // zero on entry
+  unsigned* barrier; // [2 x 32] one counter per phase (forward / backward launch), zero on entry
   float leaky;
   float sum_pi;
   float scale_gamma;  // deriv_scale * (-supervision.weight)
   float scale_y;      // deriv_scale * (-supervision.weight * l2_regularize)
   int arcs_in_smem;   // 1: arc slices staged in shared memory
+  // numerator occupancies, subtracted from the occupancy tile by the backward launch so that the
+  // flush writes w*gamma_num - w*gamma_den in one go (arcs ordered by frame)
+  const int* num_frame_off;    // [T+1] ranges into num_frame_arcs, or null (no numerator)
+  const int* num_frame_arcs;   // arc ids
+  const int* num_arc_pdf;      // [A]
+  const int* num_arc_seq;      // [A] sequence index in the whole minibatch
+  const float* num_arc_post;   // [A] written by num_fb_kernel
+  // host-buffer entry only: nnet_output arrives in chunks of y_chunk_frames frames; y_ready[k] becomes
+  // non-zero (written by the copy stream) once chunk k has landed.  null = everything is resident.
+  const unsigned* y_ready;
+  int y_chunk_frames;
   int debug_flags;    // timing experiments only (TORCHAIN_DEBUG_FLAGS): 1 = skip aux work in backward, 2 = skip REDs
   unsigned long long* timeline;  // optional: globaltimer at every phase boundary (2T+5 entries), or null
 };
 
 size_t den_smem_bytes(const DenParams& p);
-// Enqueues the persistent kernel with a cooperative launch of `grid` CTAs.
-cudaError_t launch_den(const DenParams& p, int grid, cudaStream_t stream);
+// Enqueues one persistent launch (cooperative, `grid` CTAs): phase 0 = forward (alpha)
+// recurrence over all frames, phase 1 = backward (beta + derivative) recurrence.
+cudaError_t launch_den(const DenParams& p, int phase, int grid, cudaStream_t stream);
 int den_max_grid(int device);  // co-resident CTAs (one per SM)
 
 // ---------------------------------------------------------------------------
@@ -113,12 +125,10 @@ struct FinalParams {
   const float* y;
   int64_t ystride;
   int64_t rows, cols;
-  // numerator posteriors, de-duplicated by (row, pdf)
-  int num_uniq;
-  const int* uniq_row;
-  const int* uniq_pdf;
-  const int* uniq_arc_off;      // [num_uniq+1]
-  const int* uniq_arcs;         // arc ids
+  // numerator occupancies per arc (only needed for the optional xent output)
+  int num_arcs;
+  const int* arc_row;
+  const int* arc_pdf;
   const float* arc_post;
 };
 cudaError_t launch_final(const FinalParams& p, cudaStream_t stream);

@@ -217,8 +217,17 @@ __device__ __forceinline__ void flush_gamma_tile(const DenParams& p, int frame, 
 // forceinline on purpose: as a real call (ABI stack frame, by-reference doubles in local
 // memory) the aux warps became the critical path of the backward pass (+25 us/frame).
 __device__ __forceinline__ void aux_work(const DenParams& p, int flush_frame, int stage_frame, float* tile, int auxw,
-                                         int lane, bool want_sq, double& sumsq, bool want_gsum, double& gsum) {
+                                         int lane, bool want_sq, double& sumsq, bool want_gsum, double& gsum,
+                                         int num_frame = -1) {
   const int BP = p.BP;
+  if (stage_frame >= 0 && p.y_ready != nullptr) {  // host-buffer entry: wait until this frame's chunk has landed
+    if (lane == 0) {
+      const unsigned* flag = p.y_ready + stage_frame / p.y_chunk_frames;
+      while (ld_acquire(flag) == 0u) {
+      }
+    }
+    __syncwarp();
+  }
   const int ntiles = (BP >> 5) * ((p.P + 31) >> 5);
   const int nflush = flush_frame >= 0 ? ntiles : 0, nstage = stage_frame >= 0 ? ntiles : 0;
   for (int j = blockIdx.x + gridDim.x * auxw; j < nflush + nstage; j += gridDim.x * kDenAuxWarps) {
@@ -227,6 +236,21 @@ __device__ __forceinline__ void aux_work(const DenParams& p, int flush_frame, in
     else
       stage_exp_tile(p, stage_frame, p.etile + (size_t)(stage_frame & 1) * p.P * BP, tile, j - nflush, lane, want_sq,
                      sumsq);
+  }
+  if (num_frame >= 0 && p.num_frame_off != nullptr && !(p.debug_flags & 4)) {
+    // subtract the numerator occupancies of `num_frame` from its (already zeroed) tile; the REDs
+    // of the main warps add the denominator occupancies to the same tile during this frame
+    float* gt = p.gtile + (size_t)(num_frame & 1) * p.P * BP;
+    const int a1 = p.num_frame_off[num_frame + 1];
+    for (int j = p.num_frame_off[num_frame] + (blockIdx.x + gridDim.x * auxw) * 32 + lane; j < a1;
+         j += gridDim.x * kDenAuxWarps * 32) {
+      const int a = p.num_frame_arcs[j];
+      const int s = p.num_arc_seq[a] - p.seq0;
+      if (s >= 0 && s < p.B) {
+        const float v[1] = {-p.num_arc_post[a]};
+        red_add<1>(gt + (size_t)p.num_arc_pdf[a] * BP + s, v);
+      }
+    }
   }
 }
 
@@ -450,8 +474,10 @@ __device__ __forceinline__ void load_dir(const DenParams& p, int d, const Smem& 
 }
 
 // ------------------------------------------------------------------ kernel
-template <int V, bool STAGED>
-__global__ void __launch_bounds__(kDenThreads, 1) den_chain_kernel(const __grid_constant__ DenParams p) {
+// PHASE 0: forward launch (prologue + T alpha frames + total log-likelihood).
+// PHASE 1: backward launch (beta prologue + T beta/derivative frames + last flush).
+template <int V, bool STAGED, int PHASE>
+__device__ __forceinline__ void den_chain_body(const DenParams& p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Smem sm = carve(smem_raw, p);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -474,9 +500,12 @@ __global__ void __launch_bounds__(kDenThreads, 1) den_chain_kernel(const __grid_
       tl[tli++] = ns;
     }
   };
+  unsigned* const barrier = p.barrier + 32 * PHASE;
+  if (tl) tl += PHASE * (p.T + 3);
   stamp();
-  load_dir<STAGED>(p, 0, sm, arcs, tasks, tb, te, abeg, aend, warp);
+  load_dir<STAGED>(p, PHASE, sm, arcs, tasks, tb, te, abeg, aend, warp);
 
+  if constexpr (PHASE == 0) {
   // ---- prologue: alpha_0 = pi, S_0; stage exp(y_0)
   if (is_aux) {
     aux_work(p, -1, 0, tile, auxw, lane, true, sumsq, false, gsum);
@@ -497,7 +526,7 @@ __global__ void __launch_bounds__(kDenThreads, 1) den_chain_kernel(const __grid_
     }
   }
   cta_reduce_to(sm.red, BP, p.Ssum);
-  grid_barrier(p.barrier, epoch);
+  grid_barrier(barrier, epoch);
   stamp();
 
   // ---- forward
@@ -508,16 +537,30 @@ __global__ void __launch_bounds__(kDenThreads, 1) den_chain_kernel(const __grid_
       alpha_step<V>(p, arcs, tasks, abeg, aend, tb, t, sm.red, warp, lane);
     }
     cta_reduce_to(sm.red, BP, p.Ssum + (size_t)t * BP);
-    grid_barrier(p.barrier, epoch);
+    grid_barrier(barrier, epoch);
     stamp();
   }
-
-  // ---- backward prologue: beta'_T(h,s) = 1 / sum_h alpha'_T(h,s) = 1 / (S_T (1 + leaky*sum_pi))
-  load_dir<STAGED>(p, 1, sm, arcs, tasks, tb, te, abeg, aend, warp);
   if (is_aux) {
     sumsq = warp_sum(sumsq);
     if (lane == 0 && sumsq != 0.0) atomicAdd(p.scalars + 3, sumsq);
+  }
+  if (blockIdx.x == 0) {
+    // ComputeTotLogLike: sum_s log(sum_h alpha'_T(h,s)) + sum_{t<T} sum_s log S_t(s)
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < (T + 1) * BP; i += kDenThreads) {
+      const int t = i / BP, s = i - t * BP;
+      if (s < p.B) {
+        float S = (float)__ldcg(p.Ssum + i);
+        if (t == T) S = S * (1.0f + p.leaky * p.sum_pi);
+        acc += log((double)S);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) atomicAdd(p.scalars + 2, acc);
+  }
   } else {
+  // ---- backward prologue: beta'_T(h,s) = 1 / sum_h alpha'_T(h,s) = 1 / (S_T (1 + leaky*sum_pi))
+  if (!is_aux) {
     const double* ST = p.Ssum + (size_t)T * BP;
     float* betaT = p.beta + (size_t)(T & 1) * p.N * BP;
     for (int col = lane * V; col < BP; col += 32 * V) {
@@ -540,18 +583,19 @@ __global__ void __launch_bounds__(kDenThreads, 1) den_chain_kernel(const __grid_
     }
   }
   cta_reduce_to(sm.red, BP, p.Bsum + (size_t)T * BP);
-  grid_barrier(p.barrier, epoch);
+  grid_barrier(barrier, epoch);
   stamp();
 
   // ---- backward
   for (int t = T - 1; t >= 0; t--) {
     if (is_aux) {
-      if (!(p.debug_flags & 1)) aux_work(p, t + 1 < T ? t + 1 : -1, t - 1, tile, auxw, lane, false, sumsq, false, gsum);
+      if (!(p.debug_flags & 1))
+        aux_work(p, t + 1 < T ? t + 1 : -1, t - 1, tile, auxw, lane, false, sumsq, false, gsum, t);
     } else {
       beta_step<V>(p, arcs, tasks, abeg, aend, tb, te, t, sm.red, warp, lane, ab);
     }
     cta_reduce_to(sm.red, BP, p.Bsum + (size_t)t * BP);
-    grid_barrier(p.barrier, epoch);
+    grid_barrier(barrier, epoch);
     stamp();
   }
 
@@ -564,33 +608,37 @@ __global__ void __launch_bounds__(kDenThreads, 1) den_chain_kernel(const __grid_
     ab = warp_sum(ab);
     if (lane == 0 && ab != 0.0) atomicAdd(p.scalars + 0, ab);
   }
-  if (blockIdx.x == 0) {
-    // ComputeTotLogLike: sum_s log(sum_h alpha'_T(h,s)) + sum_{t<T} sum_s log S_t(s)
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < (T + 1) * BP; i += kDenThreads) {
-      const int t = i / BP, s = i - t * BP;
-      if (s < p.B) {
-        float S = (float)__ldcg(p.Ssum + i);
-        if (t == T) S = S * (1.0f + p.leaky * p.sum_pi);
-        acc += log((double)S);
-      }
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) atomicAdd(p.scalars + 2, acc);
-  }
+  }  // PHASE
   __syncthreads();
   stamp();
 }
 
+// The forward launch is capped at 112 registers/thread so that 8 K registers per SM stay free:
+// the numerator kernel (128 threads x 48 registers per CTA) can then run on the same SMs while
+// the forward recurrence is in flight.  The backward launch takes the whole register file.
 template <int V, bool STAGED>
+__global__ void __maxnreg__(112) den_forward_kernel(const __grid_constant__ DenParams p) {
+  den_chain_body<V, STAGED, 0>(p);
+}
+template <int V, bool STAGED>
+__global__ void __launch_bounds__(kDenThreads, 1) den_backward_kernel(const __grid_constant__ DenParams p) {
+  den_chain_body<V, STAGED, 1>(p);
+}
+
+template <int V, bool STAGED, int PHASE>
 cudaError_t launch_t(const DenParams& p, int grid, size_t smem, cudaStream_t stream) {
-  auto kern = den_chain_kernel<V, STAGED>;
+  void (*kern)(DenParams) = PHASE == 0 ? den_forward_kernel<V, STAGED> : den_backward_kernel<V, STAGED>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   void* args[] = {const_cast<DenParams*>(&p)};
   e = cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(kDenThreads), args, smem, stream);
   if (e == cudaSuccess) count_launch();
   return e;
+}
+
+template <int V, bool STAGED>
+cudaError_t launch_p(const DenParams& p, int phase, int grid, size_t smem, cudaStream_t stream) {
+  return phase == 0 ? launch_t<V, STAGED, 0>(p, grid, smem, stream) : launch_t<V, STAGED, 1>(p, grid, smem, stream);
 }
 
 }  // namespace
@@ -612,17 +660,17 @@ int den_max_grid(int device) {
   return sms;
 }
 
-cudaError_t launch_den(const DenParams& p, int grid, cudaStream_t stream) {
+cudaError_t launch_den(const DenParams& p, int phase, int grid, cudaStream_t stream) {
   const size_t smem = den_smem_bytes(p);
   const int vec = p.BP >= 128 ? 4 : (p.BP >= 64 ? 2 : 1);
   if (p.arcs_in_smem) {
-    if (vec == 4) return launch_t<4, true>(p, grid, smem, stream);
-    if (vec == 2) return launch_t<2, true>(p, grid, smem, stream);
-    return launch_t<1, true>(p, grid, smem, stream);
+    if (vec == 4) return launch_p<4, true>(p, phase, grid, smem, stream);
+    if (vec == 2) return launch_p<2, true>(p, phase, grid, smem, stream);
+    return launch_p<1, true>(p, phase, grid, smem, stream);
   }
-  if (vec == 4) return launch_t<4, false>(p, grid, smem, stream);
-  if (vec == 2) return launch_t<2, false>(p, grid, smem, stream);
-  return launch_t<1, false>(p, grid, smem, stream);
+  if (vec == 4) return launch_p<4, false>(p, phase, grid, smem, stream);
+  if (vec == 2) return launch_p<2, false>(p, phase, grid, smem, stream);
+  return launch_p<1, false>(p, phase, grid, smem, stream);
 }
 
 }  // namespace tb
