@@ -41,6 +41,24 @@ def peaks():
     return 6650.0, "fallback"
 
 
+def host_cores():
+    """Host threads usable by the CPU baseline (torchrun pins OMP_NUM_THREADS=1, so ask the OS)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch pair of the denominator kernels from the
+    committed `ncu --set full` capture (profiles/ncu_den_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_den_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -122,7 +140,7 @@ def cpu_baseline(c, seconds_budget=20.0, threads=None):
     import oracle_lib as ol
     from torchain_b200 import synth
     den = c["den"]
-    ncores = threads or ol.load().oracle_max_threads()
+    ncores = threads or host_cores()
     oden = ol.OracleDen(den)
     T = c["T"]
     Bs = min(c["B"], max(8, 2 * ncores))
@@ -150,7 +168,7 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as ol
     from torchain_b200 import synth
-    ncores = ol.load().oracle_max_threads()
+    ncores = host_cores()
     oden = ol.OracleDen(c["den"])
     Bs = min(c["B"], max(8, 2 * ncores))
     T = c["T"]
@@ -297,9 +315,10 @@ def run_b200(args):
     frac_hbm = hbm_gbs / hbm_peak
     frac_l2 = gather_gbs / l2_peak if l2_peak > 0 else None
     roofline = {
-        "bound": "hbm", "kernel": "den_chain_kernel", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": "den_forward_kernel + den_backward_kernel (one launch pair per step)", "achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
         "frac": max(frac_hbm, frac_l2 or 0.0), "frac_hbm": frac_hbm, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
-        "traffic": None,
+        "traffic": (measured_traffic() or {}).get("dram_bytes_per_step") if args.config == "chime5" and not args.batch else None,
+        "traffic_source": (measured_traffic() or {}).get("source"),
         "alg_bytes_per_launch": hbm_alg * B * T, "launch_ms": den_launch_ms, "launches_timed": int(den_n.value),
         "gather": {"achieved": gather_gbs, "peak": l2_peak, "unit": "GB/s", "frac": frac_l2,
                    "alg_bytes_per_launch": gather_alg * B * T,

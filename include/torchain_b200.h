@@ -178,6 +178,12 @@ int torchain_profile_read(void* den_graph_ptr, double* den_kernel_ms, int64_t* d
  * prologue, T backward frames, end].  Copies up to max_entries; returns the count. */
 int torchain_profile_timeline(void* den_graph_ptr, int64_t* out_ns, int max_entries);
 
+/* torchain_profile_enable(2) additionally records, for every CTA and frame of the last
+ * forward/backward launch pair, %globaltimer when main warp 0 finished its arcs, when aux
+ * warp 0 finished, when the CTA passed its block reduction, and when it left the grid barrier.
+ * Layout [2][frames][grid][4] int64 ns; returns the entry count (call with out_ns = NULL to size). */
+int64_t torchain_profile_cta_trace(void* den_graph_ptr, int64_t* out_ns, int64_t max_entries, int* frames, int* grid);
+
 /* L2-resident random 512-byte-row gather: the measured denominator of the
  * gather roofline.  Returns achieved GB/s, <0 on error. */
 double torchain_microbench_l2_gather(int device, int64_t table_bytes, int row_bytes, int iters);

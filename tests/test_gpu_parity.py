@@ -209,3 +209,82 @@ def test_large_config_properties():
     res2, d2, _ = run_abi(g2, s2, y.cpu().numpy(), 0.0, 0.1)
     assert res2[0] == pytest.approx(0.5 * res[0], rel=1e-5)
     assert deriv_err(d2, 0.5 * d64) < DERIV_RTOL
+
+
+def test_gpu_single_frame_and_single_sequence():
+    """T = 1 (the reference's own test skips it, chain-supervision-test.hpp:243) and B = 1."""
+    for (B, T) in [(1, 1), (3, 1), (1, 5)]:
+        den = synth.make_den_fst(50 + B + T, 30, 9, mean_deg=2.0)
+        sup = synth.make_supervision(60, den, B, T, num_paths=2)
+        y = synth.make_nnet_output(61, B, T, 9)
+        r = ol.chain(ol.OracleDen(den), ol.OracleSup(sup), y, l2=0.01, leaky=0.1, mode="fp64")
+        g, s = handles(den, sup)
+        res, d, _ = run_abi(g, s, y, 0.01, 0.1)
+        assert rel(res[0], r["objf"]) < OBJF_RTOL
+        assert deriv_err(d, r["deriv"]) < DERIV_RTOL
+
+
+def test_gpu_states_without_in_or_out_arcs():
+    """Hand-built graph: state 3 has no in-arcs, state 4 has no out-arcs (only a final weight)."""
+    src = np.array([0, 0, 1, 1, 2, 2, 3, 0], dtype=np.int32)
+    dst = np.array([0, 1, 2, 0, 0, 4, 1, 2], dtype=np.int32)
+    ilabel = np.array([1, 2, 3, 1, 2, 4, 3, 4], dtype=np.int32)
+    prob = np.array([0.3, 0.3, 0.5, 0.4, 0.6, 0.3, 0.9, 0.3])
+    den = synth.DenFst(5, 4, 0, src, dst, ilabel, (-np.log(prob)).astype(np.float32),
+                       np.array([np.inf, 2.3, 2.3, 2.3, 0.1], dtype=np.float32))
+    B, T = 4, 6
+    # supervision: every sequence follows 0 -> 1 -> 2 -> 0 -> ... (labels 2, 3, 2) with unit costs
+    labels = [2, 3, 2]
+    arc_begin, arc_dst, arc_label, arc_cost = [0], [], [], []
+    for i in range(B * T):
+        arc_dst.append(i + 1)
+        arc_label.append(labels[(i % T) % 3])
+        arc_cost.append(0.25)
+        arc_begin.append(i + 1)
+    arc_begin.append(B * T)
+    final = np.full(B * T + 1, np.inf, dtype=np.float32)
+    final[-1] = 0.0
+    sup = synth.SupFst(1.0, B, T, 4, np.array(arc_begin, dtype=np.int32), np.array(arc_dst, dtype=np.int32),
+                       np.array(arc_label, dtype=np.int32), np.array(arc_cost, dtype=np.float32), final)
+    y = synth.make_nnet_output(5, B, T, 4)
+    r = ol.chain(ol.OracleDen(den), ol.OracleSup(sup), y, l2=0.0, leaky=0.05, mode="fp64")
+    g, s = handles(den, sup)
+    assert s.num_chains == B
+    res, d, _ = run_abi(g, s, y, 0.0, 0.05)
+    assert rel(res[0], r["objf"]) < OBJF_RTOL
+    assert deriv_err(d, r["deriv"]) < DERIV_RTOL
+
+
+def test_python_chain_loss_not_kaldi_way():
+    """kaldi_way=False (reference functions.py:96-103): the loss runs a second time on xent_input and
+    overwrites BOTH results and the LF-MMI gradient buffer."""
+    import torch
+    from torchain_b200.functions import chain_loss
+    c = synth.small_case(11)
+    B, T, P = c["B"], c["T"], c["P"]
+    g, s = handles(c["den"], c["sup"])
+    y = torch.from_numpy(c["y"]).cuda().requires_grad_(True)
+    x_np = synth.make_nnet_output(99, B, T, P)
+    x = torch.from_numpy(x_np).cuda().requires_grad_(True)
+    r = ol.chain(ol.OracleDen(c["den"]), ol.OracleSup(c["sup"]), x_np, l2=0.0, leaky=0.1, mode="fp64", want_xent=True)
+    loss, results = chain_loss(y, g, s, leaky_hmm_coefficient=0.1, xent_regularize=0.25, xent_input=x, kaldi_way=False)
+    loss.backward()
+    assert float(results.data[0]) == pytest.approx(r["objf"], rel=1e-5)        # results of the SECOND call
+    assert deriv_err(y.grad.cpu().numpy(), -r["deriv"]) < DERIV_RTOL             # mmi grad overwritten too
+    assert deriv_err(x.grad.cpu().numpy(), -0.25 * r["xent"]) < DERIV_RTOL
+
+
+def test_large_tree_config_properties():
+    """BASELINE.json cfg 4 (P=6000, N=20000, A~600k, B=256) at full size: size-independent properties."""
+    import torch
+    c = synth.make_config("large_tree", with_y=False, T=10)
+    g, s = handles(c["den"], c["sup"])
+    B, T, P = c["B"], c["T"], c["P"]
+    y = torch.randn(T * B, P, device="cuda", generator=torch.Generator(device="cuda").manual_seed(7)) * 2.0
+    res, d, x = run_abi(g, s, y.cpu().numpy(), 0.0, 0.1, xent=0.1, want_xent=True)
+    d64, x64 = d.astype(np.float64), x.astype(np.float64)
+    assert res[0] <= 0.0 and res[2] == B * T
+    assert np.abs(d64.sum(axis=1)).max() < 1e-3
+    assert np.abs(x64.sum(axis=1) - 1.0).max() < 1e-4
+    den_post = x64 - d64
+    assert den_post.min() > -1e-5 and abs(den_post.sum() - B * T) < 1e-4 * B * T

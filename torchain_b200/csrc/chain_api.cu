@@ -106,14 +106,28 @@ struct DirHost {  // one direction, partitioned
   int max_arcs_cta = 0, max_tasks_cta = 0;
 };
 
-struct DenDevice {  // per (device) copy
-  int grid = 0;
+struct DenPartition {  // one uploaded partition of both directions
   DevBuf arcs[2], tasks[2], cta_arc_off[2], cta_task_off[2], warp_task_off[2], warp_arc_off[2];
   int max_arcs_cta[2] = {0, 0}, max_tasks_cta[2] = {0, 0};
+  std::vector<double> work[2];  // [grid*kDenMainWarps] cost units assigned to each warp
 };
 
+struct DenDevice {  // per (device) state
+  int grid = 0;
+  // Partitions are never freed or overwritten while the handle lives: launches already
+  // enqueued on other streams keep reading the generation they were given.
+  std::vector<std::unique_ptr<DenPartition>> generations;
+  DenPartition* cur = nullptr;
+  // measured relative speed of every (CTA, main warp) bin per direction; 1.0 until calibrated
+  std::vector<double> speed[2];
+  int calib_rounds_done = 0;
+  DevBuf warp_busy;  // [2][grid][kDenWarps] cycles, written by the last launch pair
+};
+constexpr int kCalibRounds = 3;
+
 struct Workspace {
-  DevBuf alpha, beta, tiles, zeroed, num_scratch, scratch_deriv;
+  DevBuf alpha, beta, tiles, zeroed, num_scratch, scratch_deriv, cta_trace;
+  int trace_frames = 0, trace_grid = 0;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float* pinned = nullptr;  // 4 floats
@@ -143,27 +157,35 @@ struct DenGraph {
   std::map<std::pair<int, void*>, std::unique_ptr<Workspace>> ws;
 };
 
-// Longest-processing-time-first assignment of weighted items to `bins` bins.
-void lpt(const std::vector<int>& items, const std::vector<int>& cost, int bins, std::vector<std::vector<int>>* out) {
+// Longest-processing-time-first assignment of weighted items to bins of different speeds:
+// each item (heaviest first) goes to the bin that would finish it earliest.
+void lpt(const std::vector<int>& items, const std::vector<int>& cost, const std::vector<double>& speed,
+         std::vector<std::vector<int>>* out) {
+  const int bins = (int)speed.size();
   out->assign(bins, {});
   std::vector<int> order(items);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
-  typedef std::pair<long long, int> Load;  // (load, bin)
-  std::priority_queue<Load, std::vector<Load>, std::greater<Load>> heap;
-  for (int b = 0; b < bins; b++) heap.push({0, b});
+  std::vector<double> load(bins, 0.0);
   for (int it : order) {
-    Load l = heap.top();
-    heap.pop();
-    (*out)[l.second].push_back(it);
-    l.first += cost[it];
-    heap.push(l);
+    int best = 0;
+    double best_t = 1e300;
+    for (int b = 0; b < bins; b++) {
+      const double t = (load[b] + cost[it]) / speed[b];
+      if (t < best_t) {
+        best_t = t;
+        best = b;
+      }
+    }
+    (*out)[best].push_back(it);
+    load[best] += cost[it];
   }
 }
 
 // Partition one direction over grid CTAs x kDenMainWarps warps.
 //   dir 0: tasks = destination states with their in-arcs (other = source)
 //   dir 1: tasks = source states with their out-arcs     (other = destination)
-void build_dir(const DenGraph& g, int dir, int grid, DirHost* out) {
+void build_dir(const DenGraph& g, int dir, int grid, const std::vector<double>& speed /* [grid*kDenMainWarps] */,
+               DirHost* out, std::vector<double>* work) {
   const int N = g.N, A = g.A;
   std::vector<int> deg(N, 0), begin(N + 1, 0);
   const std::vector<int>& key = dir == 0 ? g.dst : g.src;
@@ -180,7 +202,11 @@ void build_dir(const DenGraph& g, int dir, int grid, DirHost* out) {
     all[s] = s;
   }
   std::vector<std::vector<int>> by_cta;
-  lpt(all, cost, grid, &by_cta);
+  std::vector<double> cta_speed(grid, 0.0);
+  for (int c = 0; c < grid; c++)
+    for (int w = 0; w < tb::kDenMainWarps; w++) cta_speed[c] += speed[c * tb::kDenMainWarps + w];
+  lpt(all, cost, cta_speed, &by_cta);
+  work->assign((size_t)grid * tb::kDenMainWarps, 0.0);
 
   out->arcs.clear();
   out->tasks.clear();
@@ -191,10 +217,13 @@ void build_dir(const DenGraph& g, int dir, int grid, DirHost* out) {
   out->max_arcs_cta = out->max_tasks_cta = 0;
   for (int c = 0; c < grid; c++) {
     std::vector<std::vector<int>> by_warp;
-    lpt(by_cta[c], cost, tb::kDenMainWarps, &by_warp);
+    lpt(by_cta[c], cost,
+        std::vector<double>(speed.begin() + c * tb::kDenMainWarps, speed.begin() + (c + 1) * tb::kDenMainWarps),
+        &by_warp);
     const int arc0 = (int)out->arcs.size(), task0 = (int)out->tasks.size();
     for (int w = 0; w < tb::kDenMainWarps; w++) {
       for (int s : by_warp[w]) {
+        (*work)[c * tb::kDenMainWarps + w] += cost[s];
         int4 tk;
         tk.x = s;
         tk.y = (int)out->arcs.size() - arc0;
@@ -693,6 +722,26 @@ Supervision* make_supervision(float weight, int32_t B, int32_t T, int32_t label_
 // ---------------------------------------------------------------------------
 // per-device preparation
 // ---------------------------------------------------------------------------
+// Build + upload one partition generation from the device's current speed estimates.
+int build_partition(DenGraph* g, DenDevice* d) {
+  auto part = std::make_unique<DenPartition>();
+  for (int dir = 0; dir < 2; dir++) {
+    DirHost h;
+    build_dir(*g, dir, d->grid, d->speed[dir], &h, &part->work[dir]);
+    CUDA_OK(upload(part->arcs[dir], h.arcs));
+    CUDA_OK(upload(part->tasks[dir], h.tasks));
+    CUDA_OK(upload(part->cta_arc_off[dir], h.cta_arc_off));
+    CUDA_OK(upload(part->cta_task_off[dir], h.cta_task_off));
+    CUDA_OK(upload(part->warp_task_off[dir], h.warp_task_off));
+    CUDA_OK(upload(part->warp_arc_off[dir], h.warp_arc_off));
+    part->max_arcs_cta[dir] = h.max_arcs_cta;
+    part->max_tasks_cta[dir] = h.max_tasks_cta;
+  }
+  d->cur = part.get();
+  d->generations.push_back(std::move(part));
+  return 1;
+}
+
 int get_den_device(DenGraph* g, int device, DenDevice** out) {
   std::lock_guard<std::mutex> lock(g->mu);
   auto it = g->dev.find(device);
@@ -703,21 +752,57 @@ int get_den_device(DenGraph* g, int device, DenDevice** out) {
   auto d = std::make_unique<DenDevice>();
   d->grid = tb::den_max_grid(device);
   if (d->grid <= 0) return fail("cannot query SM count");
-  for (int dir = 0; dir < 2; dir++) {
-    DirHost h;
-    build_dir(*g, dir, d->grid, &h);
-    CUDA_OK(upload(d->arcs[dir], h.arcs));
-    CUDA_OK(upload(d->tasks[dir], h.tasks));
-    CUDA_OK(upload(d->cta_arc_off[dir], h.cta_arc_off));
-    CUDA_OK(upload(d->cta_task_off[dir], h.cta_task_off));
-    CUDA_OK(upload(d->warp_task_off[dir], h.warp_task_off));
-    CUDA_OK(upload(d->warp_arc_off[dir], h.warp_arc_off));
-    d->max_arcs_cta[dir] = h.max_arcs_cta;
-    d->max_tasks_cta[dir] = h.max_tasks_cta;
-  }
+  for (int dir = 0; dir < 2; dir++) d->speed[dir].assign((size_t)d->grid * tb::kDenMainWarps, 1.0);
+  CUDA_OK(d->warp_busy.reserve(sizeof(unsigned long long) * 2 * (size_t)d->grid * tb::kDenWarps));
+  if (getenv("TORCHAIN_NO_AUTOTUNE")) d->calib_rounds_done = kCalibRounds;
+  if (!build_partition(g, d.get())) return 0;
   *out = d.get();
   g->dev[device] = std::move(d);
   return 1;
+}
+
+// Partition autotuner.  The grid barrier makes every frame as slow as its slowest warp, and
+// warps do not run at the same speed: SMs differ in their distance to the L2 slices and the
+// warps of an SM share schedulers unevenly with the aux warps.  These differences are stable
+// from frame to frame and call to call (profiles/r01_summary.md), so after each of the first
+// kCalibRounds synchronised calls the measured per-warp busy cycles of the last launch pair
+// turn into speed estimates (assigned work / busy time) and the states are re-dealt.
+int autotune_partition(DenGraph* g, DenDevice* d) {
+  std::lock_guard<std::mutex> lock(g->mu);
+  if (d->calib_rounds_done >= kCalibRounds) return 1;
+  const size_t n = 2 * (size_t)d->grid * tb::kDenWarps;
+  std::vector<unsigned long long> busy(n);
+  CUDA_OK(cudaMemcpy(busy.data(), d->warp_busy.ptr, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
+  for (int dir = 0; dir < 2; dir++) {
+    const size_t bins = (size_t)d->grid * tb::kDenMainWarps;
+    std::vector<double> est(bins, 0.0);
+    double sum = 0.0, total_busy = 0.0;
+    int valid = 0;
+    for (int c = 0; c < d->grid; c++)
+      for (int w = 0; w < tb::kDenMainWarps; w++) {
+        const double b = (double)busy[((size_t)dir * d->grid + c) * tb::kDenWarps + w];
+        const double wk = d->cur->work[dir][c * tb::kDenMainWarps + w];
+        total_busy += b;
+        if (b > 0.0 && wk > 0.0) {
+          est[c * tb::kDenMainWarps + w] = wk / b;
+          sum += wk / b;
+          valid++;
+        }
+      }
+    // too little work per warp to measure anything (tiny graphs): leave the partition alone
+    if (valid < (int)bins || total_busy / bins < 2.0e5) {
+      d->calib_rounds_done = kCalibRounds;
+      return 1;
+    }
+    const double mean = sum / valid;
+    for (size_t i = 0; i < bins; i++) {
+      double rel = est[i] / mean;
+      rel = std::min(1.5, std::max(0.67, rel));
+      d->speed[dir][i] = rel;
+    }
+  }
+  d->calib_rounds_done++;
+  return build_partition(g, d);
 }
 
 int get_sup_device(Supervision* s, int device, SupDevice** out) {
@@ -877,15 +962,24 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   CUDA_OK(cudaMemsetAsync(zb + z_scal, 0, 128, stream));
 
   tb::DenParams dp;
+  DenPartition* part;
+  bool calibrating;
+  {
+    std::lock_guard<std::mutex> lock(g->mu);
+    part = dd->cur;
+    // only a synchronising single-pass call can feed the autotuner
+    calibrating = dd->calib_rounds_done < kCalibRounds && results_host != nullptr && B <= tb::kMaxBP;
+  }
+  dp.warp_busy = calibrating ? dd->warp_busy.as<unsigned long long>() : nullptr;
   for (int dir = 0; dir < 2; dir++) {
-    dp.dir[dir].arcs = dd->arcs[dir].as<int4>();
-    dp.dir[dir].tasks = dd->tasks[dir].as<int4>();
-    dp.dir[dir].cta_arc_off = dd->cta_arc_off[dir].as<int>();
-    dp.dir[dir].cta_task_off = dd->cta_task_off[dir].as<int>();
-    dp.dir[dir].warp_task_off = dd->warp_task_off[dir].as<int>();
-    dp.dir[dir].warp_arc_off = dd->warp_arc_off[dir].as<int>();
-    dp.dir[dir].max_arcs_cta = dd->max_arcs_cta[dir];
-    dp.dir[dir].max_tasks_cta = dd->max_tasks_cta[dir];
+    dp.dir[dir].arcs = part->arcs[dir].as<int4>();
+    dp.dir[dir].tasks = part->tasks[dir].as<int4>();
+    dp.dir[dir].cta_arc_off = part->cta_arc_off[dir].as<int>();
+    dp.dir[dir].cta_task_off = part->cta_task_off[dir].as<int>();
+    dp.dir[dir].warp_task_off = part->warp_task_off[dir].as<int>();
+    dp.dir[dir].warp_arc_off = part->warp_arc_off[dir].as<int>();
+    dp.dir[dir].max_arcs_cta = part->max_arcs_cta[dir];
+    dp.dir[dir].max_tasks_cta = part->max_tasks_cta[dir];
   }
   dp.N = N;
   dp.P = P;
@@ -917,6 +1011,15 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   {
     const char* dbg = getenv("TORCHAIN_DEBUG_FLAGS");
     dp.debug_flags = dbg ? atoi(dbg) : 0;
+  }
+  dp.cta_trace = nullptr;
+  if (g_profile.load() >= 2) {
+    const size_t tb_bytes = sizeof(unsigned long long) * 2 * (size_t)(T + 1) * dd->grid * (4 + tb::kDenWarps);
+    CUDA_OK(ws->cta_trace.reserve(tb_bytes));
+    CUDA_OK(cudaMemsetAsync(ws->cta_trace.ptr, 0, tb_bytes, stream));
+    dp.cta_trace = ws->cta_trace.as<unsigned long long>();
+    ws->trace_frames = T + 1;
+    ws->trace_grid = dd->grid;
   }
   dp.timeline = g_profile.load() ? reinterpret_cast<unsigned long long*>(zb + z_tl) : nullptr;
   ws->timeline_dev = zb + z_tl;
@@ -995,6 +1098,7 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
     results_host[0] = ws->pinned[0];
     results_host[1] = ws->pinned[1];
     results_host[2] = ws->pinned[2];
+    if (calibrating && !autotune_partition(g, dd)) return 0;
   }
   return 1;
 }
@@ -1187,7 +1291,7 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
   return 1;
 }
 
-void torchain_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
+void torchain_profile_enable(int on) { g_profile.store(on); }
 int torchain_profile_read(void* den_graph_ptr, double* den_kernel_ms, int64_t* den_kernel_launches, int reset) {
   if (!den_graph_ptr) return fail("null den_graph handle");
   harvest_profile(static_cast<DenGraph*>(den_graph_ptr));
@@ -1211,6 +1315,26 @@ int torchain_profile_timeline(void* den_graph_ptr, int64_t* out_ns, int max_entr
     const int n = std::min(max_entries, w->timeline_len);
     cudaSetDevice(kv.first.first);
     if (cudaMemcpy(out_ns, w->timeline_dev, sizeof(int64_t) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return n;
+  }
+  return 0;
+}
+
+// level-2 profiling (torchain_profile_enable(2)): per-CTA, per-frame trace of the last launch pair.
+// out: [2][frames][grid][4] int64 ns; returns the number of int64 written, dims through the out params.
+int64_t torchain_profile_cta_trace(void* den_graph_ptr, int64_t* out_ns, int64_t max_entries, int* frames, int* grid) {
+  if (!den_graph_ptr) return 0;
+  auto* g = static_cast<DenGraph*>(den_graph_ptr);
+  std::lock_guard<std::mutex> lock(g->mu);
+  for (auto& kv : g->ws) {
+    Workspace* w = kv.second.get();
+    if (!w->cta_trace.ptr || w->trace_frames <= 0) continue;
+    const int64_t n = (int64_t)2 * w->trace_frames * w->trace_grid * (4 + tb::kDenWarps);
+    if (frames) *frames = w->trace_frames;
+    if (grid) *grid = w->trace_grid;
+    if (!out_ns || max_entries < n) return n;
+    cudaSetDevice(kv.first.first);
+    if (cudaMemcpy(out_ns, w->cta_trace.ptr, sizeof(int64_t) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
     return n;
   }
   return 0;

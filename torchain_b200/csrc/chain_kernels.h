@@ -72,6 +72,8 @@ struct DenParams {
   const unsigned* y_ready;
   int y_chunk_frames;
   int debug_flags;    // timing experiments only (TORCHAIN_DEBUG_FLAGS): 1 = skip aux work in backward, 2 = skip REDs
+  unsigned long long* warp_busy;  // [2][grid][kDenWarps] SM cycles each warp spent in its frame work (feeds the partition autotuner)
+  unsigned long long* cta_trace;  // optional [phase][frame][cta][4]: main warp 0 done, aux warp 0 done, CTA done, barrier exit
   unsigned long long* timeline;  // optional: globaltimer at every phase boundary (2T+5 entries), or null
 };
 

@@ -255,21 +255,29 @@ __device__ __forceinline__ void aux_work(const DenParams& p, int flush_frame, in
 }
 
 // ------------------------------------------------- main-warp work: recursions
-// A warp walks its contiguous arc list as ONE stream, kU arcs (2*kU row gathers) per
-// batch; the last arc of every state carries the end-of-state flag (bit 31 of its pdf
-// field), states without arcs get one zero-probability arc.  Measured on B200
-// (profiles/r01_variants.txt): kU = 4 is the sweet spot; deeper prefetch (kU >= 6, or
-// a second register buffer) does not speed the forward pass up and slows the
-// backward pass down, where gathers share the memory pipe with the REDs.
-#ifndef DEN_KU
-#define DEN_KU 4
+// A warp walks its contiguous arc list as ONE stream; the last arc of every state carries the
+// end-of-state flag (bit 31 of its pdf field), states without arcs get one zero-probability
+// arc.  Measured on B200 (profiles/r01_summary.md): the forward pass likes 6 arcs in flight
+// as a 3-stage ring of 2 (28.2 us/frame vs 28.7 for one stage of 4); 8 arcs in flight do not
+// fit its 112-register budget.  The backward pass is best with ONE stage of 4: every deeper
+// variant (more gathers in flight next to the REDs) is slower (44.4 us -> 48..52 us/frame).
+#ifndef DEN_F_SA
+#define DEN_F_SA 2
 #endif
-constexpr int kU = DEN_KU;
+#ifndef DEN_F_STAGES
+#define DEN_F_STAGES 3
+#endif
+#ifndef DEN_B_SA
+#define DEN_B_SA 4
+#endif
+#ifndef DEN_B_STAGES
+#define DEN_B_STAGES 1
+#endif
 
-template <int V>
+template <int V, int SA>
 struct GatherBuf {
-  float a[kU][V];  // alpha_{t-1}(src) / beta'_{t+1}(dst)
-  float e[kU][V];  // exp(y)(pdf)
+  float a[SA][V];  // alpha_{t-1}(src) / beta'_{t+1}(dst)
+  float e[SA][V];  // exp(y)(pdf)
 };
 
 // alpha_t(h,s) = (1/S_{t-1}(s)) * sum_{arcs i->h} (alpha_{t-1}(i,s) + leaky*pi(i)*S_{t-1}(s)) * p * e_{t-1}(pdf,s)
@@ -290,10 +298,12 @@ __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __res
 #pragma unroll
     for (int v = 0; v < V; v++) Sd[v] = __ldcg(Sprev + col + v);
     int task = tb;
-    GatherBuf<V> b0;
-    auto load = [&](GatherBuf<V>& buf, int k) {
+    // narrower sequence vectors leave registers for a proportionally deeper pipeline
+    constexpr int kSA = DEN_F_SA * (4 / V), kStages = DEN_F_STAGES;
+    GatherBuf<V, kSA> ring[kStages];
+    auto load = [&](GatherBuf<V, kSA>& buf, int k) {
 #pragma unroll
-      for (int u = 0; u < kU; u++) {
+      for (int u = 0; u < kSA; u++) {
         if (k + u < n) {
           const int4 ar = a[k + u];
           ld_cg<V>(alpha_prev + ar.x * BP + col, buf.a[u]);
@@ -301,9 +311,9 @@ __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __res
         }
       }
     };
-    auto consume = [&](GatherBuf<V>& buf, int k) {
+    auto consume = [&](GatherBuf<V, kSA>& buf, int k) {
 #pragma unroll
-      for (int u = 0; u < kU; u++) {
+      for (int u = 0; u < kSA; u++) {
         if (k + u < n) {
           const int4 ar = a[k + u];
           const float pr = __int_as_float(ar.z), pi = __int_as_float(ar.w);
@@ -326,7 +336,9 @@ __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __res
         }
       }
     };
-    load(b0, 0);  // first gathers are in flight before the normalisers are consumed
+    // first gathers are in flight before the normalisers are consumed
+#pragma unroll
+    for (int st = 0; st < kStages; st++) load(ring[st], st * kSA);
 #pragma unroll
     for (int v = 0; v < V; v++) {
       const float S = (float)Sd[v];
@@ -336,9 +348,14 @@ __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __res
       acc[v] = 0.f;
     }
     for (int k = 0; k < n;) {
-      consume(b0, k);
-      k += kU;
-      load(b0, k);
+#pragma unroll
+      for (int st = 0; st < kStages; st++) {
+        if (k < n) {
+          consume(ring[st], k);
+          load(ring[st], k + kStages * kSA);
+          k += kSA;
+        }
+      }
     }
 #pragma unroll
     for (int v = 0; v < V; v++) red[warp * BP + col + v] = part[v];
@@ -373,10 +390,11 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
     }
     int task = tb;
     float pi_h = 0.f;
-    GatherBuf<V> b0;
-    auto load = [&](GatherBuf<V>& buf, int k) {
+    constexpr int kSA = DEN_B_SA * (4 / V), kStages = DEN_B_STAGES;
+    GatherBuf<V, kSA> ring[kStages];
+    auto load = [&](GatherBuf<V, kSA>& buf, int k) {
 #pragma unroll
-      for (int u = 0; u < kU; u++) {
+      for (int u = 0; u < kSA; u++) {
         if (k + u < n) {
           const int4 ar = a[k + u];
           ld_cg<V>(beta_next + ar.x * BP + col, buf.a[u]);
@@ -384,9 +402,9 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
         }
       }
     };
-    auto consume = [&](GatherBuf<V>& buf, int k) {
+    auto consume = [&](GatherBuf<V, kSA>& buf, int k) {
 #pragma unroll
-      for (int u = 0; u < kU; u++) {
+      for (int u = 0; u < kSA; u++) {
         if (k + u < n) {
           const int4 ar = a[k + u];
           const float pr = __int_as_float(ar.z);
@@ -426,7 +444,8 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
       pi_h = __int_as_float(tk0.w);
       ld_cs<V>(alpha_t + tk0.x * BP + col, al0);
     }
-    load(b0, 0);
+#pragma unroll
+    for (int st = 0; st < kStages; st++) load(ring[st], st * kSA);
     if (tb + 1 < te) ld_cs<V>(alpha_t + tasks[tb + 1].x * BP + col, aln);
 #pragma unroll
     for (int v = 0; v < V; v++) {
@@ -439,9 +458,14 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
       occ[v] = fmaf(pi_h, lamS[v], al0[v]) * invS[v];
     }
     for (int k = 0; k < n;) {
-      consume(b0, k);
-      k += kU;
-      load(b0, k);
+#pragma unroll
+      for (int st = 0; st < kStages; st++) {
+        if (k < n) {
+          consume(ring[st], k);
+          load(ring[st], k + kStages * kSA);
+          k += kSA;
+        }
+      }
     }
 #pragma unroll
     for (int v = 0; v < V; v++) red[warp * BP + col + v] = part[v];
@@ -487,6 +511,7 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
   const int BP = p.BP, T = p.T;
   unsigned epoch = 0;
   double sumsq = 0.0, ab = 0.0, gsum = 0.0;
+  long long busy = 0;  // SM cycles this warp spent on its per-frame work (lane 0 only)
 
   const int4* arcs;
   const int4* tasks;
@@ -500,6 +525,43 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
       tl[tli++] = ns;
     }
   };
+  // debug trace (torchain_profile_enable(2)): slots = earliest / latest main-warp finish,
+  // latest aux-warp finish, grid-barrier exit; combined per CTA through shared-memory min/max
+  __shared__ unsigned long long s_trace[3];
+  auto trace_warp_done = [&](int frame) {
+    if (p.cta_trace && lane == 0) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      // per-warp finish times live after the [2][T+1][grid][4] block
+      p.cta_trace[(size_t)2 * (p.T + 1) * gridDim.x * 4 +
+                  (((size_t)PHASE * (p.T + 1) + frame) * gridDim.x + blockIdx.x) * kDenWarps + warp] = ns;
+      if (is_aux) {
+        atomicMax(&s_trace[2], ns);
+      } else {
+        atomicMin(&s_trace[0], ns);
+        atomicMax(&s_trace[1], ns);
+      }
+    }
+  };
+  auto trace_frame_end = [&](int frame) {  // thread 0, after the grid barrier
+    if (p.cta_trace && threadIdx.x == 0) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      unsigned long long* out = p.cta_trace + (((size_t)PHASE * (p.T + 1) + frame) * gridDim.x + blockIdx.x) * 4;
+      out[0] = s_trace[0];
+      out[1] = s_trace[1];
+      out[2] = s_trace[2];
+      out[3] = ns;
+      s_trace[0] = ~0ull;
+      s_trace[1] = 0ull;
+      s_trace[2] = 0ull;
+    }
+  };
+  if (threadIdx.x == 0) {
+    s_trace[0] = ~0ull;
+    s_trace[1] = 0ull;
+    s_trace[2] = 0ull;
+  }
   unsigned* const barrier = p.barrier + 32 * PHASE;
   if (tl) tl += PHASE * (p.T + 3);
   stamp();
@@ -534,10 +596,14 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
     if (is_aux) {
       if (t < T) aux_work(p, -1, t, tile, auxw, lane, true, sumsq, false, gsum);
     } else {
+      const long long c0 = clock64();
       alpha_step<V>(p, arcs, tasks, abeg, aend, tb, t, sm.red, warp, lane);
+      busy += clock64() - c0;
     }
+    trace_warp_done(t);
     cta_reduce_to(sm.red, BP, p.Ssum + (size_t)t * BP);
     grid_barrier(barrier, epoch);
+    trace_frame_end(t);
     stamp();
   }
   if (is_aux) {
@@ -592,10 +658,14 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
       if (!(p.debug_flags & 1))
         aux_work(p, t + 1 < T ? t + 1 : -1, t - 1, tile, auxw, lane, false, sumsq, false, gsum, t);
     } else {
+      const long long c0 = clock64();
       beta_step<V>(p, arcs, tasks, abeg, aend, tb, te, t, sm.red, warp, lane, ab);
+      busy += clock64() - c0;
     }
+    trace_warp_done(t);
     cta_reduce_to(sm.red, BP, p.Bsum + (size_t)t * BP);
     grid_barrier(barrier, epoch);
+    trace_frame_end(t);
     stamp();
   }
 
@@ -609,6 +679,8 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
     if (lane == 0 && ab != 0.0) atomicAdd(p.scalars + 0, ab);
   }
   }  // PHASE
+  if (p.warp_busy && lane == 0)
+    p.warp_busy[((size_t)PHASE * gridDim.x + blockIdx.x) * kDenWarps + warp] = (unsigned long long)busy;
   __syncthreads();
   stamp();
 }
