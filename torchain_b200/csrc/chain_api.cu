@@ -249,7 +249,7 @@ void build_dir(const DenGraph& g, int dir, int grid, const std::vector<double>& 
           ar.w = 0;
           out->arcs.push_back(ar);
         }
-        out->arcs.back().y |= (int)0x80000000u;
+        out->arcs.back().z |= (int)0x80000000u;  // end-of-state flag = sign bit of the (non-negative) probability
       }
       out->warp_task_off.push_back((int)out->tasks.size());
       out->warp_arc_off.push_back((int)out->arcs.size());
@@ -898,8 +898,8 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   if (sup->P != P) return fail("supervision.label_dim != den_graph.NumPdfs()");
   if (ystride < cols || (deriv && dstride < cols) || (xent && xstride < cols)) return fail("row stride < cols");
   if (!(leaky > 0.f && leaky < 1.f)) return fail("leaky_hmm_coefficient must be in (0, 1)");
-  if ((int64_t)N * tb::kMaxBP >= (1ll << 31) || (int64_t)P * tb::kMaxBP >= (1ll << 31))
-    return fail("graph too large for 32-bit tile offsets");
+  if ((int64_t)N * tb::kMaxBP >= (1ll << 30) || (int64_t)P * tb::kMaxBP >= (1ll << 30))
+    return fail("graph too large for 32-bit row byte offsets");
   DeviceGuard guard(device);
   if (!guard.ok) return fail("cannot select CUDA device");
 

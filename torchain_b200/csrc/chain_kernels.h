@@ -25,7 +25,7 @@ constexpr int kMaxBP = 256;                    // padded sequences per kernel pa
 //   dir 0 ("alpha"): tasks are destination states, arcs are their in-arcs
 //   dir 1 ("beta") : tasks are source states,      arcs are their out-arcs
 struct DenDir {
-  const int4* arcs;          // {other_state, pdf | end-of-state flag (bit 31), float_bits(prob), float_bits(pi[other_state])}
+  const int4* arcs;          // {other_state, pdf, float_bits(prob) | end-of-state flag in the sign bit, float_bits(pi[other_state])}
   const int4* tasks;         // {state, arc_begin (relative to the CTA's slice), arc_count, float_bits(pi[state])}
   const int* cta_arc_off;    // [grid+1]
   const int* cta_task_off;   // [grid+1]

@@ -85,6 +85,20 @@ __device__ __forceinline__ void red_add(float* ptr, const float (&v)[V]) {
   }
 }
 
+// Address of row `idx` of a [rows][BP] fp32 table whose column offset is already folded into
+// `base`: one IMAD.WIDE.U32 instead of the ~7 instructions of generic 64-bit index arithmetic
+// (the gather loops are close to issue-bound at 3.5 warps per scheduler).
+__device__ __forceinline__ const float* row_ptr(const float* base, int idx, unsigned rowbytes) {
+  unsigned long long addr;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(idx), "r"(rowbytes), "l"(base));
+  return reinterpret_cast<const float*>(addr);
+}
+__device__ __forceinline__ float* row_ptr(float* base, int idx, unsigned rowbytes) {
+  unsigned long long addr;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(idx), "r"(rowbytes), "l"(base));
+  return reinterpret_cast<float*>(addr);
+}
+
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* ptr) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
@@ -292,6 +306,7 @@ __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __res
   const double* Sprev = p.Ssum + (size_t)(t - 1) * BP;
   const int4* __restrict__ a = arcs + abeg;
   const int n = aend - abeg;
+  const unsigned rowbytes = (unsigned)BP * 4u;
   for (int col = lane * V; col < BP; col += 32 * V) {
     float lamS[V], invS[V], part[V], acc[V];
     double Sd[V];
@@ -301,13 +316,15 @@ __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __res
     // narrower sequence vectors leave registers for a proportionally deeper pipeline
     constexpr int kSA = DEN_F_SA * (4 / V), kStages = DEN_F_STAGES;
     GatherBuf<V, kSA> ring[kStages];
+    const float* const base_a = alpha_prev + col;
+    const float* const base_e = et + col;
     auto load = [&](GatherBuf<V, kSA>& buf, int k) {
 #pragma unroll
       for (int u = 0; u < kSA; u++) {
         if (k + u < n) {
-          const int4 ar = a[k + u];
-          ld_cg<V>(alpha_prev + ar.x * BP + col, buf.a[u]);
-          ld_cg<V>(et + (ar.y & 0x7fffffff) * BP + col, buf.e[u]);
+          const int2 ar = *reinterpret_cast<const int2*>(a + k + u);  // {source state, pdf}
+          ld_cg<V>(row_ptr(base_a, ar.x, rowbytes), buf.a[u]);
+          ld_cg<V>(row_ptr(base_e, ar.y, rowbytes), buf.e[u]);
         }
       }
     };
@@ -315,14 +332,14 @@ __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __res
 #pragma unroll
       for (int u = 0; u < kSA; u++) {
         if (k + u < n) {
-          const int4 ar = a[k + u];
-          const float pr = __int_as_float(ar.z), pi = __int_as_float(ar.w);
+          const int2 ar = *(reinterpret_cast<const int2*>(a + k + u) + 1);  // {prob | end flag, pi[source]}
+          const float pr = fabsf(__int_as_float(ar.x)), pi = __int_as_float(ar.y);
 #pragma unroll
           for (int v = 0; v < V; v++) {
             const float ad = fmaf(pi, lamS[v], buf.a[u][v]);
             acc[v] = fmaf(ad * pr, buf.e[u][v], acc[v]);
           }
-          if (ar.y < 0) {  // last arc of this state (warp-uniform branch)
+          if (ar.x < 0) {  // sign bit of the probability = last arc of this state (warp-uniform branch)
             const int4 tk = tasks[task++];
             float out[V];
 #pragma unroll
@@ -378,6 +395,7 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
   const double* Bn = p.Bsum + (size_t)(t + 1) * BP;
   const int4* __restrict__ a = arcs + abeg;
   const int n = aend - abeg;
+  const unsigned rowbytes = (unsigned)BP * 4u;
   for (int col = lane * V; col < BP; col += 32 * V) {
     float lamS[V], invS[V], bv[V], part[V], X[V], occ[V], aln[V], al0[V];
     double Sd[V], Bd[V];
@@ -392,13 +410,16 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
     float pi_h = 0.f;
     constexpr int kSA = DEN_B_SA * (4 / V), kStages = DEN_B_STAGES;
     GatherBuf<V, kSA> ring[kStages];
+    const float* const base_b = beta_next + col;
+    const float* const base_e = et + col;
+    float* const base_g = gt + col;
     auto load = [&](GatherBuf<V, kSA>& buf, int k) {
 #pragma unroll
       for (int u = 0; u < kSA; u++) {
         if (k + u < n) {
-          const int4 ar = a[k + u];
-          ld_cg<V>(beta_next + ar.x * BP + col, buf.a[u]);
-          ld_cg<V>(et + (ar.y & 0x7fffffff) * BP + col, buf.e[u]);
+          const int2 ar = *reinterpret_cast<const int2*>(a + k + u);  // {destination state, pdf}
+          ld_cg<V>(row_ptr(base_b, ar.x, rowbytes), buf.a[u]);
+          ld_cg<V>(row_ptr(base_e, ar.y, rowbytes), buf.e[u]);
         }
       }
     };
@@ -407,7 +428,7 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
       for (int u = 0; u < kSA; u++) {
         if (k + u < n) {
           const int4 ar = a[k + u];
-          const float pr = __int_as_float(ar.z);
+          const float pr = fabsf(__int_as_float(ar.z));
           float g[V];
 #pragma unroll
           for (int v = 0; v < V; v++) {
@@ -415,8 +436,8 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
             X[v] += vf;
             g[v] = vf * occ[v];
           }
-          if (!(p.debug_flags & 2)) red_add<V>(gt + (ar.y & 0x7fffffff) * BP + col, g);
-          if (ar.y < 0) {  // last arc of this state: finish it, set up the next one
+          if (!(p.debug_flags & 2)) red_add<V>(row_ptr(base_g, ar.y, rowbytes), g);
+          if (ar.z < 0) {  // sign bit of the probability = last arc of this state
             const int4 tk = tasks[task];
             float bd[V];
 #pragma unroll
