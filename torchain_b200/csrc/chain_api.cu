@@ -882,6 +882,7 @@ struct ChunkedInput {
   const unsigned* flags = nullptr;
   int chunk_frames = 0;
   cudaEvent_t all_landed = nullptr;  // recorded on the copy stream after the last chunk
+  unsigned* deriv_progress = nullptr;  // device pointer of a mapped pinned counter (see DenParams)
 };
 
 // The whole loss, enqueued on `stream`: forward launch -> numerator -> backward launch ->
@@ -1008,6 +1009,7 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   dp.num_arc_post = np.arc_post;
   dp.y_ready = chunked.flags;
   dp.y_chunk_frames = chunked.chunk_frames;
+  dp.deriv_progress = (B <= tb::kMaxBP) ? chunked.deriv_progress : nullptr;
   {
     const char* dbg = getenv("TORCHAIN_DEBUG_FLAGS");
     dp.debug_flags = dbg ? atoi(dbg) : 0;
@@ -1109,7 +1111,8 @@ struct HostPath {
   cudaStream_t compute = nullptr, copy = nullptr;
   cudaEvent_t ready = nullptr, landed = nullptr;
   DevBuf y, deriv, xent, flags;
-  unsigned* one = nullptr;  // pinned constant 1
+  unsigned* one = nullptr;       // pinned constant 1
+  unsigned* progress = nullptr;  // pinned, device-mapped: frames of the derivative already complete
 };
 thread_local HostPath g_host;
 
@@ -1221,6 +1224,7 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
     if (h.ready) cudaEventDestroy(h.ready);
     if (h.landed) cudaEventDestroy(h.landed);
     if (h.one) cudaFreeHost(h.one);
+    if (h.progress) cudaFreeHost(h.progress);
     h = HostPath();
     CUDA_OK(cudaStreamCreateWithFlags(&h.compute, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&h.copy, cudaStreamNonBlocking));
@@ -1228,6 +1232,7 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
     CUDA_OK(cudaEventCreateWithFlags(&h.landed, cudaEventDisableTiming));
     CUDA_OK(cudaMallocHost(&h.one, sizeof(unsigned)));
     *h.one = 1u;
+    CUDA_OK(cudaHostAlloc(&h.progress, sizeof(unsigned), cudaHostAllocMapped));
     h.device = device;
   }
   const size_t bytes = sizeof(float) * (size_t)rows * cols;
@@ -1235,26 +1240,16 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
   const bool want_xent = xent_host != nullptr && xent_regularize != 0.f;
   if (want_xent) CUDA_OK(h.xent.reserve(bytes));
 
-  // The derivative is written straight into the caller's buffer when that buffer is pinned
-  // (device-mapped under UVA): the backward launch streams its 128-byte row segments over
-  // PCIe while it runs, instead of a separate device-to-host copy afterwards.
+  // The derivative is produced in device memory and copied out chunk by chunk (whole frames)
+  // by the copy engine WHILE the backward recurrence is still running: the kernel publishes how
+  // many trailing frames are complete in a mapped pinned counter, this (blocked anyway) host
+  // thread polls it and enqueues the copies.  Only the chunk holding frame 0 waits for the end.
   float* deriv_dev = nullptr;
-  int64_t deriv_dev_stride = cols;
-  bool zero_copy = false;
+  const int64_t deriv_dev_stride = cols;
   if (deriv_host) {
-    cudaPointerAttributes attr;
-    if (cudaPointerGetAttributes(&attr, deriv_host) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
-        attr.devicePointer != nullptr) {
-      deriv_dev = static_cast<float*>(attr.devicePointer);
-      deriv_dev_stride = dstride;
-      zero_copy = true;
-    } else {
-      cudaGetLastError();  // clear the "not registered" error of pageable memory
-      CUDA_OK(h.deriv.reserve(bytes));
-      deriv_dev = h.deriv.as<float>();
-    }
+    CUDA_OK(h.deriv.reserve(bytes));
+    deriv_dev = h.deriv.as<float>();
   }
-
   // nnet_output goes up in chunks of whole frames; the forward launch starts as soon as the
   // first chunk has landed and waits (per frame) on the flag of the chunk it needs next.
   const int T = sp->T, B = sp->B;
@@ -1276,18 +1271,59 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
   ci.flags = h.flags.as<unsigned>();
   ci.chunk_frames = chunk_frames;
   ci.all_landed = h.landed;
-  // compute() synchronises the compute stream once to deliver `results`
-  if (!compute(g, sp, h.y.as<float>(), rows, cols, cols, results, nullptr, deriv_dev, deriv_dev_stride,
+  const bool pipelined_out = deriv_host != nullptr && B <= tb::kMaxBP;
+  if (pipelined_out) {
+    *reinterpret_cast<volatile unsigned*>(h.progress) = 0u;
+    unsigned* dptr = nullptr;
+    CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), h.progress, 0));
+    ci.deriv_progress = dptr;
+  }
+  // enqueue everything without synchronising (results are fetched below)
+  float* res_dev = nullptr;
+  {
+    static thread_local DevBuf res_buf;
+    CUDA_OK(res_buf.reserve(4 * sizeof(float)));
+    res_dev = res_buf.as<float>();
+  }
+  if (!compute(g, sp, h.y.as<float>(), rows, cols, cols, nullptr, res_dev, deriv_dev, deriv_dev_stride,
                want_xent ? h.xent.as<float>() : nullptr, cols, l2, leaky, xent_regularize, 1.0f, device, h.compute,
                ci))
     return 0;
-  if (deriv_host && !zero_copy)
-    CUDA_OK(cudaMemcpy2DAsync(deriv_host, sizeof(float) * dstride, deriv_dev, sizeof(float) * cols,
-                              sizeof(float) * cols, rows, cudaMemcpyDeviceToHost, h.compute));
+  auto copy_chunk = [&](int k, cudaStream_t st) -> cudaError_t {
+    const int64_t r0 = (int64_t)k * chunk_frames * B;
+    const int64_t nr = std::min<int64_t>((int64_t)chunk_frames * B, rows - r0);
+    return cudaMemcpy2DAsync(deriv_host + r0 * dstride, sizeof(float) * dstride, deriv_dev + r0 * cols,
+                             sizeof(float) * cols, sizeof(float) * cols, nr, cudaMemcpyDeviceToHost, st);
+  };
+  int next = nchunks - 1;
+  if (pipelined_out) {
+    // frames >= T - progress are complete; chunk k covers frames [k*chunk_frames, ...)
+    while (next >= 1) {
+      const unsigned need = (unsigned)(T - next * chunk_frames);
+      bool done = false;
+      while (*reinterpret_cast<volatile unsigned*>(h.progress) < need) {
+        if (cudaStreamQuery(h.compute) != cudaErrorNotReady) {
+          done = true;
+          break;
+        }
+      }
+      if (done) break;
+      CUDA_OK(copy_chunk(next, h.copy));
+      next--;
+    }
+  }
+  CUDA_OK(cudaStreamSynchronize(h.compute));
+  if (deriv_host)
+    for (; next >= 0; next--) CUDA_OK(copy_chunk(next, h.copy));
   if (want_xent)
     CUDA_OK(cudaMemcpy2DAsync(xent_host, sizeof(float) * xstride, h.xent.ptr, sizeof(float) * cols,
-                              sizeof(float) * cols, rows, cudaMemcpyDeviceToHost, h.compute));
-  CUDA_OK(cudaStreamSynchronize(h.compute));
+                              sizeof(float) * cols, rows, cudaMemcpyDeviceToHost, h.copy));
+  float res_host[3];
+  CUDA_OK(cudaMemcpyAsync(res_host, res_dev, sizeof(res_host), cudaMemcpyDeviceToHost, h.copy));
+  CUDA_OK(cudaStreamSynchronize(h.copy));
+  results[0] = res_host[0];
+  results[1] = res_host[1];
+  results[2] = res_host[2];
   return 1;
 }
 

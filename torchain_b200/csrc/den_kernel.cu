@@ -686,6 +686,10 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
     trace_warp_done(t);
     cta_reduce_to(sm.red, BP, p.Bsum + (size_t)t * BP);
     grid_barrier(barrier, epoch);
+    if (p.deriv_progress && blockIdx.x == 0 && threadIdx.x == 0) {
+      *reinterpret_cast<volatile unsigned*>(p.deriv_progress) = (unsigned)(T - 1 - t);
+      __threadfence_system();
+    }
     trace_frame_end(t);
     stamp();
   }
