@@ -288,3 +288,37 @@ def test_large_tree_config_properties():
     assert np.abs(x64.sum(axis=1) - 1.0).max() < 1e-4
     den_post = x64 - d64
     assert den_post.min() > -1e-5 and abs(den_post.sum() - B * T) < 1e-4 * B * T
+
+
+def _hub_graph(seed, N, P, hubs):
+    """Random graph plus `hubs` states that every state has an arc to and from (heavy-tailed degrees)."""
+    rng = np.random.default_rng(seed)
+    den = synth.make_den_fst(seed, N, P, mean_deg=3.0)
+    src, dst, lab, cost = [den.src], [den.dst], [den.ilabel], [den.cost]
+    for h in range(hubs):
+        others = np.arange(N, dtype=np.int32)
+        src += [others, np.full(N, h, dtype=np.int32)]
+        dst += [np.full(N, h, dtype=np.int32), others]
+        lab += [rng.integers(1, P + 1, size=N).astype(np.int32)] * 2
+        cost += [np.full(N, 3.0, dtype=np.float32), np.full(N, np.log(4.0 * N), dtype=np.float32)]
+    src, dst, lab, cost = map(np.concatenate, (src, dst, lab, cost))
+    o = np.argsort(src, kind="stable")
+    return synth.DenFst(N, P, 0, src[o], dst[o], lab[o], cost[o], den.final_cost)
+
+
+@pytest.mark.parametrize("cap", [None, "7"])
+def test_gpu_split_high_degree_states(cap, monkeypatch):
+    """States with more arcs than the split cap are spread over several warp tasks that accumulate
+    with REDs (default cap 192; a tiny cap also splits ordinary states)."""
+    if cap is not None:
+        monkeypatch.setenv("TORCHAIN_SPLIT_CAP", cap)
+    den = _hub_graph(5, 300, 40, hubs=2)
+    B, T = 37, 7
+    sup = synth.make_supervision(6, den, B, T, num_paths=3)
+    y = synth.make_nnet_output(7, B, T, 40, scale=1.5)
+    r = ol.chain(ol.OracleDen(den), ol.OracleSup(sup), y, l2=0.01, leaky=0.1, mode="fp64", threads=4)
+    g, s = handles(den, sup)
+    for _ in range(2):   # second call reuses (un-zeroed) workspace buffers
+        res, d, _ = run_abi(g, s, y, 0.01, 0.1)
+        assert rel(res[0], r["objf"]) < OBJF_RTOL
+        assert deriv_err(d, r["deriv"]) < DERIV_RTOL

@@ -104,11 +104,13 @@ struct DirHost {  // one direction, partitioned
   std::vector<int4> arcs, tasks;
   std::vector<int> cta_arc_off, cta_task_off, warp_task_off, warp_arc_off;
   int max_arcs_cta = 0, max_tasks_cta = 0;
+  bool has_split = false;
 };
 
 struct DenPartition {  // one uploaded partition of both directions
   DevBuf arcs[2], tasks[2], cta_arc_off[2], cta_task_off[2], warp_task_off[2], warp_arc_off[2];
   int max_arcs_cta[2] = {0, 0}, max_tasks_cta[2] = {0, 0};
+  bool has_split = false;
   std::vector<double> work[2];  // [grid*kDenMainWarps] cost units assigned to each warp
 };
 
@@ -196,10 +198,30 @@ void build_dir(const DenGraph& g, int dir, int grid, const std::vector<double>& 
   for (int a = 0; a < A; a++) arc_of[pos[key[a]]++] = a;  // stable: FST arc order within a state
 
   const int kTaskOverhead = 3;  // fixed per-state cost in arc units (prologue, store, partial sums)
-  std::vector<int> cost(N), all(N);
+  // States with very many arcs (real den graphs are heavy-tailed) would be one serial warp task;
+  // they are split into sub-tasks of at most `cap` arcs that accumulate with REDs.
+  int cap = 192;
+  if (const char* e = getenv("TORCHAIN_SPLIT_CAP")) cap = std::max(2, atoi(e));
+  struct Item {
+    int state, first, count, flag;  // arcs [first, first+count) of the state's CSR slice
+  };
+  std::vector<Item> items;
+  out->has_split = false;
   for (int s = 0; s < N; s++) {
-    cost[s] = deg[s] + kTaskOverhead;
-    all[s] = s;
+    if (deg[s] <= cap) {
+      items.push_back({s, 0, deg[s], 0});
+    } else {
+      out->has_split = true;
+      const int k = (deg[s] + cap - 1) / cap, per = (deg[s] + k - 1) / k;
+      for (int j = 0, first = 0; j < k; j++, first += per)
+        items.push_back({s, first, std::min(per, deg[s] - first), j == 0 ? 2 : 1});
+    }
+  }
+  const int NI = (int)items.size();
+  std::vector<int> cost(NI), all(NI);
+  for (int i = 0; i < NI; i++) {
+    cost[i] = items[i].count + kTaskOverhead;
+    all[i] = i;
   }
   std::vector<std::vector<int>> by_cta;
   std::vector<double> cta_speed(grid, 0.0);
@@ -222,16 +244,18 @@ void build_dir(const DenGraph& g, int dir, int grid, const std::vector<double>& 
         &by_warp);
     const int arc0 = (int)out->arcs.size(), task0 = (int)out->tasks.size();
     for (int w = 0; w < tb::kDenMainWarps; w++) {
-      for (int s : by_warp[w]) {
-        (*work)[c * tb::kDenMainWarps + w] += cost[s];
+      for (int it : by_warp[w]) {
+        const Item& item = items[it];
+        const int s = item.state;
+        (*work)[c * tb::kDenMainWarps + w] += cost[it];
         int4 tk;
         tk.x = s;
         tk.y = (int)out->arcs.size() - arc0;
-        tk.z = std::max(deg[s], 1);
+        tk.z = item.flag;
         float pis = g.pi[s];
         std::memcpy(&tk.w, &pis, 4);
         out->tasks.push_back(tk);
-        for (int k = begin[s]; k < begin[s + 1]; k++) {
+        for (int k = begin[s] + item.first; k < begin[s] + item.first + item.count; k++) {
           const int a = arc_of[k];
           int4 ar;
           ar.x = other[a];
@@ -241,7 +265,7 @@ void build_dir(const DenGraph& g, int dir, int grid, const std::vector<double>& 
           std::memcpy(&ar.w, &pio, 4);
           out->arcs.push_back(ar);
         }
-        if (deg[s] == 0) {  // a state without arcs still needs its end-of-state marker
+        if (item.count == 0) {  // a state without arcs still needs its end-of-state marker
           int4 ar;
           ar.x = s;
           ar.y = 0;
@@ -736,6 +760,7 @@ int build_partition(DenGraph* g, DenDevice* d) {
     CUDA_OK(upload(part->warp_arc_off[dir], h.warp_arc_off));
     part->max_arcs_cta[dir] = h.max_arcs_cta;
     part->max_tasks_cta[dir] = h.max_tasks_cta;
+    part->has_split = part->has_split || h.has_split;
   }
   d->cur = part.get();
   d->generations.push_back(std::move(part));
@@ -949,7 +974,7 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   // ---- denominator workspace; passes of at most kMaxBP sequences
   const int maxBP = pad_batch(std::min(B, tb::kMaxBP));
   CUDA_OK(ws->alpha.reserve(sizeof(float) * (size_t)(T + 1) * N * maxBP));
-  CUDA_OK(ws->beta.reserve(sizeof(float) * (size_t)2 * N * maxBP));
+  CUDA_OK(ws->beta.reserve(sizeof(float) * (size_t)3 * N * maxBP));
   const size_t tile_floats = (size_t)2 * P * maxBP;
   CUDA_OK(ws->tiles.reserve(sizeof(float) * tile_floats));  // etile
   // zeroed block: gtile | Ssum | Bsum | barriers | timeline ;  scalars + results live after it
@@ -982,6 +1007,7 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
     dp.dir[dir].max_arcs_cta = part->max_arcs_cta[dir];
     dp.dir[dir].max_tasks_cta = part->max_tasks_cta[dir];
   }
+  dp.has_split = part->has_split ? 1 : 0;
   dp.N = N;
   dp.P = P;
   dp.Btot = B;

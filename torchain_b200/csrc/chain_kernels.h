@@ -26,7 +26,7 @@ constexpr int kMaxBP = 256;                    // padded sequences per kernel pa
 //   dir 1 ("beta") : tasks are source states,      arcs are their out-arcs
 struct DenDir {
   const int4* arcs;          // {other_state, pdf, float_bits(prob) | end-of-state flag in the sign bit, float_bits(pi[other_state])}
-  const int4* tasks;         // {state, arc_begin (relative to the CTA's slice), arc_count, float_bits(pi[state])}
+  const int4* tasks;         // {state, arc_begin (relative to the CTA's slice), split flag (0 whole state, 2 first / 1 other sub-task of a split state), float_bits(pi[state])}
   const int* cta_arc_off;    // [grid+1]
   const int* cta_task_off;   // [grid+1]
   const int* warp_task_off;  // [grid*kDenMainWarps+1] absolute task indices
@@ -48,7 +48,7 @@ struct DenParams {
   float* deriv;
   int64_t dstride;
   float* alpha;      // (T+1) x N x BP   un-mixed alphas (Kaldi stores alpha-dash; we mix on the fly)
-  float* beta;       // 2 x N x BP       beta-dash ping-pong
+  float* beta;       // 3 x N x BP       beta-dash rotation (write / gather / re-zero)
   float* etile;      // 2 x P x BP       exp(y) of one frame, sequence-innermost
   float* gtile;      // 2 x P x BP       occupancies of one frame, sequence-innermost (zero on entry)
   double* Ssum;      // (T+1) x BP       sum_h alpha_t(h,s)      (zero on entry)
@@ -60,6 +60,7 @@ struct DenParams {
   float scale_gamma;  // deriv_scale * (-supervision.weight)
   float scale_y;      // deriv_scale * (-supervision.weight * l2_regularize)
   int arcs_in_smem;   // 1: arc slices staged in shared memory
+  int has_split;      // 1: some states are dealt out as several sub-tasks (selects the SPLIT kernels)
   // numerator occupancies, subtracted from the occupancy tile by the backward launch so that the
   // flush writes w*gamma_num - w*gamma_den in one go (arcs ordered by frame)
   const int* num_frame_off;    // [T+1] ranges into num_frame_arcs, or null (no numerator)

@@ -71,17 +71,19 @@ __device__ __forceinline__ void st_vec(float* ptr, const float (&v)[V]) {
   }
 }
 
-// Fire-and-forget fp32 reduction at L2 (no return value): RED.E.ADD.F32[.vN]
+// Fire-and-forget fp32 reduction at L2 (no return value): RED.E.ADD.F32[.vN].
+// No "memory" clobber on purpose: the targets (occupancy tile, rows of split states) are never
+// read back by this thread before the next barrier, and a clobber would pin the gathers of the
+// next batch behind the RED.
 template <int V>
 __device__ __forceinline__ void red_add(float* ptr, const float (&v)[V]) {
   if constexpr (V == 4) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(v[0]), "f"(v[1]), "f"(v[2]),
-                 "f"(v[3])
-                 : "memory");
+                 "f"(v[3]));
   } else if constexpr (V == 2) {
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(ptr), "f"(v[0]), "f"(v[1]) : "memory");
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(ptr), "f"(v[0]), "f"(v[1]));
   } else {
-    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(ptr), "f"(v[0]) : "memory");
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(ptr), "f"(v[0]));
   }
 }
 
@@ -295,7 +297,12 @@ struct GatherBuf {
 };
 
 // alpha_t(h,s) = (1/S_{t-1}(s)) * sum_{arcs i->h} (alpha_{t-1}(i,s) + leaky*pi(i)*S_{t-1}(s)) * p * e_{t-1}(pdf,s)
-template <int V>
+// SPLIT = true is the variant for graphs in which some state has more arcs than the split cap
+// (real den graphs are heavy-tailed): such a state is dealt out as several sub-tasks (tk.z = 2 for
+// the first, 1 for the others) that accumulate with REDs into a pre-zeroed row.  Everything is
+// linear in the arc sums, so nothing else changes.  It is a separate instantiation because the
+// mere presence of the RED path in the end-of-state block costs ~1.5 us per frame.
+template <int V, bool SPLIT>
 __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __restrict__ arcs,
                                            const int4* __restrict__ tasks, int abeg, int aend, int tb, int t,
                                            float* red, int warp, int lane) {
@@ -348,7 +355,9 @@ __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __res
               part[v] += out[v];
               acc[v] = 0.f;
             }
-            st_vec<V>(alpha_cur + tk.x * BP + col, out);
+            float* const dst = row_ptr(alpha_cur + col, tk.x, rowbytes);
+            if (SPLIT && tk.z != 0) red_add<V>(dst, out);
+            else st_vec<V>(dst, out);
           }
         }
       }
@@ -381,14 +390,17 @@ __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __res
 
 // beta'_t(h,s) = (1/S_t(s)) * sum_{arcs h->j} p * e_t(pdf,s) * (beta'_{t+1}(j,s) + b_{t+1}(s))
 // gamma_t(pdf,s) += that term * alpha'_t(h,s) / S_t(s)
-template <int V>
+template <int V, bool SPLIT>
 __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __restrict__ arcs,
                                           const int4* __restrict__ tasks, int abeg, int aend, int tb, int te, int t,
                                           float* red, int warp, int lane, double& ab) {
   const int BP = p.BP;
   const float* __restrict__ alpha_t = p.alpha + (size_t)t * p.N * BP;
-  const float* __restrict__ beta_next = p.beta + (size_t)((t + 1) & 1) * p.N * BP;
-  float* __restrict__ beta_cur = p.beta + (size_t)(t & 1) * p.N * BP;
+  // beta' rotates through three buffers: written at step t, gathered at step t-1, and (for
+  // split states, which accumulate with REDs) re-zeroed at step t-2
+  const float* __restrict__ beta_next = p.beta + (size_t)((t + 1) % 3) * p.N * BP;
+  float* __restrict__ beta_cur = p.beta + (size_t)(t % 3) * p.N * BP;
+  float* __restrict__ beta_zero = p.beta + (size_t)((t + 2) % 3) * p.N * BP;
   const float* __restrict__ et = p.etile + (size_t)(t & 1) * p.P * BP;
   float* __restrict__ gt = p.gtile + (size_t)(t & 1) * p.P * BP;
   const double* St = p.Ssum + (size_t)t * BP;
@@ -447,13 +459,24 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
               if (t == 0 && col + v < p.B) ab += (double)(occ[v] * (lamS[v] / p.leaky)) * (double)bd[v];
               X[v] = 0.f;
             }
-            st_vec<V>(beta_cur + tk.x * BP + col, bd);
+            float* const dst = row_ptr(beta_cur + col, tk.x, rowbytes);
+            if (SPLIT && tk.z != 0) {
+              red_add<V>(dst, bd);
+              if (tk.z == 2) {  // the state's first sub-task also clears the row used at step t-1
+                float zero[V];
+#pragma unroll
+                for (int v = 0; v < V; v++) zero[v] = 0.f;
+                st_vec<V>(row_ptr(beta_zero + col, tk.x, rowbytes), zero);
+              }
+            } else {
+              st_vec<V>(dst, bd);
+            }
             task++;
             if (task < te) {
               pi_h = __int_as_float(tasks[task].w);
 #pragma unroll
               for (int v = 0; v < V; v++) occ[v] = fmaf(pi_h, lamS[v], aln[v]) * invS[v];
-              if (task + 1 < te) ld_cs<V>(alpha_t + tasks[task + 1].x * BP + col, aln);
+              if (task + 1 < te) ld_cs<V>(row_ptr(alpha_t + col, tasks[task + 1].x, rowbytes), aln);
             }
           }
         }
@@ -463,11 +486,11 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
     if (tb < te) {
       const int4 tk0 = tasks[tb];
       pi_h = __int_as_float(tk0.w);
-      ld_cs<V>(alpha_t + tk0.x * BP + col, al0);
+      ld_cs<V>(row_ptr(alpha_t + col, tk0.x, rowbytes), al0);
     }
 #pragma unroll
     for (int st = 0; st < kStages; st++) load(ring[st], st * kSA);
-    if (tb + 1 < te) ld_cs<V>(alpha_t + tasks[tb + 1].x * BP + col, aln);
+    if (tb + 1 < te) ld_cs<V>(row_ptr(alpha_t + col, tasks[tb + 1].x, rowbytes), aln);
 #pragma unroll
     for (int v = 0; v < V; v++) {
       const float S = (float)Sd[v];
@@ -521,7 +544,7 @@ __device__ __forceinline__ void load_dir(const DenParams& p, int d, const Smem& 
 // ------------------------------------------------------------------ kernel
 // PHASE 0: forward launch (prologue + T alpha frames + total log-likelihood).
 // PHASE 1: backward launch (beta prologue + T beta/derivative frames + last flush).
-template <int V, bool STAGED, int PHASE>
+template <int V, bool STAGED, int PHASE, bool SPLIT>
 __device__ __forceinline__ void den_chain_body(const DenParams& p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Smem sm = carve(smem_raw, p);
@@ -598,11 +621,17 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
       for (int task = tb; task < te; task++) {
         const int4 tk = tasks[task];
         const float pi_h = __int_as_float(tk.w);
+        if (SPLIT && tk.z == 1) continue;  // secondary sub-task of a split state: its first one does the set-up
         float out[V];
 #pragma unroll
         for (int v = 0; v < V; v++) out[v] = pi_h;
         st_vec<V>(p.alpha + tk.x * BP + col, out);
         part += pi_h;
+        if (SPLIT && tk.z == 2) {  // rows of frames 1..T are accumulated with REDs: clear them
+#pragma unroll
+          for (int v = 0; v < V; v++) out[v] = 0.f;
+          for (int tt = 1; tt <= T; tt++) st_vec<V>(p.alpha + ((size_t)tt * p.N + tk.x) * BP + col, out);
+        }
       }
 #pragma unroll
       for (int v = 0; v < V; v++) sm.red[warp * BP + col + v] = part;
@@ -618,7 +647,7 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
       if (t < T) aux_work(p, -1, t, tile, auxw, lane, true, sumsq, false, gsum);
     } else {
       const long long c0 = clock64();
-      alpha_step<V>(p, arcs, tasks, abeg, aend, tb, t, sm.red, warp, lane);
+      alpha_step<V, SPLIT>(p, arcs, tasks, abeg, aend, tb, t, sm.red, warp, lane);
       busy += clock64() - c0;
     }
     trace_warp_done(t);
@@ -649,7 +678,8 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
   // ---- backward prologue: beta'_T(h,s) = 1 / sum_h alpha'_T(h,s) = 1 / (S_T (1 + leaky*sum_pi))
   if (!is_aux) {
     const double* ST = p.Ssum + (size_t)T * BP;
-    float* betaT = p.beta + (size_t)(T & 1) * p.N * BP;
+    float* betaT = p.beta + (size_t)(T % 3) * p.N * BP;
+    float* betaTm1 = p.beta + (size_t)((T + 2) % 3) * p.N * BP;  // buffer of step T-1
     for (int col = lane * V; col < BP; col += 32 * V) {
       float inv[V], part[V];
 #pragma unroll
@@ -661,9 +691,16 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
       for (int task = tb; task < te; task++) {
         const int4 tk = tasks[task];
         const float pi_h = __int_as_float(tk.w);
+        if (SPLIT && tk.z == 1) continue;
         st_vec<V>(betaT + tk.x * BP + col, inv);
 #pragma unroll
         for (int v = 0; v < V; v++) part[v] = fmaf(pi_h, inv[v], part[v]);
+        if (SPLIT && tk.z == 2) {
+          float zero[V];
+#pragma unroll
+          for (int v = 0; v < V; v++) zero[v] = 0.f;
+          st_vec<V>(betaTm1 + tk.x * BP + col, zero);
+        }
       }
 #pragma unroll
       for (int v = 0; v < V; v++) sm.red[warp * BP + col + v] = part[v];
@@ -680,7 +717,7 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
         aux_work(p, t + 1 < T ? t + 1 : -1, t - 1, tile, auxw, lane, false, sumsq, false, gsum, t);
     } else {
       const long long c0 = clock64();
-      beta_step<V>(p, arcs, tasks, abeg, aend, tb, te, t, sm.red, warp, lane, ab);
+      beta_step<V, SPLIT>(p, arcs, tasks, abeg, aend, tb, te, t, sm.red, warp, lane, ab);
       busy += clock64() - c0;
     }
     trace_warp_done(t);
@@ -713,18 +750,19 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
 // The forward launch is capped at 112 registers/thread so that 8 K registers per SM stay free:
 // the numerator kernel (128 threads x 48 registers per CTA) can then run on the same SMs while
 // the forward recurrence is in flight.  The backward launch takes the whole register file.
-template <int V, bool STAGED>
+template <int V, bool STAGED, bool SPLIT>
 __global__ void __maxnreg__(112) den_forward_kernel(const __grid_constant__ DenParams p) {
-  den_chain_body<V, STAGED, 0>(p);
+  den_chain_body<V, STAGED, 0, SPLIT>(p);
 }
-template <int V, bool STAGED>
+template <int V, bool STAGED, bool SPLIT>
 __global__ void __launch_bounds__(kDenThreads, 1) den_backward_kernel(const __grid_constant__ DenParams p) {
-  den_chain_body<V, STAGED, 1>(p);
+  den_chain_body<V, STAGED, 1, SPLIT>(p);
 }
 
-template <int V, bool STAGED, int PHASE>
-cudaError_t launch_t(const DenParams& p, int grid, size_t smem, cudaStream_t stream) {
-  void (*kern)(DenParams) = PHASE == 0 ? den_forward_kernel<V, STAGED> : den_backward_kernel<V, STAGED>;
+template <int V, bool STAGED, bool SPLIT>
+cudaError_t launch_t(const DenParams& p, int phase, int grid, size_t smem, cudaStream_t stream) {
+  void (*kern)(DenParams) =
+      phase == 0 ? den_forward_kernel<V, STAGED, SPLIT> : den_backward_kernel<V, STAGED, SPLIT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   void* args[] = {const_cast<DenParams*>(&p)};
@@ -735,7 +773,8 @@ cudaError_t launch_t(const DenParams& p, int grid, size_t smem, cudaStream_t str
 
 template <int V, bool STAGED>
 cudaError_t launch_p(const DenParams& p, int phase, int grid, size_t smem, cudaStream_t stream) {
-  return phase == 0 ? launch_t<V, STAGED, 0>(p, grid, smem, stream) : launch_t<V, STAGED, 1>(p, grid, smem, stream);
+  return p.has_split ? launch_t<V, STAGED, true>(p, phase, grid, smem, stream)
+                     : launch_t<V, STAGED, false>(p, phase, grid, smem, stream);
 }
 
 }  // namespace
