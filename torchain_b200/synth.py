@@ -274,8 +274,27 @@ def small_case(seed):
     return dict(den=den, sup=sup, y=y, leaky=leaky, l2=l2, B=B, T=T, P=P, N=N)
 
 
+def add_hubs(den, hubs, seed=0):
+    """Heavy-tailed variant of a den graph: `hubs` states get an arc from and to every state
+    (real chain den graphs have such states; they exercise the state-splitting path)."""
+    rng = np.random.default_rng(seed)
+    N, P = den.num_states, den.num_pdfs
+    src, dst, lab, cost = [den.src], [den.dst], [den.ilabel], [den.cost]
+    for h in range(hubs):
+        others = np.arange(N, dtype=np.int32)
+        src += [others, np.full(N, h, dtype=np.int32)]
+        dst += [np.full(N, h, dtype=np.int32), others]
+        lab += [rng.integers(1, P + 1, size=N).astype(np.int32), rng.integers(1, P + 1, size=N).astype(np.int32)]
+        cost += [np.full(N, 3.0, dtype=np.float32), np.full(N, np.log(4.0 * N), dtype=np.float32)]
+    src, dst, lab, cost = map(np.concatenate, (src, dst, lab, cost))
+    o = np.argsort(src, kind="stable")
+    return DenFst(N, P, den.start, src[o], dst[o], lab[o], cost[o], den.final_cost)
+
+
 CONFIGS = {
     # name: (P, N, mean_deg, B, T, leaky, l2)
+    "tiny": dict(P=40, N=120, mean_deg=4.0, B=6, T=8, leaky=0.1, l2=5e-5),
+    "chime5_hubs": dict(P=2928, N=10_000, mean_deg=26.0, B=128, T=50, leaky=0.1, l2=5e-5, hubs=2),
     "chime5": dict(P=2928, N=10_000, mean_deg=28.0, B=128, T=50, leaky=0.1, l2=5e-5),
     "chime5_b512": dict(P=2928, N=10_000, mean_deg=28.0, B=512, T=50, leaky=0.1, l2=5e-5),
     "large_tree": dict(P=6000, N=20_000, mean_deg=28.0, B=256, T=50, leaky=0.1, l2=5e-5),
