@@ -264,7 +264,6 @@ def run_b200(args):
     sync_all()
     ms = e0.elapsed_time(e1)
     launches = lib.torchain_kernel_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
     den_ms, den_n = ctypes.c_double(0), ctypes.c_int64(0)
     lib.torchain_profile_read(g.ptr, ctypes.byref(den_ms), ctypes.byref(den_n), 1)
     lib.torchain_profile_enable(0)
@@ -297,6 +296,7 @@ def run_b200(args):
         e2e_step()
     torch.cuda.synchronize(dev)
     e2e_s = (time.perf_counter() - t0) / n_e2e
+    clocks = sampler.stop() if rank == 0 else None   # sampled over the device-timed AND the e2e-timed loops
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

@@ -322,3 +322,42 @@ def test_gpu_split_high_degree_states(cap, monkeypatch):
         res, d, _ = run_abi(g, s, y, 0.01, 0.1)
         assert rel(res[0], r["objf"]) < OBJF_RTOL
         assert deriv_err(d, r["deriv"]) < DERIV_RTOL
+
+
+def test_gpu_ex_entry_async_results_and_objective_only():
+    """torchain_ComputeChainObjfAndDeriv_ex: results to a device triple without a host sync, and
+    nnet_output_deriv = NULL (objective only, as Kaldi allows)."""
+    import torch
+    lib = _lib.load()
+    c = load_golden(GOLDEN[1])
+    g, s = handles(c["den"], c["sup"])
+    y = torch.from_numpy(np.ascontiguousarray(c["y"], dtype=np.float32)).cuda()
+    res_dev = torch.zeros(3, device="cuda")
+    ok = lib.torchain_ComputeChainObjfAndDeriv_ex(
+        g.ptr, s.ptr, y.data_ptr(), y.shape[0], y.shape[1], y.stride(0), None, res_dev.data_ptr(),
+        None, 0, None, 0, c["l2"], c["leaky"], 0.0, 1.0, 0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert ok == 1, _lib.last_error()
+    r = res_dev.cpu().numpy()
+    assert rel(r[0], c["objf"]) < OBJF_RTOL and r[2] == pytest.approx(c["weight"])
+    assert abs(r[1] - c["l2_term"]) <= OBJF_RTOL * max(abs(c["l2_term"]), 1e-30)
+
+
+def test_gpu_deriv_scale_and_repeatability():
+    """deriv_scale = -1 yields the negated derivative (what backward() returns); two calls agree to
+    rounding (the occupancy REDs make the summation order vary, nothing else)."""
+    import torch
+    lib = _lib.load()
+    c = synth.small_case(13)
+    g, s = handles(c["den"], c["sup"])
+    y = torch.from_numpy(c["y"]).cuda()
+    outs = []
+    for scale in (1.0, -1.0, -1.0):
+        d = torch.empty_like(y)
+        res = np.zeros(3, dtype=np.float32)
+        ok = lib.torchain_ComputeChainObjfAndDeriv_ex(
+            g.ptr, s.ptr, y.data_ptr(), y.shape[0], y.shape[1], y.stride(0), res.ctypes.data_as(ctypes.c_void_p), None,
+            d.data_ptr(), d.stride(0), None, 0, 0.01, 0.1, 0.0, scale, 0, None)
+        assert ok == 1, _lib.last_error()
+        outs.append(d.cpu().numpy().astype(np.float64))
+    assert np.abs(outs[0] + outs[1]).max() <= 1e-5 * np.abs(outs[0]).max()
+    assert np.abs(outs[1] - outs[2]).max() <= 1e-5 * np.abs(outs[0]).max()
