@@ -49,7 +49,7 @@ def main():
                                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         assert ok == 1, _lib.last_error()
 
-    for _ in range(3):
+    for _ in range(int(os.environ.get("TL_WARMUP", "3"))):
         step()
     lib.torchain_profile_enable(2 if os.environ.get("TL_TRACE") else 1)
     step()
