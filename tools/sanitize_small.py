@@ -1,0 +1,41 @@
+"""Small chain-loss calls for compute-sanitizer (memcheck / racecheck / synccheck):
+    compute-sanitizer --tool memcheck python tools/sanitize_small.py
+Covers V = 1, 2, 4 kernels, a split (heavy-tailed) graph and the host-buffer entry."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("TORCHAIN_SPLIT_CAP", "9")
+
+import torch  # noqa: E402
+from torchain_b200 import _lib, io, synth  # noqa: E402
+
+lib = _lib.load()
+for (B, T, N, P, hubs) in [(5, 4, 60, 17, 0), (40, 3, 80, 21, 1), (70, 3, 90, 33, 0)]:
+    den = synth.make_den_fst(B, N, P, mean_deg=3.0)
+    if hubs:
+        den = synth.add_hubs(den, hubs)
+    sup = synth.make_supervision(B + 1, den, B, T, num_paths=2)
+    y = synth.make_nnet_output(B + 2, B, T, P)
+    g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
+                                        den.final_cost, den.num_pdfs)
+    s = io.Supervision.from_arrays(sup.weight, B, T, P, sup.arc_begin, sup.arc_dst, sup.arc_label, sup.arc_cost,
+                                   sup.final_cost)
+    yt = torch.from_numpy(y).cuda()
+    d = torch.empty_like(yt)
+    x = torch.empty_like(yt)
+    res = np.zeros(3, dtype=np.float32)
+    ok = lib.my_lib_ComputeChainObjfAndDeriv(g.ptr, s.ptr, yt.data_ptr(), B * T, P, P, res.ctypes.data_as(ctypes.c_void_p),
+                                             d.data_ptr(), P, x.data_ptr(), P, 0.01, 0.1, 0.1, 0, None)
+    assert ok == 1, _lib.last_error()
+    torch.cuda.synchronize()
+    dh = np.empty_like(y)
+    ok = lib.torchain_ComputeChainObjfAndDeriv_host(g.ptr, s.ptr, y.ctypes.data_as(ctypes.c_void_p), B * T, P, P,
+                                                    res.ctypes.data_as(ctypes.c_void_p), dh.ctypes.data_as(ctypes.c_void_p),
+                                                    P, None, 0, 0.01, 0.1, 0.0, 0)
+    assert ok == 1, _lib.last_error()
+    print("ok", B, T, N, P, res, float(np.abs(dh - d.cpu().numpy()).max()))
