@@ -119,7 +119,8 @@ struct DenDevice {  // per (device) state
   // Partitions are never freed or overwritten while the handle lives: launches already
   // enqueued on other streams keep reading the generation they were given.
   std::vector<std::unique_ptr<DenPartition>> generations;
-  DenPartition* cur = nullptr;
+  DenPartition* cur = nullptr;              // subs = 1 (batches of 128+ sequences; autotuned)
+  DenPartition* cur_sub[2] = {nullptr, nullptr};  // subs = 2 / 4 (BP = 64 / 32), built on first use
   // measured relative speed of every (CTA, main warp) bin per direction; 1.0 until calibrated
   std::vector<double> speed[2];
   int calib_rounds_done = 0;
@@ -186,7 +187,7 @@ void lpt(const std::vector<int>& items, const std::vector<int>& cost, const std:
 // Partition one direction over grid CTAs x kDenMainWarps warps.
 //   dir 0: tasks = destination states with their in-arcs (other = source)
 //   dir 1: tasks = source states with their out-arcs     (other = destination)
-void build_dir(const DenGraph& g, int dir, int grid, const std::vector<double>& speed /* [grid*kDenMainWarps] */,
+void build_dir(const DenGraph& g, int dir, int grid, int bins_per_cta, const std::vector<double>& speed /* [grid*bins_per_cta] */,
                DirHost* out, std::vector<double>* work) {
   const int N = g.N, A = g.A;
   std::vector<int> deg(N, 0), begin(N + 1, 0);
@@ -226,9 +227,9 @@ void build_dir(const DenGraph& g, int dir, int grid, const std::vector<double>& 
   std::vector<std::vector<int>> by_cta;
   std::vector<double> cta_speed(grid, 0.0);
   for (int c = 0; c < grid; c++)
-    for (int w = 0; w < tb::kDenMainWarps; w++) cta_speed[c] += speed[c * tb::kDenMainWarps + w];
+    for (int w = 0; w < bins_per_cta; w++) cta_speed[c] += speed[c * bins_per_cta + w];
   lpt(all, cost, cta_speed, &by_cta);
-  work->assign((size_t)grid * tb::kDenMainWarps, 0.0);
+  work->assign((size_t)grid * bins_per_cta, 0.0);
 
   out->arcs.clear();
   out->tasks.clear();
@@ -240,14 +241,13 @@ void build_dir(const DenGraph& g, int dir, int grid, const std::vector<double>& 
   for (int c = 0; c < grid; c++) {
     std::vector<std::vector<int>> by_warp;
     lpt(by_cta[c], cost,
-        std::vector<double>(speed.begin() + c * tb::kDenMainWarps, speed.begin() + (c + 1) * tb::kDenMainWarps),
-        &by_warp);
+        std::vector<double>(speed.begin() + c * bins_per_cta, speed.begin() + (c + 1) * bins_per_cta), &by_warp);
     const int arc0 = (int)out->arcs.size(), task0 = (int)out->tasks.size();
-    for (int w = 0; w < tb::kDenMainWarps; w++) {
+    for (int w = 0; w < bins_per_cta; w++) {
       for (int it : by_warp[w]) {
         const Item& item = items[it];
         const int s = item.state;
-        (*work)[c * tb::kDenMainWarps + w] += cost[it];
+        (*work)[c * bins_per_cta + w] += cost[it];
         int4 tk;
         tk.x = s;
         tk.y = (int)out->arcs.size() - arc0;
@@ -746,12 +746,15 @@ Supervision* make_supervision(float weight, int32_t B, int32_t T, int32_t label_
 // ---------------------------------------------------------------------------
 // per-device preparation
 // ---------------------------------------------------------------------------
-// Build + upload one partition generation from the device's current speed estimates.
-int build_partition(DenGraph* g, DenDevice* d) {
+// Build + upload one partition generation: subs = 1 from the device's current speed estimates,
+// subs = 2 / 4 (one bin per lane group, small batches) with uniform speeds.
+int build_partition(DenGraph* g, DenDevice* d, int subs = 1) {
   auto part = std::make_unique<DenPartition>();
+  const int bins = tb::kDenMainWarps * subs;
+  const std::vector<double> uniform((size_t)d->grid * bins, 1.0);
   for (int dir = 0; dir < 2; dir++) {
     DirHost h;
-    build_dir(*g, dir, d->grid, d->speed[dir], &h, &part->work[dir]);
+    build_dir(*g, dir, d->grid, bins, subs == 1 ? d->speed[dir] : uniform, &h, &part->work[dir]);
     CUDA_OK(upload(part->arcs[dir], h.arcs));
     CUDA_OK(upload(part->tasks[dir], h.tasks));
     CUDA_OK(upload(part->cta_arc_off[dir], h.cta_arc_off));
@@ -762,7 +765,8 @@ int build_partition(DenGraph* g, DenDevice* d) {
     part->max_tasks_cta[dir] = h.max_tasks_cta;
     part->has_split = part->has_split || h.has_split;
   }
-  d->cur = part.get();
+  if (subs == 1) d->cur = part.get();
+  else d->cur_sub[subs == 2 ? 0 : 1] = part.get();
   d->generations.push_back(std::move(part));
   return 1;
 }
@@ -971,6 +975,7 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   np.arc_post = reinterpret_cast<float*>(nb + off_post);
   np.chain_logprob = reinterpret_cast<double*>(nb + off_clp);
 
+  tb::DenParams dp;
   // ---- denominator workspace; passes of at most kMaxBP sequences
   const int maxBP = pad_batch(std::min(B, tb::kMaxBP));
   CUDA_OK(ws->alpha.reserve(sizeof(float) * (size_t)(T + 1) * N * maxBP));
@@ -987,27 +992,34 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   char* zb = ws->zeroed.as<char>();
   CUDA_OK(cudaMemsetAsync(zb + z_scal, 0, 128, stream));
 
-  tb::DenParams dp;
-  DenPartition* part;
+  // the partition depends on the lane-group geometry of a pass (subs = 1, 2 or 4)
+  auto partition_for = [&](int subs, DenPartition** out) -> int {
+    std::lock_guard<std::mutex> lock(g->mu);
+    if (subs > 1 && dd->cur_sub[subs == 2 ? 0 : 1] == nullptr && !build_partition(g, dd, subs)) return 0;
+    *out = subs == 1 ? dd->cur : dd->cur_sub[subs == 2 ? 0 : 1];
+    return 1;
+  };
+  auto bind = [&](const DenPartition* part) {
+    for (int dir = 0; dir < 2; dir++) {
+      dp.dir[dir].arcs = part->arcs[dir].as<int4>();
+      dp.dir[dir].tasks = part->tasks[dir].as<int4>();
+      dp.dir[dir].cta_arc_off = part->cta_arc_off[dir].as<int>();
+      dp.dir[dir].cta_task_off = part->cta_task_off[dir].as<int>();
+      dp.dir[dir].warp_task_off = part->warp_task_off[dir].as<int>();
+      dp.dir[dir].warp_arc_off = part->warp_arc_off[dir].as<int>();
+      dp.dir[dir].max_arcs_cta = part->max_arcs_cta[dir];
+      dp.dir[dir].max_tasks_cta = part->max_tasks_cta[dir];
+    }
+    dp.has_split = part->has_split ? 1 : 0;
+  };
+  // only a synchronising single-pass call on the full-width partition can feed the autotuner
   bool calibrating;
   {
     std::lock_guard<std::mutex> lock(g->mu);
-    part = dd->cur;
-    // only a synchronising single-pass call can feed the autotuner
-    calibrating = dd->calib_rounds_done < kCalibRounds && results_host != nullptr && B <= tb::kMaxBP;
+    calibrating = B <= tb::kMaxBP && tb::den_subs(pad_batch(B)) == 1 && dd->calib_rounds_done < kCalibRounds &&
+                  results_host != nullptr;
   }
   dp.warp_busy = calibrating ? dd->warp_busy.as<unsigned long long>() : nullptr;
-  for (int dir = 0; dir < 2; dir++) {
-    dp.dir[dir].arcs = part->arcs[dir].as<int4>();
-    dp.dir[dir].tasks = part->tasks[dir].as<int4>();
-    dp.dir[dir].cta_arc_off = part->cta_arc_off[dir].as<int>();
-    dp.dir[dir].cta_task_off = part->cta_task_off[dir].as<int>();
-    dp.dir[dir].warp_task_off = part->warp_task_off[dir].as<int>();
-    dp.dir[dir].warp_arc_off = part->warp_arc_off[dir].as<int>();
-    dp.dir[dir].max_arcs_cta = part->max_arcs_cta[dir];
-    dp.dir[dir].max_tasks_cta = part->max_tasks_cta[dir];
-  }
-  dp.has_split = part->has_split ? 1 : 0;
   dp.N = N;
   dp.P = P;
   dp.Btot = B;
@@ -1057,6 +1069,10 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
     dp.seq0 = seq0;
     dp.B = std::min(B - seq0, tb::kMaxBP);
     dp.BP = pad_batch(dp.B);
+    dp.subs = tb::den_subs(dp.BP);
+    DenPartition* part = nullptr;
+    if (!partition_for(dp.subs, &part)) return 0;
+    bind(part);
     dp.arcs_in_smem = 1;
     if (tb::den_smem_bytes(dp) > 200 * 1024) dp.arcs_in_smem = 0;
     CUDA_OK(cudaMemsetAsync(zb, 0, z_end, stream));

@@ -29,8 +29,8 @@ struct DenDir {
   const int4* tasks;         // {state, arc_begin (relative to the CTA's slice), split flag (0 whole state, 2 first / 1 other sub-task of a split state), float_bits(pi[state])}
   const int* cta_arc_off;    // [grid+1]
   const int* cta_task_off;   // [grid+1]
-  const int* warp_task_off;  // [grid*kDenMainWarps+1] absolute task indices
-  const int* warp_arc_off;   // [grid*kDenMainWarps+1] absolute arc indices
+  const int* warp_task_off;  // [grid*kDenMainWarps*subs+1] absolute task indices, one bin per lane group
+  const int* warp_arc_off;   // [grid*kDenMainWarps*subs+1] absolute arc indices
   int max_arcs_cta;
   int max_tasks_cta;
 };
@@ -60,6 +60,7 @@ struct DenParams {
   float scale_gamma;  // deriv_scale * (-supervision.weight)
   float scale_y;      // deriv_scale * (-supervision.weight * l2_regularize)
   int arcs_in_smem;   // 1: arc slices staged in shared memory
+  int subs;           // lane groups per warp: 1 (BP >= 128), 2 (BP = 64), 4 (BP = 32); the partition has grid*kDenMainWarps*subs bins
   int has_split;      // 1: some states are dealt out as several sub-tasks (selects the SPLIT kernels)
   // numerator occupancies, subtracted from the occupancy tile by the backward launch so that the
   // flush writes w*gamma_num - w*gamma_den in one go (arcs ordered by frame)
@@ -87,6 +88,7 @@ size_t den_smem_bytes(const DenParams& p);
 // recurrence over all frames, phase 1 = backward (beta + derivative) recurrence.
 cudaError_t launch_den(const DenParams& p, int phase, int grid, cudaStream_t stream);
 int den_max_grid(int device);  // co-resident CTAs (one per SM)
+int den_subs(int BP);          // lane groups per warp for a padded batch size
 
 // ---------------------------------------------------------------------------
 // Numerator (batched supervision-FST forward-backward) + final pass

@@ -136,7 +136,7 @@ struct Smem {
 __device__ __forceinline__ Smem carve(unsigned char* base, const DenParams& p) {
   Smem s;
   s.red = reinterpret_cast<float*>(base);
-  size_t off = sizeof(float) * kDenMainWarps * p.BP;
+  size_t off = sizeof(float) * kDenMainWarps * p.subs * p.BP;
   s.tile = reinterpret_cast<float*>(base + off);
   off += sizeof(float) * kDenAuxWarps * 32 * 33;
   off = (off + 15) & ~size_t(15);
@@ -149,12 +149,16 @@ __device__ __forceinline__ Smem carve(unsigned char* base, const DenParams& p) {
 
 // CTA-level reduction of the main warps' per-sequence partial sums followed by
 // one fp64 atomic per sequence (148-way contention per address per frame).
-__device__ __forceinline__ void cta_reduce_to(const float* red, int BP, double* dst) {
+__device__ __forceinline__ void cta_reduce_to(const float* red, int BP, int rows, double* dst) {
   __syncthreads();
   for (int c = threadIdx.x; c < BP; c += kDenThreads) {
     float acc = 0.f;
+    if (rows == kDenMainWarps) {
 #pragma unroll
-    for (int w = 0; w < kDenMainWarps; w++) acc += red[w * BP + c];
+      for (int w = 0; w < kDenMainWarps; w++) acc += red[w * BP + c];
+    } else {
+      for (int w = 0; w < rows; w++) acc += red[w * BP + c];
+    }
     atomicAdd(dst + c, (double)acc);
   }
 }
@@ -302,7 +306,7 @@ struct GatherBuf {
 // the first, 1 for the others) that accumulate with REDs into a pre-zeroed row.  Everything is
 // linear in the arc sums, so nothing else changes.  It is a separate instantiation because the
 // mere presence of the RED path in the end-of-state block costs ~1.5 us per frame.
-template <int V, bool SPLIT>
+template <int V, int SUBS, bool SPLIT>
 __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __restrict__ arcs,
                                            const int4* __restrict__ tasks, int abeg, int aend, int tb, int t,
                                            float* red, int warp, int lane) {
@@ -314,14 +318,13 @@ __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __res
   const int4* __restrict__ a = arcs + abeg;
   const int n = aend - abeg;
   const unsigned rowbytes = (unsigned)BP * 4u;
-  for (int col = lane * V; col < BP; col += 32 * V) {
+  for (int col = (lane % (32 / SUBS)) * V; col < BP; col += (32 / SUBS) * V) {
     float lamS[V], invS[V], part[V], acc[V];
     double Sd[V];
 #pragma unroll
     for (int v = 0; v < V; v++) Sd[v] = __ldcg(Sprev + col + v);
     int task = tb;
-    // narrower sequence vectors leave registers for a proportionally deeper pipeline
-    constexpr int kSA = DEN_F_SA * (4 / V), kStages = DEN_F_STAGES;
+    constexpr int kSA = DEN_F_SA, kStages = DEN_F_STAGES;
     GatherBuf<V, kSA> ring[kStages];
     const float* const base_a = alpha_prev + col;
     const float* const base_e = et + col;
@@ -384,13 +387,13 @@ __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __res
       }
     }
 #pragma unroll
-    for (int v = 0; v < V; v++) red[warp * BP + col + v] = part[v];
+    for (int v = 0; v < V; v++) red[(warp * SUBS + lane / (32 / SUBS)) * BP + col + v] = part[v];
   }
 }
 
 // beta'_t(h,s) = (1/S_t(s)) * sum_{arcs h->j} p * e_t(pdf,s) * (beta'_{t+1}(j,s) + b_{t+1}(s))
 // gamma_t(pdf,s) += that term * alpha'_t(h,s) / S_t(s)
-template <int V, bool SPLIT>
+template <int V, int SUBS, bool SPLIT>
 __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __restrict__ arcs,
                                           const int4* __restrict__ tasks, int abeg, int aend, int tb, int te, int t,
                                           float* red, int warp, int lane, double& ab) {
@@ -408,7 +411,7 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
   const int4* __restrict__ a = arcs + abeg;
   const int n = aend - abeg;
   const unsigned rowbytes = (unsigned)BP * 4u;
-  for (int col = lane * V; col < BP; col += 32 * V) {
+  for (int col = (lane % (32 / SUBS)) * V; col < BP; col += (32 / SUBS) * V) {
     float lamS[V], invS[V], bv[V], part[V], X[V], occ[V], aln[V], al0[V];
     double Sd[V], Bd[V];
 #pragma unroll
@@ -420,7 +423,7 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
     }
     int task = tb;
     float pi_h = 0.f;
-    constexpr int kSA = DEN_B_SA * (4 / V), kStages = DEN_B_STAGES;
+    constexpr int kSA = DEN_B_SA, kStages = DEN_B_STAGES;
     GatherBuf<V, kSA> ring[kStages];
     const float* const base_b = beta_next + col;
     const float* const base_e = et + col;
@@ -512,22 +515,24 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
       }
     }
 #pragma unroll
-    for (int v = 0; v < V; v++) red[warp * BP + col + v] = part[v];
+    for (int v = 0; v < V; v++) red[(warp * SUBS + lane / (32 / SUBS)) * BP + col + v] = part[v];
   }
 }
 
-template <bool STAGED>
+template <bool STAGED, int SUBS>
 __device__ __forceinline__ void load_dir(const DenParams& p, int d, const Smem& sm, const int4*& arcs,
-                                         const int4*& tasks, int& tb, int& te, int& abeg, int& aend, int warp) {
+                                         const int4*& tasks, int& tb, int& te, int& abeg, int& aend, int warp,
+                                         int lane) {
   const DenDir& D = p.dir[d];
   const int task0 = D.cta_task_off[blockIdx.x], ntask = D.cta_task_off[blockIdx.x + 1] - task0;
   const int arc0 = D.cta_arc_off[blockIdx.x], narc = D.cta_arc_off[blockIdx.x + 1] - arc0;
   tb = te = abeg = aend = 0;
-  if (warp < kDenMainWarps) {
-    tb = D.warp_task_off[blockIdx.x * kDenMainWarps + warp] - task0;
-    te = D.warp_task_off[blockIdx.x * kDenMainWarps + warp + 1] - task0;
-    abeg = D.warp_arc_off[blockIdx.x * kDenMainWarps + warp] - arc0;
-    aend = D.warp_arc_off[blockIdx.x * kDenMainWarps + warp + 1] - arc0;
+  if (warp < kDenMainWarps) {  // one bin per lane group
+    const int bin = (blockIdx.x * kDenMainWarps + warp) * SUBS + lane / (32 / SUBS);
+    tb = D.warp_task_off[bin] - task0;
+    te = D.warp_task_off[bin + 1] - task0;
+    abeg = D.warp_arc_off[bin] - arc0;
+    aend = D.warp_arc_off[bin + 1] - arc0;
   }
   if constexpr (STAGED) {
     for (int i = threadIdx.x; i < ntask; i += kDenThreads) sm.tasks[i] = D.tasks[task0 + i];
@@ -544,8 +549,14 @@ __device__ __forceinline__ void load_dir(const DenParams& p, int d, const Smem& 
 // ------------------------------------------------------------------ kernel
 // PHASE 0: forward launch (prologue + T alpha frames + total log-likelihood).
 // PHASE 1: backward launch (beta prologue + T beta/derivative frames + last flush).
-template <int V, bool STAGED, int PHASE, bool SPLIT>
+// SUBS = 1: a warp handles one state for 128 sequences at a time (BP >= 128).  For smaller
+// batches the 32 lanes are split into SUBS = 2 or 4 groups of 16 / 8 lanes (BP = 64 / 32), each
+// walking its OWN arc stream with float4 vectors: the same instruction stream then covers SUBS
+// states at once, which is what small batches need (they are bound by per-warp instruction
+// latency, not by bandwidth).  All per-warp quantities below are simply per-lane-group values.
+template <int SUBS, bool STAGED, int PHASE, bool SPLIT>
 __device__ __forceinline__ void den_chain_body(const DenParams& p) {
+  constexpr int V = 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Smem sm = carve(smem_raw, p);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -609,14 +620,14 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
   unsigned* const barrier = p.barrier + 32 * PHASE;
   if (tl) tl += PHASE * (p.T + 3);
   stamp();
-  load_dir<STAGED>(p, PHASE, sm, arcs, tasks, tb, te, abeg, aend, warp);
+  load_dir<STAGED, SUBS>(p, PHASE, sm, arcs, tasks, tb, te, abeg, aend, warp, lane);
 
   if constexpr (PHASE == 0) {
   // ---- prologue: alpha_0 = pi, S_0; stage exp(y_0)
   if (is_aux) {
     aux_work(p, -1, 0, tile, auxw, lane, true, sumsq, false, gsum);
   } else {
-    for (int col = lane * V; col < BP; col += 32 * V) {
+    for (int col = (lane % (32 / SUBS)) * V; col < BP; col += (32 / SUBS) * V) {
       float part = 0.f;
       for (int task = tb; task < te; task++) {
         const int4 tk = tasks[task];
@@ -634,10 +645,10 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
         }
       }
 #pragma unroll
-      for (int v = 0; v < V; v++) sm.red[warp * BP + col + v] = part;
+      for (int v = 0; v < V; v++) sm.red[(warp * SUBS + lane / (32 / SUBS)) * BP + col + v] = part;
     }
   }
-  cta_reduce_to(sm.red, BP, p.Ssum);
+  cta_reduce_to(sm.red, BP, kDenMainWarps * SUBS, p.Ssum);
   grid_barrier(barrier, epoch);
   stamp();
 
@@ -647,11 +658,11 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
       if (t < T) aux_work(p, -1, t, tile, auxw, lane, true, sumsq, false, gsum);
     } else {
       const long long c0 = clock64();
-      alpha_step<V, SPLIT>(p, arcs, tasks, abeg, aend, tb, t, sm.red, warp, lane);
+      alpha_step<V, SUBS, SPLIT>(p, arcs, tasks, abeg, aend, tb, t, sm.red, warp, lane);
       busy += clock64() - c0;
     }
     trace_warp_done(t);
-    cta_reduce_to(sm.red, BP, p.Ssum + (size_t)t * BP);
+    cta_reduce_to(sm.red, BP, kDenMainWarps * SUBS, p.Ssum + (size_t)t * BP);
     grid_barrier(barrier, epoch);
     trace_frame_end(t);
     stamp();
@@ -680,7 +691,7 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
     const double* ST = p.Ssum + (size_t)T * BP;
     float* betaT = p.beta + (size_t)(T % 3) * p.N * BP;
     float* betaTm1 = p.beta + (size_t)((T + 2) % 3) * p.N * BP;  // buffer of step T-1
-    for (int col = lane * V; col < BP; col += 32 * V) {
+    for (int col = (lane % (32 / SUBS)) * V; col < BP; col += (32 / SUBS) * V) {
       float inv[V], part[V];
 #pragma unroll
       for (int v = 0; v < V; v++) {
@@ -703,10 +714,10 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
         }
       }
 #pragma unroll
-      for (int v = 0; v < V; v++) sm.red[warp * BP + col + v] = part[v];
+      for (int v = 0; v < V; v++) sm.red[(warp * SUBS + lane / (32 / SUBS)) * BP + col + v] = part[v];
     }
   }
-  cta_reduce_to(sm.red, BP, p.Bsum + (size_t)T * BP);
+  cta_reduce_to(sm.red, BP, kDenMainWarps * SUBS, p.Bsum + (size_t)T * BP);
   grid_barrier(barrier, epoch);
   stamp();
 
@@ -717,11 +728,11 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
         aux_work(p, t + 1 < T ? t + 1 : -1, t - 1, tile, auxw, lane, false, sumsq, false, gsum, t);
     } else {
       const long long c0 = clock64();
-      beta_step<V, SPLIT>(p, arcs, tasks, abeg, aend, tb, te, t, sm.red, warp, lane, ab);
+      beta_step<V, SUBS, SPLIT>(p, arcs, tasks, abeg, aend, tb, te, t, sm.red, warp, lane, ab);
       busy += clock64() - c0;
     }
     trace_warp_done(t);
-    cta_reduce_to(sm.red, BP, p.Bsum + (size_t)t * BP);
+    cta_reduce_to(sm.red, BP, kDenMainWarps * SUBS, p.Bsum + (size_t)t * BP);
     grid_barrier(barrier, epoch);
     if (p.deriv_progress && blockIdx.x == 0 && threadIdx.x == 0) {
       *reinterpret_cast<volatile unsigned*>(p.deriv_progress) = (unsigned)(T - 1 - t);
@@ -750,19 +761,19 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
 // The forward launch is capped at 112 registers/thread so that 8 K registers per SM stay free:
 // the numerator kernel (128 threads x 48 registers per CTA) can then run on the same SMs while
 // the forward recurrence is in flight.  The backward launch takes the whole register file.
-template <int V, bool STAGED, bool SPLIT>
+template <int SUBS, bool STAGED, bool SPLIT>
 __global__ void __maxnreg__(112) den_forward_kernel(const __grid_constant__ DenParams p) {
-  den_chain_body<V, STAGED, 0, SPLIT>(p);
+  den_chain_body<SUBS, STAGED, 0, SPLIT>(p);
 }
-template <int V, bool STAGED, bool SPLIT>
+template <int SUBS, bool STAGED, bool SPLIT>
 __global__ void __launch_bounds__(kDenThreads, 1) den_backward_kernel(const __grid_constant__ DenParams p) {
-  den_chain_body<V, STAGED, 1, SPLIT>(p);
+  den_chain_body<SUBS, STAGED, 1, SPLIT>(p);
 }
 
-template <int V, bool STAGED, bool SPLIT>
+template <int SUBS, bool STAGED, bool SPLIT>
 cudaError_t launch_t(const DenParams& p, int phase, int grid, size_t smem, cudaStream_t stream) {
   void (*kern)(DenParams) =
-      phase == 0 ? den_forward_kernel<V, STAGED, SPLIT> : den_backward_kernel<V, STAGED, SPLIT>;
+      phase == 0 ? den_forward_kernel<SUBS, STAGED, SPLIT> : den_backward_kernel<SUBS, STAGED, SPLIT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   void* args[] = {const_cast<DenParams*>(&p)};
@@ -771,16 +782,18 @@ cudaError_t launch_t(const DenParams& p, int phase, int grid, size_t smem, cudaS
   return e;
 }
 
-template <int V, bool STAGED>
+template <int SUBS, bool STAGED>
 cudaError_t launch_p(const DenParams& p, int phase, int grid, size_t smem, cudaStream_t stream) {
-  return p.has_split ? launch_t<V, STAGED, true>(p, phase, grid, smem, stream)
-                     : launch_t<V, STAGED, false>(p, phase, grid, smem, stream);
+  return p.has_split ? launch_t<SUBS, STAGED, true>(p, phase, grid, smem, stream)
+                     : launch_t<SUBS, STAGED, false>(p, phase, grid, smem, stream);
 }
 
 }  // namespace
 
+int den_subs(int BP) { return BP >= 128 ? 1 : (BP >= 64 ? 2 : 4); }
+
 size_t den_smem_bytes(const DenParams& p) {
-  size_t off = sizeof(float) * kDenMainWarps * p.BP;
+  size_t off = sizeof(float) * kDenMainWarps * p.subs * p.BP;
   off += sizeof(float) * kDenAuxWarps * 32 * 33;
   off = (off + 15) & ~size_t(15);
   if (p.arcs_in_smem) {
@@ -798,15 +811,15 @@ int den_max_grid(int device) {
 
 cudaError_t launch_den(const DenParams& p, int phase, int grid, cudaStream_t stream) {
   const size_t smem = den_smem_bytes(p);
-  const int vec = p.BP >= 128 ? 4 : (p.BP >= 64 ? 2 : 1);
+  if (p.subs != den_subs(p.BP)) return cudaErrorInvalidValue;
   if (p.arcs_in_smem) {
-    if (vec == 4) return launch_p<4, true>(p, phase, grid, smem, stream);
-    if (vec == 2) return launch_p<2, true>(p, phase, grid, smem, stream);
-    return launch_p<1, true>(p, phase, grid, smem, stream);
+    if (p.subs == 1) return launch_p<1, true>(p, phase, grid, smem, stream);
+    if (p.subs == 2) return launch_p<2, true>(p, phase, grid, smem, stream);
+    return launch_p<4, true>(p, phase, grid, smem, stream);
   }
-  if (vec == 4) return launch_p<4, false>(p, phase, grid, smem, stream);
-  if (vec == 2) return launch_p<2, false>(p, phase, grid, smem, stream);
-  return launch_p<1, false>(p, phase, grid, smem, stream);
+  if (p.subs == 1) return launch_p<1, false>(p, phase, grid, smem, stream);
+  if (p.subs == 2) return launch_p<2, false>(p, phase, grid, smem, stream);
+  return launch_p<4, false>(p, phase, grid, smem, stream);
 }
 
 }  // namespace tb
