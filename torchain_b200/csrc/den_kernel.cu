@@ -9,22 +9,25 @@
 // /root/reference/src/my_lib_chain.cpp:129-131.  Algorithm restated in
 // SURVEY.md Appendix A.2; nothing here is derived from Kaldi's CUDA code.
 //
-// Design (DESIGN.md "Kernels"):
-//  * ONE launch for all 2T+3 phases; one CTA per SM; phases separated by a
-//    software grid barrier (cooperative launch guarantees co-residency).
-//  * HMM states are partitioned over CTAs x warps by a host-side LPT schedule
-//    (balanced by arc count); each CTA keeps its arc/task slice in shared memory.
-//  * Sequences are innermost: a warp handles one state for 32*V sequences, so
-//    every gather of alpha / beta / exp(y) is one coalesced 128*V-byte row.
-//  * exp(y) is produced on the fly, one frame ahead, by "aux" warps that
-//    transpose frame t of nnet_output into an L2-resident [pdf][seq] tile;
-//    the same warps transpose the finished occupancy tile of frame t+1 out to
-//    nnet_output_deriv (scaled, with the l2 term) during the backward pass.
-//  * Leaky-HMM mixing is applied by the consumer (alpha' = alpha + leaky*pi*S),
-//    so a frame needs ONE grid barrier; the per-frame normalisers S_t and the
-//    leaky beta sums are CTA-reduced and then accumulated with fp64 atomics.
-//  * Occupancies are accumulated with vectorised red.global.add.f32 into the
-//    L2-resident tile: no separate scatter kernel, no transposed deriv copy.
+// Design:
+//  * TWO launches per pass, forward (alpha) and backward (beta + derivative); each runs all its
+//    frames inside, one CTA per SM, frames separated by a software grid barrier (cooperative
+//    launch guarantees co-residency).  The forward launch leaves 8 K registers per SM free so the
+//    numerator kernel (num_kernel.cu) runs next to it.
+//  * HMM states are dealt to CTA x warp bins by a host-side LPT schedule (balanced by arc count,
+//    re-balanced from measured per-warp busy cycles); each CTA keeps its arc/task slice in
+//    shared memory.  States with very many arcs are split into RED-accumulating sub-tasks.
+//  * Sequences are innermost: a lane group handles one state for 4 x (lanes in the group)
+//    sequences, so every gather of alpha / beta / exp(y) is one coalesced row segment.
+//  * exp(y) is produced on the fly, one frame ahead, by "aux" warps that transpose frame t of
+//    nnet_output into an L2-resident [pdf][seq] tile; in the backward launch the same warps
+//    subtract the numerator occupancies from the occupancy tile and transpose the finished tile
+//    of frame t+1 out to nnet_output_deriv (scaled, with the l2 term): one write per element.
+//  * Leaky-HMM mixing is applied by the consumer (alpha' = alpha + leaky*pi*S), so a frame needs
+//    ONE grid barrier; the per-frame normalisers S_t and the leaky beta sums are CTA-reduced
+//    and then accumulated with fp64 atomics.
+//  * Denominator occupancies are accumulated with vectorised red.global.add.f32 into the
+//    L2-resident tile: no separate scatter kernel, no transposed derivative copy.
 
 #include "chain_kernels.h"
 

@@ -130,7 +130,7 @@ def make_supervision(seed, den, num_sequences, frames_per_sequence, num_paths=4,
         q = den.dst[a].astype(np.int64)
 
     den_cost = den.cost.astype(np.float64)
-    states_final = []   # merged FST, built sequence by sequence
+    # merged FST, built sequence by sequence
     arc_src, arc_dst, arc_lab, arc_cost = [], [], [], []
     n_states = 1        # state 0 = global start
     prev_finals = None  # merged ids of the previous sequence's last-level states
