@@ -976,18 +976,20 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   np.chain_logprob = reinterpret_cast<double*>(nb + off_clp);
 
   tb::DenParams dp;
-  // ---- denominator workspace; passes of at most kMaxBP sequences
-  const int maxBP = pad_batch(std::min(B, tb::kMaxBP));
-  CUDA_OK(ws->alpha.reserve(sizeof(float) * (size_t)(T + 1) * N * maxBP));
-  CUDA_OK(ws->beta.reserve(sizeof(float) * (size_t)3 * N * maxBP));
-  const size_t tile_floats = (size_t)2 * P * maxBP;
-  CUDA_OK(ws->tiles.reserve(sizeof(float) * tile_floats));  // etile
-  // zeroed block: gtile | Ssum | Bsum | barriers | timeline ;  scalars + results live after it
-  const size_t z_gtile = 0, z_S = align_up(z_gtile + 4 * tile_floats, 256),
-               z_B = align_up(z_S + 8 * (size_t)(T + 1) * maxBP, 256),
-               z_bar = align_up(z_B + 8 * (size_t)(T + 1) * maxBP, 256),
-               z_tl = z_bar + 256, z_end = align_up(z_tl + 8 * (size_t)(2 * T + 8), 256),
-               z_scal = z_end, z_res = z_scal + 64, z_total = z_res + 64;
+  // ---- denominator workspace.  A launch pair covers up to kMaxBP = 256 sequences as one or two
+  // contexts of kCtxBP = 128 (own buffers each); larger minibatches run as consecutive passes.
+  const int nctx_max = B > tb::kCtxBP ? 2 : 1;
+  const int BPmax = B > tb::kCtxBP ? tb::kCtxBP : pad_batch(B);
+  const size_t alpha_ctx = (size_t)(T + 1) * N * BPmax, beta_ctx = (size_t)3 * N * BPmax,
+               tile_ctx = (size_t)2 * P * BPmax;
+  CUDA_OK(ws->alpha.reserve(sizeof(float) * alpha_ctx * nctx_max));
+  CUDA_OK(ws->beta.reserve(sizeof(float) * beta_ctx * nctx_max));
+  CUDA_OK(ws->tiles.reserve(sizeof(float) * tile_ctx * nctx_max));  // etile
+  // zeroed block: per context {gtile | Ssum | Bsum | barriers}, then the timeline; scalars + results after it
+  const size_t zc_S = align_up(4 * tile_ctx, 256), zc_B = align_up(zc_S + 8 * (size_t)(T + 1) * BPmax, 256),
+               zc_bar = align_up(zc_B + 8 * (size_t)(T + 1) * BPmax, 256), zc_size = zc_bar + 256,
+               z_tl = zc_size * nctx_max, z_end = align_up(z_tl + 8 * (size_t)(2 * T + 8), 256), z_scal = z_end,
+               z_res = z_scal + 64, z_total = z_res + 64;
   CUDA_OK(ws->zeroed.reserve(z_total));
   char* zb = ws->zeroed.as<char>();
   CUDA_OK(cudaMemsetAsync(zb + z_scal, 0, 128, stream));
@@ -1016,7 +1018,7 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   bool calibrating;
   {
     std::lock_guard<std::mutex> lock(g->mu);
-    calibrating = B <= tb::kMaxBP && tb::den_subs(pad_batch(B)) == 1 && dd->calib_rounds_done < kCalibRounds &&
+    calibrating = B <= tb::kMaxBP && tb::den_subs(BPmax) == 1 && dd->calib_rounds_done < kCalibRounds &&
                   results_host != nullptr;
   }
   dp.warp_busy = calibrating ? dd->warp_busy.as<unsigned long long>() : nullptr;
@@ -1028,13 +1030,6 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   dp.ystride = ystride;
   dp.deriv = deriv;
   dp.dstride = dstride;
-  dp.alpha = ws->alpha.as<float>();
-  dp.beta = ws->beta.as<float>();
-  dp.etile = ws->tiles.as<float>();
-  dp.gtile = reinterpret_cast<float*>(zb + z_gtile);
-  dp.Ssum = reinterpret_cast<double*>(zb + z_S);
-  dp.Bsum = reinterpret_cast<double*>(zb + z_B);
-  dp.barrier = reinterpret_cast<unsigned*>(zb + z_bar);
   dp.scalars = reinterpret_cast<double*>(zb + z_scal);
   dp.leaky = leaky;
   dp.sum_pi = (float)g->sum_pi;
@@ -1048,10 +1043,6 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   dp.y_ready = chunked.flags;
   dp.y_chunk_frames = chunked.chunk_frames;
   dp.deriv_progress = (B <= tb::kMaxBP) ? chunked.deriv_progress : nullptr;
-  {
-    const char* dbg = getenv("TORCHAIN_DEBUG_FLAGS");
-    dp.debug_flags = dbg ? atoi(dbg) : 0;
-  }
   dp.cta_trace = nullptr;
   if (g_profile.load() >= 2) {
     const size_t tb_bytes = sizeof(unsigned long long) * 2 * (size_t)(T + 1) * dd->grid * (4 + tb::kDenWarps);
@@ -1061,20 +1052,40 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
     ws->trace_frames = T + 1;
     ws->trace_grid = dd->grid;
   }
+  {
+    const char* dbg = getenv("TORCHAIN_DEBUG_FLAGS");
+    dp.debug_flags = dbg ? atoi(dbg) : 0;
+  }
   dp.timeline = g_profile.load() ? reinterpret_cast<unsigned long long*>(zb + z_tl) : nullptr;
   ws->timeline_dev = zb + z_tl;
   ws->timeline_len = 2 * T + 6;
   bool numerator_done = false;
   for (int seq0 = 0; seq0 < B; seq0 += tb::kMaxBP) {
-    dp.seq0 = seq0;
-    dp.B = std::min(B - seq0, tb::kMaxBP);
-    dp.BP = pad_batch(dp.B);
+    const int pass_B = std::min(B - seq0, tb::kMaxBP);
+    tb::DenBatch batch;
+    batch.nctx = pass_B > tb::kCtxBP ? 2 : 1;
+    dp.BP = batch.nctx == 2 ? tb::kCtxBP : pad_batch(pass_B);
     dp.subs = tb::den_subs(dp.BP);
     DenPartition* part = nullptr;
     if (!partition_for(dp.subs, &part)) return 0;
     bind(part);
     dp.arcs_in_smem = 1;
     if (tb::den_smem_bytes(dp) > 200 * 1024) dp.arcs_in_smem = 0;
+    for (int ci = 0; ci < 2; ci++) {
+      tb::DenParams& c = batch.c[ci];
+      c = dp;
+      const int cc = std::min(ci, batch.nctx - 1);  // an unused second slot mirrors the first
+      c.seq0 = seq0 + cc * tb::kCtxBP;
+      c.B = batch.nctx == 2 ? std::min(pass_B - cc * tb::kCtxBP, tb::kCtxBP) : pass_B;
+      c.alpha = ws->alpha.as<float>() + alpha_ctx * cc;
+      c.beta = ws->beta.as<float>() + beta_ctx * cc;
+      c.etile = ws->tiles.as<float>() + tile_ctx * cc;
+      char* zc = zb + zc_size * cc;
+      c.gtile = reinterpret_cast<float*>(zc);
+      c.Ssum = reinterpret_cast<double*>(zc + zc_S);
+      c.Bsum = reinterpret_cast<double*>(zc + zc_B);
+      c.barrier = reinterpret_cast<unsigned*>(zc + zc_bar);
+    }
     CUDA_OK(cudaMemsetAsync(zb, 0, z_end, stream));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_profile.load()) {
@@ -1095,12 +1106,12 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
       CUDA_OK(tb::launch_numerator(np, ws->side));
       CUDA_OK(cudaEventRecord(ws->ev_join, ws->side));
     }
-    CUDA_OK(tb::launch_den(dp, 0, dd->grid, stream));
+    CUDA_OK(tb::launch_den(batch, 0, dd->grid, stream));
     if (!numerator_done) {
       CUDA_OK(cudaStreamWaitEvent(stream, ws->ev_join, 0));
       numerator_done = true;
     }
-    CUDA_OK(tb::launch_den(dp, 1, dd->grid, stream));
+    CUDA_OK(tb::launch_den(batch, 1, dd->grid, stream));
     if (e0) {
       CUDA_OK(cudaEventRecord(e1, stream));
       std::lock_guard<std::mutex> lock(g->mu);

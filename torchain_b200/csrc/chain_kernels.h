@@ -19,7 +19,8 @@ constexpr int kDenThreads = DEN_THREADS;       // threads per CTA (one CTA per S
 constexpr int kDenWarps = kDenThreads / 32;
 constexpr int kDenAuxWarps = DEN_AUX_WARPS;                // staging (transpose+exp) / derivative write-out warps
 constexpr int kDenMainWarps = kDenWarps - kDenAuxWarps;
-constexpr int kMaxBP = 256;                    // padded sequences per kernel pass
+constexpr int kCtxBP = 128;                    // sequences per context (lane width of the full-size kernels)
+constexpr int kMaxBP = 256;                    // sequences per launch pair: two contexts of kCtxBP
 
 // One direction of the graph, partitioned over `grid` CTAs x kDenMainWarps warps.
 //   dir 0 ("alpha"): tasks are destination states, arcs are their in-arcs
@@ -83,10 +84,17 @@ struct DenParams {
   unsigned long long* timeline;  // optional: globaltimer at every phase boundary (2T+5 entries), or null
 };
 
+// One launch carries one or two independent sequence groups ("contexts") of the same geometry;
+// c[i] differ only in B, seq0 and their buffers (alpha, beta, etile, gtile, Ssum, Bsum, barrier).
+struct DenBatch {
+  DenParams c[2];
+  int nctx;
+};
+
 size_t den_smem_bytes(const DenParams& p);
 // Enqueues one persistent launch (cooperative, `grid` CTAs): phase 0 = forward (alpha)
 // recurrence over all frames, phase 1 = backward (beta + derivative) recurrence.
-cudaError_t launch_den(const DenParams& p, int phase, int grid, cudaStream_t stream);
+cudaError_t launch_den(const DenBatch& b, int phase, int grid, cudaStream_t stream);
 int den_max_grid(int device);  // co-resident CTAs (one per SM)
 int den_subs(int BP);          // lane groups per warp for a padded batch size
 

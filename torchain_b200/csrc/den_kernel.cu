@@ -552,29 +552,38 @@ __device__ __forceinline__ void load_dir(const DenParams& p, int d, const Smem& 
 // ------------------------------------------------------------------ kernel
 // PHASE 0: forward launch (prologue + T alpha frames + total log-likelihood).
 // PHASE 1: backward launch (beta prologue + T beta/derivative frames + last flush).
-// SUBS = 1: a warp handles one state for 128 sequences at a time (BP >= 128).  For smaller
+// SUBS = 1: a warp handles one state for 128 sequences at a time (BP = 128).  For smaller
 // batches the 32 lanes are split into SUBS = 2 or 4 groups of 16 / 8 lanes (BP = 64 / 32), each
 // walking its OWN arc stream with float4 vectors: the same instruction stream then covers SUBS
 // states at once, which is what small batches need (they are bound by per-warp instruction
 // latency, not by bandwidth).  All per-warp quantities below are simply per-lane-group values.
-template <int SUBS, bool STAGED, int PHASE, bool SPLIT>
-__device__ __forceinline__ void den_chain_body(const DenParams& p) {
+//
+// NCTX = 2: the launch carries TWO independent sequence groups ("contexts", 128 sequences each,
+// own alpha/beta/tile/sum buffers and own barrier counter) and alternates between them frame by
+// frame: a CTA arrives at the barrier of context A's frame t, works on context B's frame t, and
+// only then waits for A -- barrier latency and the other CTAs' finish-time spread are hidden
+// behind useful work.  With NCTX = 1 arrive and wait are back to back (a plain grid barrier).
+template <int SUBS, bool STAGED, int PHASE, bool SPLIT, int NCTX>
+__device__ __forceinline__ void den_chain_body(const DenBatch& batch) {
   constexpr int V = 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const Smem sm = carve(smem_raw, p);
+  const DenParams& p0 = batch.c[0];  // geometry, graph and options are common to all contexts
+  const Smem sm = carve(smem_raw, p0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool is_aux = warp >= kDenMainWarps;
   const int auxw = warp - kDenMainWarps;
   float* tile = sm.tile + (is_aux ? auxw : 0) * 32 * 33;
-  const int BP = p.BP, T = p.T;
-  unsigned epoch = 0;
+  const int BP = p0.BP, T = p0.T;
+  unsigned epoch[NCTX];
+#pragma unroll
+  for (int ci = 0; ci < NCTX; ci++) epoch[ci] = 0;
   double sumsq = 0.0, ab = 0.0, gsum = 0.0;
   long long busy = 0;  // SM cycles this warp spent on its per-frame work (lane 0 only)
 
   const int4* arcs;
   const int4* tasks;
   int tb, te, abeg, aend;
-  unsigned long long* tl = (p.timeline && blockIdx.x == 0 && threadIdx.x == 0) ? p.timeline : nullptr;
+  unsigned long long* tl = (p0.timeline && blockIdx.x == 0 && threadIdx.x == 0) ? p0.timeline : nullptr;
   int tli = 0;
   auto stamp = [&]() {
     if (tl) {
@@ -583,16 +592,16 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
       tl[tli++] = ns;
     }
   };
-  // debug trace (torchain_profile_enable(2)): slots = earliest / latest main-warp finish,
-  // latest aux-warp finish, grid-barrier exit; combined per CTA through shared-memory min/max
+  // debug trace (torchain_profile_enable(2), single context only): slots = earliest / latest
+  // main-warp finish, latest aux-warp finish, grid-barrier exit; combined per CTA in shared memory
   __shared__ unsigned long long s_trace[3];
   auto trace_warp_done = [&](int frame) {
-    if (p.cta_trace && lane == 0) {
+    if (NCTX == 1 && p0.cta_trace && lane == 0) {
       unsigned long long ns;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
       // per-warp finish times live after the [2][T+1][grid][4] block
-      p.cta_trace[(size_t)2 * (p.T + 1) * gridDim.x * 4 +
-                  (((size_t)PHASE * (p.T + 1) + frame) * gridDim.x + blockIdx.x) * kDenWarps + warp] = ns;
+      p0.cta_trace[(size_t)2 * (T + 1) * gridDim.x * 4 +
+                   (((size_t)PHASE * (T + 1) + frame) * gridDim.x + blockIdx.x) * kDenWarps + warp] = ns;
       if (is_aux) {
         atomicMax(&s_trace[2], ns);
       } else {
@@ -601,11 +610,11 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
       }
     }
   };
-  auto trace_frame_end = [&](int frame) {  // thread 0, after the grid barrier
-    if (p.cta_trace && threadIdx.x == 0) {
+  auto trace_frame_end = [&](int frame) {  // thread 0, after the grid barrier of `frame`
+    if (NCTX == 1 && p0.cta_trace && threadIdx.x == 0) {
       unsigned long long ns;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-      unsigned long long* out = p.cta_trace + (((size_t)PHASE * (p.T + 1) + frame) * gridDim.x + blockIdx.x) * 4;
+      unsigned long long* out = p0.cta_trace + (((size_t)PHASE * (T + 1) + frame) * gridDim.x + blockIdx.x) * 4;
       out[0] = s_trace[0];
       out[1] = s_trace[1];
       out[2] = s_trace[2];
@@ -620,143 +629,194 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
     s_trace[1] = 0ull;
     s_trace[2] = 0ull;
   }
-  unsigned* const barrier = p.barrier + 32 * PHASE;
-  if (tl) tl += PHASE * (p.T + 3);
+  // split grid barrier: arrive() publishes this CTA's work on context ci, wait() blocks until
+  // every CTA has arrived there
+  auto arrive = [&](int ci) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      epoch[ci] += gridDim.x;
+      __threadfence();  // release everything this CTA wrote (cumulative over the bar.sync above)
+      atomicAdd(batch.c[ci].barrier + 32 * PHASE, 1u);
+    }
+  };
+  auto wait = [&](int ci) {
+    if (threadIdx.x == 0) {
+      const unsigned* ctr = batch.c[ci].barrier + 32 * PHASE;
+      while (ld_acquire(ctr) < epoch[ci]) {
+      }
+    }
+    __syncthreads();
+  };
+  if (tl) tl += PHASE * (T + 3);
   stamp();
-  load_dir<STAGED, SUBS>(p, PHASE, sm, arcs, tasks, tb, te, abeg, aend, warp, lane);
+  load_dir<STAGED, SUBS>(p0, PHASE, sm, arcs, tasks, tb, te, abeg, aend, warp, lane);
 
   if constexpr (PHASE == 0) {
-  // ---- prologue: alpha_0 = pi, S_0; stage exp(y_0)
-  if (is_aux) {
-    aux_work(p, -1, 0, tile, auxw, lane, true, sumsq, false, gsum);
-  } else {
-    for (int col = (lane % (32 / SUBS)) * V; col < BP; col += (32 / SUBS) * V) {
-      float part = 0.f;
-      for (int task = tb; task < te; task++) {
-        const int4 tk = tasks[task];
-        const float pi_h = __int_as_float(tk.w);
-        if (SPLIT && tk.z == 1) continue;  // secondary sub-task of a split state: its first one does the set-up
-        float out[V];
+    // ---- prologue: alpha_0 = pi, S_0; stage exp(y_0)
 #pragma unroll
-        for (int v = 0; v < V; v++) out[v] = pi_h;
-        st_vec<V>(p.alpha + tk.x * BP + col, out);
-        part += pi_h;
-        if (SPLIT && tk.z == 2) {  // rows of frames 1..T are accumulated with REDs: clear them
+    for (int ci = 0; ci < NCTX; ci++) {
+      const DenParams& p = batch.c[ci];
+      if (is_aux) {
+        aux_work(p, -1, 0, tile, auxw, lane, true, sumsq, false, gsum);
+      } else {
+        for (int col = (lane % (32 / SUBS)) * V; col < BP; col += (32 / SUBS) * V) {
+          float part = 0.f;
+          for (int task = tb; task < te; task++) {
+            const int4 tk = tasks[task];
+            const float pi_h = __int_as_float(tk.w);
+            if (SPLIT && tk.z == 1) continue;  // secondary sub-task of a split state: its first one does the set-up
+            float out[V];
 #pragma unroll
-          for (int v = 0; v < V; v++) out[v] = 0.f;
-          for (int tt = 1; tt <= T; tt++) st_vec<V>(p.alpha + ((size_t)tt * p.N + tk.x) * BP + col, out);
+            for (int v = 0; v < V; v++) out[v] = pi_h;
+            st_vec<V>(p.alpha + tk.x * BP + col, out);
+            part += pi_h;
+            if (SPLIT && tk.z == 2) {  // rows of frames 1..T are accumulated with REDs: clear them
+#pragma unroll
+              for (int v = 0; v < V; v++) out[v] = 0.f;
+              for (int tt = 1; tt <= T; tt++) st_vec<V>(p.alpha + ((size_t)tt * p.N + tk.x) * BP + col, out);
+            }
+          }
+#pragma unroll
+          for (int v = 0; v < V; v++) sm.red[(warp * SUBS + lane / (32 / SUBS)) * BP + col + v] = part;
         }
       }
-#pragma unroll
-      for (int v = 0; v < V; v++) sm.red[(warp * SUBS + lane / (32 / SUBS)) * BP + col + v] = part;
+      cta_reduce_to(sm.red, BP, kDenMainWarps * SUBS, p.Ssum);
+      arrive(ci);
     }
-  }
-  cta_reduce_to(sm.red, BP, kDenMainWarps * SUBS, p.Ssum);
-  grid_barrier(barrier, epoch);
-  stamp();
 
-  // ---- forward
-  for (int t = 1; t <= T; t++) {
-    if (is_aux) {
-      if (t < T) aux_work(p, -1, t, tile, auxw, lane, true, sumsq, false, gsum);
-    } else {
-      const long long c0 = clock64();
-      alpha_step<V, SUBS, SPLIT>(p, arcs, tasks, abeg, aend, tb, t, sm.red, warp, lane);
-      busy += clock64() - c0;
+    // ---- forward
+    for (int t = 1; t <= T; t++) {
+#pragma unroll
+      for (int ci = 0; ci < NCTX; ci++) {
+        const DenParams& p = batch.c[ci];
+        wait(ci);  // frame t-1 of this context is complete everywhere
+        if (ci == 0) {
+          if (t > 1) trace_frame_end(t - 1);
+          stamp();
+        }
+        if (is_aux) {
+          if (t < T) aux_work(p, -1, t, tile, auxw, lane, true, sumsq, false, gsum);
+        } else {
+          const long long c0 = clock64();
+          alpha_step<V, SUBS, SPLIT>(p, arcs, tasks, abeg, aend, tb, t, sm.red, warp, lane);
+          busy += clock64() - c0;
+        }
+        trace_warp_done(t);
+        cta_reduce_to(sm.red, BP, kDenMainWarps * SUBS, p.Ssum + (size_t)t * BP);
+        arrive(ci);
+      }
     }
-    trace_warp_done(t);
-    cta_reduce_to(sm.red, BP, kDenMainWarps * SUBS, p.Ssum + (size_t)t * BP);
-    grid_barrier(barrier, epoch);
-    trace_frame_end(t);
+#pragma unroll
+    for (int ci = 0; ci < NCTX; ci++) wait(ci);
+    trace_frame_end(T);
     stamp();
-  }
-  if (is_aux) {
-    sumsq = warp_sum(sumsq);
-    if (lane == 0 && sumsq != 0.0) atomicAdd(p.scalars + 3, sumsq);
-  }
-  if (blockIdx.x == 0) {
-    // ComputeTotLogLike: sum_s log(sum_h alpha'_T(h,s)) + sum_{t<T} sum_s log S_t(s)
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < (T + 1) * BP; i += kDenThreads) {
-      const int t = i / BP, s = i - t * BP;
-      if (s < p.B) {
-        float S = (float)__ldcg(p.Ssum + i);
-        if (t == T) S = S * (1.0f + p.leaky * p.sum_pi);
-        acc += log((double)S);
-      }
+    if (is_aux) {
+      sumsq = warp_sum(sumsq);
+      if (lane == 0 && sumsq != 0.0) atomicAdd(p0.scalars + 3, sumsq);
     }
-    acc = warp_sum(acc);
-    if (lane == 0) atomicAdd(p.scalars + 2, acc);
-  }
-  } else {
-  // ---- backward prologue: beta'_T(h,s) = 1 / sum_h alpha'_T(h,s) = 1 / (S_T (1 + leaky*sum_pi))
-  if (!is_aux) {
-    const double* ST = p.Ssum + (size_t)T * BP;
-    float* betaT = p.beta + (size_t)(T % 3) * p.N * BP;
-    float* betaTm1 = p.beta + (size_t)((T + 2) % 3) * p.N * BP;  // buffer of step T-1
-    for (int col = (lane % (32 / SUBS)) * V; col < BP; col += (32 / SUBS) * V) {
-      float inv[V], part[V];
+    if (blockIdx.x == 0) {
+      // ComputeTotLogLike: sum_s log(sum_h alpha'_T(h,s)) + sum_{t<T} sum_s log S_t(s)
+      double acc = 0.0;
 #pragma unroll
-      for (int v = 0; v < V; v++) {
-        const float S = (float)__ldcg(ST + col + v);
-        inv[v] = 1.0f / (S * (1.0f + p.leaky * p.sum_pi));
-        part[v] = 0.f;
-      }
-      for (int task = tb; task < te; task++) {
-        const int4 tk = tasks[task];
-        const float pi_h = __int_as_float(tk.w);
-        if (SPLIT && tk.z == 1) continue;
-        st_vec<V>(betaT + tk.x * BP + col, inv);
-#pragma unroll
-        for (int v = 0; v < V; v++) part[v] = fmaf(pi_h, inv[v], part[v]);
-        if (SPLIT && tk.z == 2) {
-          float zero[V];
-#pragma unroll
-          for (int v = 0; v < V; v++) zero[v] = 0.f;
-          st_vec<V>(betaTm1 + tk.x * BP + col, zero);
+      for (int ci = 0; ci < NCTX; ci++) {
+        const DenParams& p = batch.c[ci];
+        for (int i = threadIdx.x; i < (T + 1) * BP; i += kDenThreads) {
+          const int t = i / BP, s = i - t * BP;
+          if (s < p.B) {
+            float S = (float)__ldcg(p.Ssum + i);
+            if (t == T) S = S * (1.0f + p.leaky * p.sum_pi);
+            acc += log((double)S);
+          }
         }
       }
-#pragma unroll
-      for (int v = 0; v < V; v++) sm.red[(warp * SUBS + lane / (32 / SUBS)) * BP + col + v] = part[v];
+      acc = warp_sum(acc);
+      if (lane == 0) atomicAdd(p0.scalars + 2, acc);
     }
-  }
-  cta_reduce_to(sm.red, BP, kDenMainWarps * SUBS, p.Bsum + (size_t)T * BP);
-  grid_barrier(barrier, epoch);
-  stamp();
-
-  // ---- backward
-  for (int t = T - 1; t >= 0; t--) {
-    if (is_aux) {
-      if (!(p.debug_flags & 1))
-        aux_work(p, t + 1 < T ? t + 1 : -1, t - 1, tile, auxw, lane, false, sumsq, false, gsum, t);
-    } else {
-      const long long c0 = clock64();
-      beta_step<V, SUBS, SPLIT>(p, arcs, tasks, abeg, aend, tb, te, t, sm.red, warp, lane, ab);
-      busy += clock64() - c0;
-    }
-    trace_warp_done(t);
-    cta_reduce_to(sm.red, BP, kDenMainWarps * SUBS, p.Bsum + (size_t)t * BP);
-    grid_barrier(barrier, epoch);
-    if (p.deriv_progress && blockIdx.x == 0 && threadIdx.x == 0) {
-      *reinterpret_cast<volatile unsigned*>(p.deriv_progress) = (unsigned)(T - 1 - t);
-      __threadfence_system();
-    }
-    trace_frame_end(t);
-    stamp();
-  }
-
-  // ---- epilogue: frame 0's derivative rows, sanity sums, total log-likelihood
-  if (is_aux) {
-    aux_work(p, 0, -1, tile, auxw, lane, false, sumsq, true, gsum);
-    gsum = warp_sum(gsum);
-    if (lane == 0 && gsum != 0.0) atomicAdd(p.scalars + 1, gsum);
   } else {
-    ab = warp_sum(ab);
-    if (lane == 0 && ab != 0.0) atomicAdd(p.scalars + 0, ab);
-  }
+    // ---- backward prologue: beta'_T(h,s) = 1 / sum_h alpha'_T(h,s) = 1 / (S_T (1 + leaky*sum_pi))
+#pragma unroll
+    for (int ci = 0; ci < NCTX; ci++) {
+      const DenParams& p = batch.c[ci];
+      if (!is_aux) {
+        const double* ST = p.Ssum + (size_t)T * BP;
+        float* betaT = p.beta + (size_t)(T % 3) * p.N * BP;
+        float* betaTm1 = p.beta + (size_t)((T + 2) % 3) * p.N * BP;  // buffer of step T-1
+        for (int col = (lane % (32 / SUBS)) * V; col < BP; col += (32 / SUBS) * V) {
+          float inv[V], part[V];
+#pragma unroll
+          for (int v = 0; v < V; v++) {
+            const float S = (float)__ldcg(ST + col + v);
+            inv[v] = 1.0f / (S * (1.0f + p.leaky * p.sum_pi));
+            part[v] = 0.f;
+          }
+          for (int task = tb; task < te; task++) {
+            const int4 tk = tasks[task];
+            const float pi_h = __int_as_float(tk.w);
+            if (SPLIT && tk.z == 1) continue;
+            st_vec<V>(betaT + tk.x * BP + col, inv);
+#pragma unroll
+            for (int v = 0; v < V; v++) part[v] = fmaf(pi_h, inv[v], part[v]);
+            if (SPLIT && tk.z == 2) {
+              float zero[V];
+#pragma unroll
+              for (int v = 0; v < V; v++) zero[v] = 0.f;
+              st_vec<V>(betaTm1 + tk.x * BP + col, zero);
+            }
+          }
+#pragma unroll
+          for (int v = 0; v < V; v++) sm.red[(warp * SUBS + lane / (32 / SUBS)) * BP + col + v] = part[v];
+        }
+      }
+      cta_reduce_to(sm.red, BP, kDenMainWarps * SUBS, p.Bsum + (size_t)T * BP);
+      arrive(ci);
+    }
+
+    // ---- backward
+    for (int t = T - 1; t >= 0; t--) {
+#pragma unroll
+      for (int ci = 0; ci < NCTX; ci++) {
+        const DenParams& p = batch.c[ci];
+        wait(ci);  // step t+1 of this context is complete everywhere
+        if (ci == 0) {
+          if (t < T - 1) trace_frame_end(t + 1);
+          stamp();
+        }
+        if (ci == NCTX - 1 && t < T - 1 && p0.deriv_progress && blockIdx.x == 0 && threadIdx.x == 0) {
+          // the derivative rows of frames > t+1 are complete in every context
+          *reinterpret_cast<volatile unsigned*>(p0.deriv_progress) = (unsigned)(T - 2 - t);
+          __threadfence_system();
+        }
+        if (is_aux) {
+          if (!(p.debug_flags & 1))
+            aux_work(p, t + 1 < T ? t + 1 : -1, t - 1, tile, auxw, lane, false, sumsq, false, gsum, t);
+        } else {
+          const long long c0 = clock64();
+          beta_step<V, SUBS, SPLIT>(p, arcs, tasks, abeg, aend, tb, te, t, sm.red, warp, lane, ab);
+          busy += clock64() - c0;
+        }
+        trace_warp_done(t);
+        cta_reduce_to(sm.red, BP, kDenMainWarps * SUBS, p.Bsum + (size_t)t * BP);
+        arrive(ci);
+      }
+    }
+#pragma unroll
+    for (int ci = 0; ci < NCTX; ci++) wait(ci);
+    trace_frame_end(0);
+    stamp();
+
+    // ---- epilogue: frame 0's derivative rows, sanity sums
+    if (is_aux) {
+#pragma unroll
+      for (int ci = 0; ci < NCTX; ci++) aux_work(batch.c[ci], 0, -1, tile, auxw, lane, false, sumsq, true, gsum);
+      gsum = warp_sum(gsum);
+      if (lane == 0 && gsum != 0.0) atomicAdd(p0.scalars + 1, gsum);
+    } else {
+      ab = warp_sum(ab);
+      if (lane == 0 && ab != 0.0) atomicAdd(p0.scalars + 0, ab);
+    }
   }  // PHASE
-  if (p.warp_busy && lane == 0)
-    p.warp_busy[((size_t)PHASE * gridDim.x + blockIdx.x) * kDenWarps + warp] = (unsigned long long)busy;
+  if (p0.warp_busy && lane == 0)
+    p0.warp_busy[((size_t)PHASE * gridDim.x + blockIdx.x) * kDenWarps + warp] = (unsigned long long)busy;
   __syncthreads();
   stamp();
 }
@@ -764,31 +824,37 @@ __device__ __forceinline__ void den_chain_body(const DenParams& p) {
 // The forward launch is capped at 112 registers/thread so that 8 K registers per SM stay free:
 // the numerator kernel (128 threads x 48 registers per CTA) can then run on the same SMs while
 // the forward recurrence is in flight.  The backward launch takes the whole register file.
-template <int SUBS, bool STAGED, bool SPLIT>
-__global__ void __maxnreg__(112) den_forward_kernel(const __grid_constant__ DenParams p) {
-  den_chain_body<SUBS, STAGED, 0, SPLIT>(p);
+template <int SUBS, bool STAGED, bool SPLIT, int NCTX>
+__global__ void __maxnreg__(112) den_forward_kernel(const __grid_constant__ DenBatch batch) {
+  den_chain_body<SUBS, STAGED, 0, SPLIT, NCTX>(batch);
 }
-template <int SUBS, bool STAGED, bool SPLIT>
-__global__ void __launch_bounds__(kDenThreads, 1) den_backward_kernel(const __grid_constant__ DenParams p) {
-  den_chain_body<SUBS, STAGED, 1, SPLIT>(p);
+template <int SUBS, bool STAGED, bool SPLIT, int NCTX>
+__global__ void __launch_bounds__(kDenThreads, 1) den_backward_kernel(const __grid_constant__ DenBatch batch) {
+  den_chain_body<SUBS, STAGED, 1, SPLIT, NCTX>(batch);
 }
 
-template <int SUBS, bool STAGED, bool SPLIT>
-cudaError_t launch_t(const DenParams& p, int phase, int grid, size_t smem, cudaStream_t stream) {
-  void (*kern)(DenParams) =
-      phase == 0 ? den_forward_kernel<SUBS, STAGED, SPLIT> : den_backward_kernel<SUBS, STAGED, SPLIT>;
+template <int SUBS, bool STAGED, bool SPLIT, int NCTX>
+cudaError_t launch_t(const DenBatch& b, int phase, int grid, size_t smem, cudaStream_t stream) {
+  void (*kern)(DenBatch) = phase == 0 ? den_forward_kernel<SUBS, STAGED, SPLIT, NCTX>
+                                      : den_backward_kernel<SUBS, STAGED, SPLIT, NCTX>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  void* args[] = {const_cast<DenParams*>(&p)};
+  void* args[] = {const_cast<DenBatch*>(&b)};
   e = cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(kDenThreads), args, smem, stream);
   if (e == cudaSuccess) count_launch();
   return e;
 }
 
 template <int SUBS, bool STAGED>
-cudaError_t launch_p(const DenParams& p, int phase, int grid, size_t smem, cudaStream_t stream) {
-  return p.has_split ? launch_t<SUBS, STAGED, true>(p, phase, grid, smem, stream)
-                     : launch_t<SUBS, STAGED, false>(p, phase, grid, smem, stream);
+cudaError_t launch_p(const DenBatch& b, int phase, int grid, size_t smem, cudaStream_t stream) {
+  const bool split = b.c[0].has_split != 0;
+  if constexpr (SUBS == 1) {
+    if (b.nctx == 2)
+      return split ? launch_t<1, STAGED, true, 2>(b, phase, grid, smem, stream)
+                   : launch_t<1, STAGED, false, 2>(b, phase, grid, smem, stream);
+  }
+  return split ? launch_t<SUBS, STAGED, true, 1>(b, phase, grid, smem, stream)
+               : launch_t<SUBS, STAGED, false, 1>(b, phase, grid, smem, stream);
 }
 
 }  // namespace
@@ -812,17 +878,18 @@ int den_max_grid(int device) {
   return sms;
 }
 
-cudaError_t launch_den(const DenParams& p, int phase, int grid, cudaStream_t stream) {
+cudaError_t launch_den(const DenBatch& b, int phase, int grid, cudaStream_t stream) {
+  const DenParams& p = b.c[0];
   const size_t smem = den_smem_bytes(p);
-  if (p.subs != den_subs(p.BP)) return cudaErrorInvalidValue;
+  if (p.subs != den_subs(p.BP) || b.nctx < 1 || b.nctx > 2 || (b.nctx == 2 && p.subs != 1)) return cudaErrorInvalidValue;
   if (p.arcs_in_smem) {
-    if (p.subs == 1) return launch_p<1, true>(p, phase, grid, smem, stream);
-    if (p.subs == 2) return launch_p<2, true>(p, phase, grid, smem, stream);
-    return launch_p<4, true>(p, phase, grid, smem, stream);
+    if (p.subs == 1) return launch_p<1, true>(b, phase, grid, smem, stream);
+    if (p.subs == 2) return launch_p<2, true>(b, phase, grid, smem, stream);
+    return launch_p<4, true>(b, phase, grid, smem, stream);
   }
-  if (p.subs == 1) return launch_p<1, false>(p, phase, grid, smem, stream);
-  if (p.subs == 2) return launch_p<2, false>(p, phase, grid, smem, stream);
-  return launch_p<4, false>(p, phase, grid, smem, stream);
+  if (p.subs == 1) return launch_p<1, false>(b, phase, grid, smem, stream);
+  if (p.subs == 2) return launch_p<2, false>(b, phase, grid, smem, stream);
+  return launch_p<4, false>(b, phase, grid, smem, stream);
 }
 
 }  // namespace tb
