@@ -90,6 +90,13 @@ void* torchain_supervision_from_arrays(float weight, int32_t num_sequences,
                                        const int32_t* arc_dst, const int32_t* arc_label,
                                        const float* arc_cost, const float* final_cost);
 
+/* One binary Kaldi `Supervision` object (as chain::Supervision::Write(os, true) emits it, e.g. the
+ * payload of an ark written by chain-get-supervision; kaldi@22fbdd:src/chain/chain-supervision.cc),
+ * starting at the "<Supervision>" token.  *consumed (optional) receives the bytes parsed.  The
+ * byte layout is restated from the published Kaldi / OpenFst sources and is unverified against
+ * a Kaldi-written file (none is available in the build environment). */
+void* torchain_supervision_from_kaldi_bytes(const void* data, int64_t nbytes, int64_t* consumed);
+
 /* The reference's reader-based constructors; egs reading is out of scope, so
  * these always return NULL and set the error string. */
 void* my_lib_supervision_new(void* reader_ptr);

@@ -165,3 +165,45 @@ def test_chain_loss_requires_cuda():
     from torchain_b200.functions import chain_loss
     with pytest.raises(AssertionError, match="Only CUDA"):
         chain_loss(torch.zeros(4, 3), None, None)
+
+
+def kaldi_supervision_bytes(sup, end2end_token=False):
+    """Byte layout of chain::Supervision::Write(os, binary=true) (Kaldi) with the FST written by
+    fst::StdCompactAcceptorFst::WriteFst (OpenFst): see the parser's header comment."""
+    out = b"<Supervision> <Weight> " + struct.pack("<Bf", 4, sup.weight)
+    out += b"<NumSequences> " + struct.pack("<Bi", 4, sup.num_sequences)
+    out += b"<FramesPerSeq> " + struct.pack("<Bi", 4, sup.frames_per_sequence)
+    out += b"<LabelDim> " + struct.pack("<Bi", 4, sup.label_dim)
+    if end2end_token:
+        out += b"<End2End> F"
+    S = sup.num_states
+    offs, elems = [0], b""
+    n = 0
+    for s in range(S):
+        if np.isfinite(sup.final_cost[s]):
+            elems += struct.pack("<ifi", -1, float(sup.final_cost[s]), -1)
+            n += 1
+        for a in range(sup.arc_begin[s], sup.arc_begin[s + 1]):
+            elems += struct.pack("<ifi", int(sup.arc_label[a]), float(sup.arc_cost[a]), int(sup.arc_dst[a]))
+            n += 1
+        offs.append(n)
+    out += struct.pack("<i", 2125659606)
+    for t in (b"compact_acceptor", b"standard"):
+        out += struct.pack("<i", len(t)) + t
+    out += struct.pack("<iiQqqq", 2, 0, 0, 0, S, sup.num_arcs)
+    out += struct.pack("<%dI" % (S + 1), *offs) + elems + b"</Supervision> "
+    return out
+
+
+def test_supervision_from_kaldi_bytes_round_trip():
+    den = synth.make_den_fst(3, 40, 9, mean_deg=3.0)
+    sup = synth.make_supervision(4, den, 4, 5, num_paths=3, weight=0.5, boundary_final_costs=True)
+    for e2e in (False, True):
+        blob = kaldi_supervision_bytes(sup, end2end_token=e2e)
+        h, used = io.Supervision.from_kaldi_bytes(blob + b"trailing")
+        assert used == len(blob) - 1 or used == len(blob)   # the token's trailing space is consumed
+        assert h.shape == (4, 5, 9) and h.num_chains == 4
+    with pytest.raises(ValueError):
+        io.Supervision.from_kaldi_bytes(blob[:40])
+    with pytest.raises(ValueError):
+        io.Supervision.from_kaldi_bytes(b"<Nnet3ChainEg> ")

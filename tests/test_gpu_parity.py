@@ -361,3 +361,13 @@ def test_gpu_deriv_scale_and_repeatability():
         outs.append(d.cpu().numpy().astype(np.float64))
     assert np.abs(outs[0] + outs[1]).max() <= 1e-5 * np.abs(outs[0]).max()
     assert np.abs(outs[1] - outs[2]).max() <= 1e-5 * np.abs(outs[0]).max()
+
+
+def test_gpu_supervision_from_kaldi_bytes_matches_arrays():
+    from test_abi import kaldi_supervision_bytes
+    c = load_golden(GOLDEN[2])
+    g, _ = handles(c["den"], c["sup"])
+    s, _ = io.Supervision.from_kaldi_bytes(kaldi_supervision_bytes(c["sup"]))
+    res, d, _ = run_abi(g, s, c["y"], c["l2"], c["leaky"])
+    assert rel(res[0], c["objf"]) < OBJF_RTOL
+    assert deriv_err(d, c["deriv"]) < DERIV_RTOL

@@ -1169,6 +1169,133 @@ struct HostPath {
 };
 thread_local HostPath g_host;
 
+
+// ---------------------------------------------------------------------------
+// Kaldi binary `Supervision` object (kaldi@22fbdd:src/chain/chain-supervision.cc
+// Supervision::Write/Read, binary mode): tokens <Supervision> <Weight> float <NumSequences> int32
+// <FramesPerSeq> int32 <LabelDim> int32 [<End2End> F], then the FST written with
+// fst::StdCompactAcceptorFst::WriteFst (OpenFst CompactFst<StdArc, AcceptorCompactor>: FstHeader
+// "compact_acceptor"/"standard", uint32 state offsets [numstates+1], 12-byte elements
+// {int32 label, float weight, int32 nextstate}, a final weight being an element with label -1),
+// then </Supervision>.  Layout restated from the published Kaldi / OpenFst sources; no
+// Kaldi-written file is available offline to check it against.
+// ---------------------------------------------------------------------------
+struct ByteReader {
+  const unsigned char* p;
+  const unsigned char* end;
+  bool ok = true;
+  bool get(void* dst, size_t n) {
+    if (!ok || (size_t)(end - p) < n) {
+      ok = false;
+      return false;
+    }
+    std::memcpy(dst, p, n);
+    p += n;
+    return true;
+  }
+  bool token(const char* want) {  // "<Token> " (token followed by one space)
+    const size_t n = std::strlen(want);
+    if (!ok || (size_t)(end - p) < n + 1 || std::memcmp(p, want, n) != 0 || p[n] != ' ') return false;
+    p += n + 1;
+    return true;
+  }
+  template <typename T>
+  bool basic(T* v) {  // Kaldi WriteBasicType: one size byte, then the value
+    unsigned char sz = 0;
+    if (!get(&sz, 1) || sz != sizeof(T)) {
+      ok = false;
+      return false;
+    }
+    return get(v, sizeof(T));
+  }
+  bool str(std::string* s) {  // OpenFst string: int32 length + bytes
+    int32_t n = 0;
+    if (!get(&n, 4) || n < 0 || n > 4096) {
+      ok = false;
+      return false;
+    }
+    s->resize(n);
+    return n == 0 || get(&(*s)[0], n);
+  }
+};
+
+Supervision* parse_kaldi_supervision(const void* data, int64_t nbytes, int64_t* consumed) {
+  ByteReader r{static_cast<const unsigned char*>(data), static_cast<const unsigned char*>(data) + nbytes};
+  float weight = 0.f;
+  int32_t B = 0, T = 0, P = 0;
+  if (!r.token("<Supervision>") || !r.token("<Weight>") || !r.basic(&weight) || !r.token("<NumSequences>") ||
+      !r.basic(&B) || !r.token("<FramesPerSeq>") || !r.basic(&T) || !r.token("<LabelDim>") || !r.basic(&P)) {
+    g_error = "not a binary Kaldi Supervision object (header tokens)";
+    return nullptr;
+  }
+  if (r.token("<End2End>")) {  // written by later Kaldi revisions
+    unsigned char e2e = 0;
+    if (!r.get(&e2e, 1) || e2e != 'F') {
+      g_error = "end-to-end supervisions are not supported";
+      return nullptr;
+    }
+  }
+  int32_t magic = 0, version = 0, flags = 0;
+  uint64_t props = 0;
+  int64_t start = 0, nstates = 0, narcs = 0;
+  std::string fsttype, arctype;
+  if (!r.get(&magic, 4) || magic != 2125659606 || !r.str(&fsttype) || !r.str(&arctype) || !r.get(&version, 4) ||
+      !r.get(&flags, 4) || !r.get(&props, 8) || !r.get(&start, 8) || !r.get(&nstates, 8) || !r.get(&narcs, 8)) {
+    g_error = "Supervision: truncated or foreign FST header";
+    return nullptr;
+  }
+  if (fsttype != "compact_acceptor" || arctype != "standard" || (flags & 7) != 0) {
+    g_error = "Supervision: expected an unaligned compact_acceptor/standard FST without symbol tables (got '" +
+              fsttype + "'/'" + arctype + "')";
+    return nullptr;
+  }
+  if (nstates <= 0 || nstates > (1 << 28) || start != 0) {
+    g_error = "Supervision: implausible FST header (states / start)";
+    return nullptr;
+  }
+  std::vector<uint32_t> offs(nstates + 1);
+  if (!r.get(offs.data(), sizeof(uint32_t) * (nstates + 1))) {
+    g_error = "Supervision: truncated state table";
+    return nullptr;
+  }
+  const uint32_t ncompacts = offs[nstates];
+  struct Element {
+    int32_t label;
+    float weight;
+    int32_t nextstate;
+  };
+  std::vector<Element> el(ncompacts);
+  if (ncompacts > 0 && !r.get(el.data(), sizeof(Element) * (size_t)ncompacts)) {
+    g_error = "Supervision: truncated arc table";
+    return nullptr;
+  }
+  if (!r.token("</Supervision>")) {
+    g_error = "Supervision: missing </Supervision>";
+    return nullptr;
+  }
+  std::vector<int32_t> arc_begin(nstates + 1, 0), arc_dst, arc_label;
+  std::vector<float> arc_cost, final_cost(nstates, kInf);
+  for (int64_t s = 0; s < nstates; s++) {
+    if (offs[s + 1] < offs[s] || offs[s + 1] > ncompacts) {
+      g_error = "Supervision: corrupt state table";
+      return nullptr;
+    }
+    for (uint32_t k = offs[s]; k < offs[s + 1]; k++) {
+      if (el[k].label == -1) {
+        final_cost[s] = el[k].weight;
+      } else {
+        arc_dst.push_back(el[k].nextstate);
+        arc_label.push_back(el[k].label);
+        arc_cost.push_back(el[k].weight);
+      }
+    }
+    arc_begin[s + 1] = (int32_t)arc_dst.size();
+  }
+  if (consumed) *consumed = (int64_t)(r.p - static_cast<const unsigned char*>(data));
+  return make_supervision(weight, B, T, P, (int32_t)nstates, arc_begin.data(), arc_dst.data(), arc_label.data(),
+                          arc_cost.data(), final_cost.data());
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -1225,6 +1352,11 @@ void* torchain_supervision_from_arrays(float weight, int32_t num_sequences, int3
     return fail_ptr("supervision: null arc arrays");
   return make_supervision(weight, num_sequences, frames_per_sequence, label_dim, num_states, arc_begin, arc_dst,
                           arc_label, arc_cost, final_cost);
+}
+
+void* torchain_supervision_from_kaldi_bytes(const void* data, int64_t nbytes, int64_t* consumed) {
+  if (!data || nbytes <= 0) return fail_ptr("supervision: null / empty buffer");
+  return parse_kaldi_supervision(data, nbytes, consumed);
 }
 
 void* my_lib_supervision_new(void*) {

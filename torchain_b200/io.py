@@ -64,6 +64,19 @@ class Supervision:
             raise ValueError("invalid supervision: " + _lib.last_error())
         return cls(ptr)
 
+    @classmethod
+    def from_kaldi_bytes(cls, data):
+        """Parse one binary Kaldi ``Supervision`` object (bytes starting at ``<Supervision>``).
+        Returns ``(supervision, bytes_consumed)``."""
+        lib = _lib.load()
+        buf = (ctypes.c_char * len(data)).from_buffer_copy(data)
+        consumed = ctypes.c_int64(0)
+        ptr = lib.torchain_supervision_from_kaldi_bytes(ctypes.cast(buf, ctypes.c_void_p), len(data),
+                                                        ctypes.byref(consumed))
+        if not ptr:
+            raise ValueError("invalid supervision: " + _lib.last_error())
+        return cls(ptr), int(consumed.value)
+
     @property
     def num_chains(self):
         return _lib.load().torchain_supervision_num_chains(self.ptr)
