@@ -198,6 +198,9 @@ double torchain_microbench_l2_gather(int device, int64_t table_bytes, int row_by
 double torchain_microbench_l2_red(int device, int64_t table_bytes, int row_bytes, int iters);
 /* Mean latency in microseconds of the software grid barrier at one CTA per SM. */
 double torchain_microbench_grid_barrier(int device, int iters);
+/* The forward recurrence's gather pattern (5 MB + 1.5 MB tables, 512-byte rows) with `warps` warps per SM
+ * and `depth` (8, 12, 16 or 24) gathers in flight per warp; GB/s. */
+double torchain_microbench_pattern(int device, int warps, int depth, int iters);
 
 #ifdef __cplusplus
 }

@@ -1568,5 +1568,8 @@ double torchain_microbench_l2_red(int device, int64_t table_bytes, int row_bytes
   return tb::microbench_l2_red(device, table_bytes, row_bytes, iters);
 }
 double torchain_microbench_grid_barrier(int device, int iters) { return tb::microbench_grid_barrier(device, iters); }
+double torchain_microbench_pattern(int device, int warps, int depth, int iters) {
+  return tb::microbench_pattern(device, warps, depth, iters);
+}
 
 }  // extern "C"

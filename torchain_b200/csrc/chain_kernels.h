@@ -158,5 +158,6 @@ int64_t launch_count();
 double microbench_l2_gather(int device, int64_t table_bytes, int row_bytes, int iters);
 double microbench_l2_red(int device, int64_t table_bytes, int row_bytes, int iters);
 double microbench_grid_barrier(int device, int iters);
+double microbench_pattern(int device, int warps, int depth, int iters);
 
 }  // namespace tb

@@ -824,12 +824,21 @@ __device__ __forceinline__ void den_chain_body(const DenBatch& batch) {
 // The forward launch is capped at 112 registers/thread so that 8 K registers per SM stay free:
 // the numerator kernel (128 threads x 48 registers per CTA) can then run on the same SMs while
 // the forward recurrence is in flight.  The backward launch takes the whole register file.
+#ifndef DEN_F_MAXNREG
+#define DEN_F_MAXNREG 112
+#endif
 template <int SUBS, bool STAGED, bool SPLIT, int NCTX>
-__global__ void __maxnreg__(112) den_forward_kernel(const __grid_constant__ DenBatch batch) {
+__global__ void __maxnreg__(DEN_F_MAXNREG) den_forward_kernel(const __grid_constant__ DenBatch batch) {
   den_chain_body<SUBS, STAGED, 0, SPLIT, NCTX>(batch);
 }
+#ifdef DEN_B_MAXNREG
 template <int SUBS, bool STAGED, bool SPLIT, int NCTX>
-__global__ void __launch_bounds__(kDenThreads, 1) den_backward_kernel(const __grid_constant__ DenBatch batch) {
+__global__ void __maxnreg__(DEN_B_MAXNREG) den_backward_kernel(
+#else
+template <int SUBS, bool STAGED, bool SPLIT, int NCTX>
+__global__ void __launch_bounds__(kDenThreads, 1) den_backward_kernel(
+#endif
+    const __grid_constant__ DenBatch batch) {
   den_chain_body<SUBS, STAGED, 1, SPLIT, NCTX>(batch);
 }
 

@@ -75,7 +75,78 @@ __global__ void __launch_bounds__(512) barrier_kernel(unsigned* counter, int ite
   }
 }
 
+// Emulates the forward recurrence's access pattern: `warps` warps per CTA (one CTA per SM), each
+// keeping `depth` 512-byte row gathers in flight, alternating between a 5 MB and a 1.5 MB table.
+template <int DEPTH>
+__global__ void __launch_bounds__(1024) pattern_kernel(const float4* __restrict__ ta, unsigned na,
+                                                       const float4* __restrict__ te, unsigned ne, int iters,
+                                                       float* sink) {
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned seed = warp * 9781u + 17u;
+  for (int it = 0; it < iters; it++) {
+    float4 v[DEPTH];
+#pragma unroll
+    for (int u = 0; u < DEPTH; u += 2) {
+      const unsigned r = hash32(seed + (unsigned)(it * DEPTH + u) * 2654435761u);
+      v[u] = __ldcg(ta + (size_t)(r % na) * 32 + lane);
+      v[u + 1] = __ldcg(te + (size_t)((r >> 7) % ne) * 32 + lane);
+    }
+#pragma unroll
+    for (int u = 0; u < DEPTH; u++) {
+      acc.x += v[u].x;
+      acc.y += v[u].y;
+      acc.z += v[u].z;
+      acc.w += v[u].w;
+    }
+  }
+  if (acc.x + acc.y + acc.z + acc.w == 123.456f) *sink = acc.x;
+}
+
 }  // namespace
+
+double microbench_pattern(int device, int warps, int depth, int iters) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const unsigned na = 10000, ne = 2928;
+  float4 *ta = nullptr, *te = nullptr;
+  float* sink = nullptr;
+  cudaMalloc(&ta, (size_t)na * 512);
+  cudaMalloc(&te, (size_t)ne * 512);
+  cudaMalloc(&sink, 4);
+  cudaMemset(ta, 0, (size_t)na * 512);
+  cudaMemset(te, 0, (size_t)ne * 512);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(e0);
+    if (depth == 2) pattern_kernel<2><<<sms, warps * 32>>>(ta, na, te, ne, iters, sink);
+    else if (depth == 4) pattern_kernel<4><<<sms, warps * 32>>>(ta, na, te, ne, iters, sink);
+    else if (depth == 6) pattern_kernel<6><<<sms, warps * 32>>>(ta, na, te, ne, iters, sink);
+    else if (depth == 8) pattern_kernel<8><<<sms, warps * 32>>>(ta, na, te, ne, iters, sink);
+    else if (depth == 12) pattern_kernel<12><<<sms, warps * 32>>>(ta, na, te, ne, iters, sink);
+    else if (depth == 16) pattern_kernel<16><<<sms, warps * 32>>>(ta, na, te, ne, iters, sink);
+    else pattern_kernel<24><<<sms, warps * 32>>>(ta, na, te, ne, iters, sink);
+    count_launch();
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0) best = std::min(best, ms);
+  }
+  const bool ok = cudaGetLastError() == cudaSuccess;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(ta);
+  cudaFree(te);
+  cudaFree(sink);
+  if (!ok) return -1.0;
+  const int d = depth == 2 || depth == 4 || depth == 6 || depth == 8 || depth == 12 || depth == 16 ? depth : 24;
+  return (double)sms * warps * (double)iters * d * 512.0 / (best * 1e-3) / 1e9;
+}
 
 double microbench_l2_gather(int device, int64_t table_bytes, int row_bytes, int iters) {
   if (cudaSetDevice(device) != cudaSuccess) return -1.0;
