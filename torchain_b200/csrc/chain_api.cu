@@ -188,7 +188,8 @@ void lpt(const std::vector<int>& items, const std::vector<int>& cost, const std:
 //   dir 0: tasks = destination states with their in-arcs (other = source)
 //   dir 1: tasks = source states with their out-arcs     (other = destination)
 void build_dir(const DenGraph& g, int dir, int grid, int bins_per_cta, const std::vector<double>& speed /* [grid*bins_per_cta] */,
-               DirHost* out, std::vector<double>* work) {
+               unsigned rowbytes /* bytes of one [state|pdf] row of this geometry: 4 * BP */, DirHost* out,
+               std::vector<double>* work) {
   const int N = g.N, A = g.A;
   std::vector<int> deg(N, 0), begin(N + 1, 0);
   const std::vector<int>& key = dir == 0 ? g.dst : g.src;
@@ -257,9 +258,9 @@ void build_dir(const DenGraph& g, int dir, int grid, int bins_per_cta, const std
         out->tasks.push_back(tk);
         for (int k = begin[s] + item.first; k < begin[s] + item.first + item.count; k++) {
           const int a = arc_of[k];
-          int4 ar;
-          ar.x = other[a];
-          ar.y = g.pdf[a];
+          int4 ar;  // state / pdf stored as row BYTE offsets: the gather address is base + offset
+          ar.x = (int)((unsigned)other[a] * rowbytes);
+          ar.y = (int)((unsigned)g.pdf[a] * rowbytes);
           float pr = g.prob[a], pio = g.pi[other[a]];
           std::memcpy(&ar.z, &pr, 4);
           std::memcpy(&ar.w, &pio, 4);
@@ -267,7 +268,7 @@ void build_dir(const DenGraph& g, int dir, int grid, int bins_per_cta, const std
         }
         if (item.count == 0) {  // a state without arcs still needs its end-of-state marker
           int4 ar;
-          ar.x = s;
+          ar.x = (int)((unsigned)s * rowbytes);
           ar.y = 0;
           ar.z = 0;  // probability 0.0f
           ar.w = 0;
@@ -754,7 +755,8 @@ int build_partition(DenGraph* g, DenDevice* d, int subs = 1) {
   const std::vector<double> uniform((size_t)d->grid * bins, 1.0);
   for (int dir = 0; dir < 2; dir++) {
     DirHost h;
-    build_dir(*g, dir, d->grid, bins, subs == 1 ? d->speed[dir] : uniform, &h, &part->work[dir]);
+    build_dir(*g, dir, d->grid, bins, subs == 1 ? d->speed[dir] : uniform, 4u * (unsigned)(tb::kCtxBP / subs), &h,
+              &part->work[dir]);
     CUDA_OK(upload(part->arcs[dir], h.arcs));
     CUDA_OK(upload(part->tasks[dir], h.tasks));
     CUDA_OK(upload(part->cta_arc_off[dir], h.cta_arc_off));
@@ -928,7 +930,7 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   if (sup->P != P) return fail("supervision.label_dim != den_graph.NumPdfs()");
   if (ystride < cols || (deriv && dstride < cols) || (xent && xstride < cols)) return fail("row stride < cols");
   if (!(leaky > 0.f && leaky < 1.f)) return fail("leaky_hmm_coefficient must be in (0, 1)");
-  if ((int64_t)N * tb::kMaxBP >= (1ll << 30) || (int64_t)P * tb::kMaxBP >= (1ll << 30))
+  if ((int64_t)N * tb::kCtxBP * 4 >= (1ll << 32) || (int64_t)P * tb::kCtxBP * 4 >= (1ll << 32))
     return fail("graph too large for 32-bit row byte offsets");
   DeviceGuard guard(device);
   if (!guard.ok) return fail("cannot select CUDA device");

@@ -26,7 +26,7 @@ constexpr int kMaxBP = 256;                    // sequences per launch pair: two
 //   dir 0 ("alpha"): tasks are destination states, arcs are their in-arcs
 //   dir 1 ("beta") : tasks are source states,      arcs are their out-arcs
 struct DenDir {
-  const int4* arcs;          // {other_state, pdf, float_bits(prob) | end-of-state flag in the sign bit, float_bits(pi[other_state])}
+  const int4* arcs;          // {other_state * 4BP, pdf * 4BP (row byte offsets), float_bits(prob) | end-of-state flag in the sign bit, float_bits(pi[other_state])}
   const int4* tasks;         // {state, arc_begin (relative to the CTA's slice), split flag (0 whole state, 2 first / 1 other sub-task of a split state), float_bits(pi[state])}
   const int* cta_arc_off;    // [grid+1]
   const int* cta_task_off;   // [grid+1]

@@ -329,15 +329,16 @@ __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __res
     int task = tb;
     constexpr int kSA = DEN_F_SA, kStages = DEN_F_STAGES;
     GatherBuf<V, kSA> ring[kStages];
-    const float* const base_a = alpha_prev + col;
-    const float* const base_e = et + col;
+    // warp-uniform 64-bit bases + per-lane 32-bit byte offsets (arc fields are pre-scaled by the host)
+    const char* const ua = reinterpret_cast<const char*>(alpha_prev + col);
+    const char* const ue = reinterpret_cast<const char*>(et + col);
     auto load = [&](GatherBuf<V, kSA>& buf, int k) {
 #pragma unroll
       for (int u = 0; u < kSA; u++) {
         if (k + u < n) {
-          const int2 ar = *reinterpret_cast<const int2*>(a + k + u);  // {source state, pdf}
-          ld_cg<V>(row_ptr(base_a, ar.x, rowbytes), buf.a[u]);
-          ld_cg<V>(row_ptr(base_e, ar.y, rowbytes), buf.e[u]);
+          const uint2 ar = *reinterpret_cast<const uint2*>(a + k + u);  // {source state, pdf} as row byte offsets
+          ld_cg<V>(reinterpret_cast<const float*>(ua + ar.x), buf.a[u]);
+          ld_cg<V>(reinterpret_cast<const float*>(ue + ar.y), buf.e[u]);
         }
       }
     };
@@ -428,16 +429,16 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
     float pi_h = 0.f;
     constexpr int kSA = DEN_B_SA, kStages = DEN_B_STAGES;
     GatherBuf<V, kSA> ring[kStages];
-    const float* const base_b = beta_next + col;
-    const float* const base_e = et + col;
-    float* const base_g = gt + col;
+    const char* const ub = reinterpret_cast<const char*>(beta_next + col);
+    const char* const ue = reinterpret_cast<const char*>(et + col);
+    char* const ug = reinterpret_cast<char*>(gt + col);
     auto load = [&](GatherBuf<V, kSA>& buf, int k) {
 #pragma unroll
       for (int u = 0; u < kSA; u++) {
         if (k + u < n) {
-          const int2 ar = *reinterpret_cast<const int2*>(a + k + u);  // {destination state, pdf}
-          ld_cg<V>(row_ptr(base_b, ar.x, rowbytes), buf.a[u]);
-          ld_cg<V>(row_ptr(base_e, ar.y, rowbytes), buf.e[u]);
+          const uint2 ar = *reinterpret_cast<const uint2*>(a + k + u);  // {destination state, pdf} as row byte offsets
+          ld_cg<V>(reinterpret_cast<const float*>(ub + ar.x), buf.a[u]);
+          ld_cg<V>(reinterpret_cast<const float*>(ue + ar.y), buf.e[u]);
         }
       }
     };
@@ -454,7 +455,7 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
             X[v] += vf;
             g[v] = vf * occ[v];
           }
-          if (!(p.debug_flags & 2)) red_add<V>(row_ptr(base_g, ar.y, rowbytes), g);
+          if (!(p.debug_flags & 2)) red_add<V>(reinterpret_cast<float*>(ug + (unsigned)ar.y), g);
           if (ar.z < 0) {  // sign bit of the probability = last arc of this state
             const int4 tk = tasks[task];
             float bd[V];
