@@ -78,7 +78,7 @@ struct DenParams {
   // derivative rows of frames > t are complete and the kernel publishes T-1-t here, so the host can
   // start copying finished frame chunks out while the recurrence is still running.  null = unused.
   unsigned* deriv_progress;
-  int debug_flags;    // timing experiments only (TORCHAIN_DEBUG_FLAGS): 1 = skip aux work in backward, 2 = skip REDs, 4 = skip the numerator scatter
+  int debug_flags;    // timing experiments only (TORCHAIN_DEBUG_FLAGS): 1 = skip the aux-warp work of the backward launch (wrong results)
   unsigned long long* warp_busy;  // [2][grid][kDenWarps] SM cycles each warp spent in its frame work (feeds the partition autotuner)
   unsigned long long* cta_trace;  // optional [phase][frame][cta][4]: main warp 0 done, aux warp 0 done, CTA done, barrier exit
   unsigned long long* timeline;  // optional: globaltimer at every phase boundary (2T+5 entries), or null

@@ -260,7 +260,7 @@ __device__ __forceinline__ void aux_work(const DenParams& p, int flush_frame, in
       stage_exp_tile(p, stage_frame, p.etile + (size_t)(stage_frame & 1) * p.P * BP, tile, j - nflush, lane, want_sq,
                      sumsq);
   }
-  if (num_frame >= 0 && p.num_frame_off != nullptr && !(p.debug_flags & 4)) {
+  if (num_frame >= 0 && p.num_frame_off != nullptr) {
     // subtract the numerator occupancies of `num_frame` from its (already zeroed) tile; the REDs
     // of the main warps add the denominator occupancies to the same tile during this frame
     float* gt = p.gtile + (size_t)(num_frame & 1) * p.P * BP;
@@ -455,7 +455,7 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
             X[v] += vf;
             g[v] = vf * occ[v];
           }
-          if (!(p.debug_flags & 2)) red_add<V>(reinterpret_cast<float*>(ug + (unsigned)ar.y), g);
+          red_add<V>(reinterpret_cast<float*>(ug + (unsigned)ar.y), g);
           if (ar.z < 0) {  // sign bit of the probability = last arc of this state
             const int4 tk = tasks[task];
             float bd[V];
