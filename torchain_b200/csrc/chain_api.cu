@@ -276,6 +276,15 @@ void build_dir(const DenGraph& g, int dir, int grid, int bins_per_cta, const std
         }
         out->arcs.back().z |= (int)0x80000000u;  // end-of-state flag = sign bit of the (non-negative) probability
       }
+      // pad the stream to a multiple of kStreamPad arcs: zero-probability arcs without an end flag,
+      // pointing at rows the stream touches anyway (they add 0 to an accumulator nobody reads)
+      const int stream_begin = out->warp_arc_off.back();
+      while (((int)out->arcs.size() - stream_begin) % tb::kStreamPad != 0) {
+        int4 ar = out->arcs.size() > (size_t)stream_begin ? out->arcs.back() : make_int4(0, 0, 0, 0);
+        ar.z = 0;  // +0.0f: no probability, no end-of-state flag
+        ar.w = 0;
+        out->arcs.push_back(ar);
+      }
       out->warp_task_off.push_back((int)out->tasks.size());
       out->warp_arc_off.push_back((int)out->arcs.size());
     }

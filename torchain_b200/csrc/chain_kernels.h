@@ -19,6 +19,11 @@ constexpr int kDenThreads = DEN_THREADS;       // threads per CTA (one CTA per S
 constexpr int kDenWarps = kDenThreads / 32;
 constexpr int kDenAuxWarps = DEN_AUX_WARPS;                // staging (transpose+exp) / derivative write-out warps
 constexpr int kDenMainWarps = kDenWarps - kDenAuxWarps;
+// every lane group's arc stream is padded (zero-probability arcs) to a multiple of this many arcs,
+// a common multiple of the stage widths of the two gather loops
+constexpr int kStreamPad = 4;
+#define DEN_F_SA_DEFAULT 2
+#define DEN_B_SA_DEFAULT 4
 constexpr int kCtxBP = 128;                    // sequences per context (lane width of the full-size kernels)
 constexpr int kMaxBP = 256;                    // sequences per launch pair: two contexts of kCtxBP
 

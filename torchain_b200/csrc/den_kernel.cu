@@ -284,15 +284,17 @@ __device__ __forceinline__ void aux_work(const DenParams& p, int flush_frame, in
 // as a 3-stage ring of 2 (28.2 us/frame vs 28.7 for one stage of 4); 8 arcs in flight do not
 // fit its 112-register budget.  The backward pass is best with ONE stage of 4: every deeper
 // variant (more gathers in flight next to the REDs) is slower (44.4 us -> 48..52 us/frame).
+static_assert(kStreamPad % DEN_F_SA_DEFAULT == 0 && kStreamPad % DEN_B_SA_DEFAULT == 0, "stream padding");
 #ifndef DEN_F_SA
-#define DEN_F_SA 2
+#define DEN_F_SA DEN_F_SA_DEFAULT
 #endif
 #ifndef DEN_F_STAGES
 #define DEN_F_STAGES 3
 #endif
 #ifndef DEN_B_SA
-#define DEN_B_SA 4
+#define DEN_B_SA DEN_B_SA_DEFAULT
 #endif
+static_assert(kStreamPad % DEN_F_SA == 0 && kStreamPad % DEN_B_SA == 0, "arc streams are padded to kStreamPad arcs");
 #ifndef DEN_B_STAGES
 #define DEN_B_STAGES 1
 #endif
@@ -332,10 +334,12 @@ __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __res
     // warp-uniform 64-bit bases + per-lane 32-bit byte offsets (arc fields are pre-scaled by the host)
     const char* const ua = reinterpret_cast<const char*>(alpha_prev + col);
     const char* const ue = reinterpret_cast<const char*>(et + col);
+    // every stream is padded by the host to a multiple of kPad arcs with zero-probability
+    // arcs, so a stage needs ONE bounds check instead of one per arc
     auto load = [&](GatherBuf<V, kSA>& buf, int k) {
+      if (k < n) {
 #pragma unroll
-      for (int u = 0; u < kSA; u++) {
-        if (k + u < n) {
+        for (int u = 0; u < kSA; u++) {
           const uint2 ar = *reinterpret_cast<const uint2*>(a + k + u);  // {source state, pdf} as row byte offsets
           ld_cg<V>(reinterpret_cast<const float*>(ua + ar.x), buf.a[u]);
           ld_cg<V>(reinterpret_cast<const float*>(ue + ar.y), buf.e[u]);
@@ -345,7 +349,7 @@ __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __res
     auto consume = [&](GatherBuf<V, kSA>& buf, int k) {
 #pragma unroll
       for (int u = 0; u < kSA; u++) {
-        if (k + u < n) {
+        {
           const int2 ar = *(reinterpret_cast<const int2*>(a + k + u) + 1);  // {prob | end flag, pi[source]}
           const float pr = fabsf(__int_as_float(ar.x)), pi = __int_as_float(ar.y);
 #pragma unroll
@@ -433,9 +437,9 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
     const char* const ue = reinterpret_cast<const char*>(et + col);
     char* const ug = reinterpret_cast<char*>(gt + col);
     auto load = [&](GatherBuf<V, kSA>& buf, int k) {
+      if (k < n) {  // streams are padded to a multiple of kPad arcs (see alpha_step)
 #pragma unroll
-      for (int u = 0; u < kSA; u++) {
-        if (k + u < n) {
+        for (int u = 0; u < kSA; u++) {
           const uint2 ar = *reinterpret_cast<const uint2*>(a + k + u);  // {destination state, pdf} as row byte offsets
           ld_cg<V>(reinterpret_cast<const float*>(ub + ar.x), buf.a[u]);
           ld_cg<V>(reinterpret_cast<const float*>(ue + ar.y), buf.e[u]);
@@ -445,7 +449,7 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
     auto consume = [&](GatherBuf<V, kSA>& buf, int k) {
 #pragma unroll
       for (int u = 0; u < kSA; u++) {
-        if (k + u < n) {
+        {
           const int4 ar = a[k + u];
           const float pr = fabsf(__int_as_float(ar.z));
           float g[V];
