@@ -1449,7 +1449,7 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
   // nnet_output goes up in chunks of whole frames; the forward launch starts as soon as the
   // first chunk has landed and waits (per frame) on the flag of the chunk it needs next.
   const int T = sp->T, B = sp->B;
-  const int chunk_frames = std::max(1, (T + 7) / 8);
+  const int chunk_frames = std::max(1, (T + 15) / 16);  // ~16 chunks: short first-in / last-out latency
   const int nchunks = (T + chunk_frames - 1) / chunk_frames;
   CUDA_OK(h.flags.reserve(sizeof(unsigned) * (size_t)nchunks));
   CUDA_OK(cudaMemsetAsync(h.flags.ptr, 0, sizeof(unsigned) * nchunks, h.compute));
