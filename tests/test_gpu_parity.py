@@ -371,3 +371,17 @@ def test_gpu_supervision_from_kaldi_bytes_matches_arrays():
     res, d, _ = run_abi(g, s, c["y"], c["l2"], c["leaky"])
     assert rel(res[0], c["objf"]) < OBJF_RTOL
     assert deriv_err(d, c["deriv"]) < DERIV_RTOL
+
+
+def test_gpu_unstaged_arcs_path(monkeypatch):
+    """Graphs whose per-CTA arc slice does not fit in shared memory read arcs from global memory."""
+    monkeypatch.setenv("TORCHAIN_FORCE_UNSTAGED", "1")
+    for seed, B in ((21, 5), (22, 130)):
+        den = synth.make_den_fst(seed, 200, 30, mean_deg=4.0)
+        sup = synth.make_supervision(seed + 1, den, B, 6, num_paths=3)
+        y = synth.make_nnet_output(seed + 2, B, 6, 30)
+        r = ol.chain(ol.OracleDen(den), ol.OracleSup(sup), y, l2=0.0, leaky=0.1, mode="fp64", threads=4)
+        g, s = handles(den, sup)
+        res, d, _ = run_abi(g, s, y, 0.0, 0.1)
+        assert rel(res[0], r["objf"]) < OBJF_RTOL
+        assert deriv_err(d, r["deriv"]) < DERIV_RTOL

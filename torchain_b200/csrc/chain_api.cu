@@ -1080,8 +1080,10 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
     DenPartition* part = nullptr;
     if (!partition_for(dp.subs, &part)) return 0;
     bind(part);
+    // arc / task slices are staged in shared memory unless the graph is too large for it
+    // (TORCHAIN_FORCE_UNSTAGED=1 exercises the global-memory path on small graphs)
     dp.arcs_in_smem = 1;
-    if (tb::den_smem_bytes(dp) > 200 * 1024) dp.arcs_in_smem = 0;
+    if (tb::den_smem_bytes(dp) > 200 * 1024 || getenv("TORCHAIN_FORCE_UNSTAGED")) dp.arcs_in_smem = 0;
     for (int ci = 0; ci < 2; ci++) {
       tb::DenParams& c = batch.c[ci];
       c = dp;
