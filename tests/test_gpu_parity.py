@@ -385,3 +385,56 @@ def test_gpu_unstaged_arcs_path(monkeypatch):
         res, d, _ = run_abi(g, s, y, 0.0, 0.1)
         assert rel(res[0], r["objf"]) < OBJF_RTOL
         assert deriv_err(d, r["deriv"]) < DERIV_RTOL
+
+
+def test_gpu_degenerate_graphs_and_leaky_extremes():
+    """One-state / one-pdf graph, and leaky coefficients near both ends of (0, 1)."""
+    den1 = synth.DenFst(1, 1, 0, np.array([0], dtype=np.int32), np.array([0], dtype=np.int32),
+                        np.array([1], dtype=np.int32), np.array([0.1], dtype=np.float32),
+                        np.array([2.0], dtype=np.float32))
+    B, T = 3, 4
+    S = B * T + 1
+    sup1 = synth.SupFst(1.0, B, T, 1, np.arange(S + 1, dtype=np.int32).clip(max=S - 1),
+                        np.arange(1, S, dtype=np.int32), np.ones(S - 1, dtype=np.int32),
+                        np.full(S - 1, 0.3, dtype=np.float32),
+                        np.concatenate([np.full(S - 1, np.inf), [0.0]]).astype(np.float32))
+    y1 = synth.make_nnet_output(1, B, T, 1)
+    cases = [(den1, sup1, y1, 0.1)]
+    den = synth.make_den_fst(31, 70, 13, mean_deg=3.0)
+    sup = synth.make_supervision(32, den, 4, 9, num_paths=3)
+    y = synth.make_nnet_output(33, 4, 9, 13, scale=2.0)
+    cases += [(den, sup, y, 1e-6), (den, sup, y, 0.9)]
+    for (dn, sp, yy, leaky) in cases:
+        r = ol.chain(ol.OracleDen(dn), ol.OracleSup(sp), yy, l2=0.0, leaky=leaky, mode="fp64")
+        g, s = handles(dn, sp)
+        res, d, _ = run_abi(g, s, yy, 0.0, leaky)
+        assert rel(res[0], r["objf"]) < OBJF_RTOL
+        # the one-pdf case has an exactly zero derivative (both posteriors are 1): absolute tolerance there
+        assert np.abs(d.astype(np.float64) - r["deriv"]).max() < DERIV_RTOL * max(1.0, np.abs(r["deriv"]).max())
+
+
+def test_gpu_two_devices_one_process():
+    """The reference's parallel_train.py drives several GPUs from one process; handles keep
+    per-device copies of the graph and per-(device, stream) workspaces."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    lib = _lib.load()
+    c = load_golden(GOLDEN[2])
+    g, s = handles(c["den"], c["sup"])
+    outs = []
+    for dev in (0, 1, 0):
+        with torch.cuda.device(dev):
+            y = torch.from_numpy(np.ascontiguousarray(c["y"], dtype=np.float32)).cuda(dev)
+            d = torch.empty_like(y)
+            res = np.zeros(3, dtype=np.float32)
+            ok = lib.my_lib_ComputeChainObjfAndDeriv(
+                g.ptr, s.ptr, y.data_ptr(), y.shape[0], y.shape[1], y.stride(0), res.ctypes.data_as(ctypes.c_void_p),
+                d.data_ptr(), d.stride(0), None, 0, c["l2"], c["leaky"], 0.0, dev,
+                ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            assert ok == 1, _lib.last_error()
+            torch.cuda.synchronize(dev)
+            outs.append((res.copy(), d.cpu().numpy()))
+    for res, d in outs:
+        assert rel(res[0], c["objf"]) < OBJF_RTOL
+        assert deriv_err(d, c["deriv"]) < DERIV_RTOL
