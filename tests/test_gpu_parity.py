@@ -438,3 +438,44 @@ def test_gpu_two_devices_one_process():
     for res, d in outs:
         assert rel(res[0], c["objf"]) < OBJF_RTOL
         assert deriv_err(d, c["deriv"]) < DERIV_RTOL
+
+
+def test_gpu_two_threads_two_streams():
+    """Re-entrancy per (handle, stream): two host threads drive the same handles on their own
+    CUDA streams (the reference's parallel_apply used Python threads, parallel_train.py:67)."""
+    import threading
+    import torch
+    lib = _lib.load()
+    c = synth.make_config("chime5", B=32, T=8, with_y=False)
+    g, s = handles(c["den"], c["sup"])
+    y = torch.randn(8 * 32, c["P"], device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+    ref_d = torch.empty_like(y)
+    ref = np.zeros(3, dtype=np.float32)
+    args = lambda d, res, st: (g.ptr, s.ptr, y.data_ptr(), y.shape[0], y.shape[1], y.stride(0),
+                               res.ctypes.data_as(ctypes.c_void_p), d.data_ptr(), d.stride(0), None, 0,
+                               0.0, 0.1, 0.0, 0, ctypes.c_void_p(st.cuda_stream))
+    assert lib.my_lib_ComputeChainObjfAndDeriv(*args(ref_d, ref, torch.cuda.current_stream())) == 1
+    torch.cuda.synchronize()
+    results = {}
+
+    def worker(i):
+        st = torch.cuda.Stream()
+        d = torch.empty_like(y)
+        res = np.zeros(3, dtype=np.float32)
+        st.wait_stream(torch.cuda.default_stream())
+        for _ in range(5):
+            ok = lib.my_lib_ComputeChainObjfAndDeriv(*args(d, res, st))
+            assert ok == 1, _lib.last_error()
+        st.synchronize()
+        results[i] = (res.copy(), d.clone())
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+        assert not t.is_alive()
+    for i in range(2):
+        res, d = results[i]
+        assert rel(res[0], ref[0]) < OBJF_RTOL
+        assert float((d - ref_d).abs().max()) <= 1e-4 * float(ref_d.abs().max())
