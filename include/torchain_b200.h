@@ -158,6 +158,37 @@ int torchain_ComputeChainObjfAndDeriv_ex(void* den_graph_ptr, void* supervision_
                                          float xent_regularize, float deriv_scale,
                                          int device, void* stream);
 
+/* Strided form: replaces the pair to2d + my_lib_ComputeChainObjfAndDeriv of
+ * torchain/functions.py:118-125,128-138.  chain_loss permutes a (B, num_pdfs, T)
+ * network output into a fresh (T*B, num_pdfs) copy before the call and autograd
+ * permutes the gradient back; here each matrix is (pointer, three ELEMENT strides
+ * {frame, sequence, pdf}), so the kernels read the network output and write its
+ * gradient where they are.  The reference's 2-D form is {B*row_stride, row_stride, 1};
+ * a contiguous (B, P, T) tensor is {1, P*T, T}.  num_frames / num_sequences /
+ * num_pdfs must equal the supervision's and the den graph's; derivative strides
+ * must be positive and describe non-overlapping elements.  Everything else as
+ * torchain_ComputeChainObjfAndDeriv_ex. */
+int torchain_ComputeChainObjfAndDeriv_strided(void* den_graph_ptr, void* supervision_ptr,
+                                              const float* nnet_output, int64_t num_frames,
+                                              int64_t num_sequences, int64_t num_pdfs,
+                                              const int64_t* nnet_output_strides /* [3] */,
+                                              float* results, float* results_dev,
+                                              float* nnet_output_deriv, const int64_t* deriv_strides /* [3] */,
+                                              float* xent_output_deriv, const int64_t* xent_strides /* [3] */,
+                                              float l2_regularize, float leaky_hmm_coefficient,
+                                              float xent_regularize, float deriv_scale,
+                                              int device, void* stream);
+
+/* Replace `to2d` (torchain/functions.py:118-125: x.permute(2, 0, 1).contiguous().view(-1, C))
+ * and the permuted gradient copy its autograd backward makes: tiled relayout kernels between a
+ * contiguous (B, P, T) device tensor and the (T*B, P) matrix (row = t*B + b, row stride in
+ * elements).  torchain_from2d multiplies by `scale`.  Return 0 when T or B is too large for
+ * the tiled kernel (T > 1599 frames, B > 65535); the caller then permutes some other way. */
+int torchain_to2d(const float* x_bpt, int64_t num_sequences, int64_t num_pdfs, int64_t num_frames,
+                  float* out_rows, int64_t out_stride, int device, void* stream);
+int torchain_from2d(const float* rows, int64_t in_stride, int64_t num_sequences, int64_t num_pdfs,
+                    int64_t num_frames, float* out_bpt, float scale, int device, void* stream);
+
 /* Host-buffer form (what a non-torch host binding would call): nnet_output,
  * nnet_output_deriv (and xent_output_deriv, may be NULL) are HOST pointers,
  * ideally pinned; the call copies the input to the device, runs the loss and

@@ -479,3 +479,168 @@ def test_gpu_two_threads_two_streams():
         res, d = results[i]
         assert rel(res[0], ref[0]) < OBJF_RTOL
         assert float((d - ref_d).abs().max()) <= 1e-4 * float(ref_d.abs().max())
+
+
+# ---------------------------------------------------------------- strided (to2d-free) entry
+def run_strided(g, s, y_np, B, T, l2, leaky, layout, xent=0.0, want_xent=False, deriv_scale=1.0):
+    """torchain_ComputeChainObjfAndDeriv_strided on a device tensor laid out as `layout`:
+    "BPT" = the network's native (B, P, T); "BTP" = (B, T, P); "TBP" = the reference's 2-D form.
+    Returns results and the derivative(s) brought back to the (T*B, P) order of the oracle."""
+    import torch
+    lib = _lib.load()
+    P = y_np.shape[1]
+    y_tbp = torch.from_numpy(np.ascontiguousarray(y_np, dtype=np.float32)).cuda().view(T, B, P)
+    perm = {"BPT": (1, 2, 0), "BTP": (1, 0, 2), "TBP": (0, 1, 2)}[layout]
+    y = y_tbp.permute(*perm).contiguous()
+    names = layout
+
+    def strides(x):
+        return (ctypes.c_int64 * 3)(x.stride(names.index("T")), x.stride(names.index("B")), x.stride(names.index("P")))
+
+    deriv = torch.full_like(y, float("nan"))
+    xd = torch.full_like(y, float("nan")) if want_xent else None
+    res = np.zeros(3, dtype=np.float32)
+    ok = lib.torchain_ComputeChainObjfAndDeriv_strided(
+        g.ptr, s.ptr, y.data_ptr(), T, B, P, strides(y), res.ctypes.data_as(ctypes.c_void_p), None,
+        deriv.data_ptr(), strides(deriv), xd.data_ptr() if want_xent else None, strides(xd) if want_xent else None,
+        l2, leaky, xent, deriv_scale, torch.cuda.current_device(),
+        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert ok == 1, _lib.last_error()
+    torch.cuda.synchronize()
+    inv = [perm.index(i) for i in range(3)]
+    back = lambda x: x.permute(*inv).reshape(T * B, P).cpu().numpy()
+    return res, back(deriv), (back(xd) if want_xent else None)
+
+
+@pytest.mark.parametrize("layout", ["BPT", "BTP", "TBP"])
+@pytest.mark.parametrize("seed", [0, 3, 5, 11, 18, 26])
+def test_gpu_strided_layouts_match_oracle(seed, layout):
+    """Row f4 of SURVEY.md section 8: the network output read in its own (B, P, T) layout and the
+    gradient written there, no to2d copy; same numbers as the 2-D path."""
+    c = synth.small_case(seed)
+    sup = c["sup"]
+    r = ol.chain(ol.OracleDen(c["den"]), ol.OracleSup(sup), c["y"], l2=c["l2"], leaky=c["leaky"], mode="fp64",
+                 want_xent=True)
+    g, s = handles(c["den"], sup)
+    res, d, x = run_strided(g, s, c["y"], sup.num_sequences, sup.frames_per_sequence, c["l2"], c["leaky"], layout,
+                            xent=0.1, want_xent=True)
+    assert rel(res[0], r["objf"]) < OBJF_RTOL
+    assert abs(res[1] - r["l2_term"]) <= OBJF_RTOL * max(abs(r["l2_term"]), 1e-30)
+    assert res[2] == pytest.approx(r["weight"])
+    assert deriv_err(d, r["deriv"]) < DERIV_RTOL
+    assert deriv_err(x, r["xent"]) < DERIV_RTOL
+
+
+@pytest.mark.parametrize("B,T,N,P", [(64, 11, 500, 100), (128, 9, 700, 130), (200, 5, 350, 90)])
+def test_gpu_strided_bpt_batch_shapes(B, T, N, P):
+    den = synth.make_den_fst(B, N, P, mean_deg=6.0)
+    sup = synth.make_supervision(B + 1, den, B, T, num_paths=3, weight=0.5)
+    y = synth.make_nnet_output(B + 2, B, T, P, scale=1.5)
+    r = ol.chain(ol.OracleDen(den), ol.OracleSup(sup), y, l2=5e-5, leaky=0.1, mode="fp64", threads=4)
+    g, s = handles(den, sup)
+    res, d, _ = run_strided(g, s, y, B, T, 5e-5, 0.1, "BPT", deriv_scale=-1.0)
+    assert rel(res[0], r["objf"]) < OBJF_RTOL
+    assert rel(res[1], r["l2_term"]) < OBJF_RTOL
+    assert deriv_err(-d, r["deriv"]) < DERIV_RTOL
+
+
+def test_gpu_strided_guard_on_nan():
+    """Kaldi's numeric guard rewrites the whole derivative: it must follow the caller's layout too."""
+    c = synth.small_case(1)
+    sup = c["sup"]
+    g, s = handles(c["den"], sup)
+    y = c["y"].copy()
+    y[0, 0] = np.nan
+    res, d, x = run_strided(g, s, y, sup.num_sequences, sup.frames_per_sequence, 0.0, 0.1, "BPT", xent=0.1,
+                            want_xent=True)
+    assert res[0] == pytest.approx(-10.0 * res[2])
+    assert np.all(d == 0.0) and np.all(x == 0.0)
+
+
+def test_gpu_strided_error_paths():
+    import torch
+    lib = _lib.load()
+    c = synth.small_case(2)
+    sup = c["sup"]
+    g, s = handles(c["den"], sup)
+    B, T, P = sup.num_sequences, sup.frames_per_sequence, c["y"].shape[1]
+    y = torch.zeros(B, P, T, device="cuda")
+    d = torch.empty_like(y)
+    res = np.zeros(3, dtype=np.float32)
+    good = (ctypes.c_int64 * 3)(1, P * T, T)
+    zero = (ctypes.c_int64 * 3)(1, 0, T)
+    call = lambda nt, ys, ds: lib.torchain_ComputeChainObjfAndDeriv_strided(
+        g.ptr, s.ptr, y.data_ptr(), nt, B, P, ys, res.ctypes.data_as(ctypes.c_void_p), None, d.data_ptr(), ds,
+        None, None, 0.0, 0.1, 0.0, 1.0, 0, None)
+    assert call(T + 1, good, good) == 0 and "frames" in _lib.last_error()
+    assert call(T, None, good) == 0 and "stride" in _lib.last_error()
+    assert call(T, good, zero) == 0 and "positive" in _lib.last_error()
+    assert call(T, good, good) == 1, _lib.last_error()
+    torch.cuda.synchronize()
+
+
+def test_gpu_chain_loss_3d_input_needs_no_to2d():
+    """chain_loss on the (B, P, T) network output equals the reference's to2d route
+    (functions.py:118-138) in loss, results and the gradient reaching the 3-D tensor."""
+    import torch
+    from torchain_b200.functions import chain_loss, to2d
+    c = synth.small_case(9)
+    sup = c["sup"]
+    B, T, P = sup.num_sequences, sup.frames_per_sequence, c["y"].shape[1]
+    g, s = handles(c["den"], sup)
+    x3 = torch.from_numpy(c["y"]).cuda().view(T, B, P).permute(1, 2, 0).contiguous()
+    xe3 = (0.5 * x3 + 0.1).contiguous()
+
+    def run(use_to2d, **kw):
+        a = x3.clone().requires_grad_(True)
+        b = xe3.clone().requires_grad_(True)
+        loss, results = chain_loss(to2d(a) if use_to2d else a, g, s, l2_regularize=0.01, leaky_hmm_coefficient=0.1,
+                                   xent_regularize=0.1, xent_input=to2d(b) if use_to2d else b, **kw)
+        loss.backward()
+        return float(loss), results.data.clone(), a.grad.cpu().numpy(), b.grad.cpu().numpy()
+
+    for kw in ({"kaldi_way": True}, {"kaldi_way": False}):
+        l2d, r2d, ga2, gb2 = run(True, **kw)
+        l3d, r3d, ga3, gb3 = run(False, **kw)
+        assert l3d == pytest.approx(l2d, rel=1e-6)
+        assert torch.allclose(r3d, r2d, rtol=1e-6)
+        assert ga3.shape == (B, P, T) and gb3.shape == (B, P, T)
+        assert deriv_err(ga3, ga2.astype(np.float64)) < 1e-5
+        assert deriv_err(gb3, gb2.astype(np.float64)) < 1e-5
+    # a (B, T, P) tensor viewed as (B, P, T): arbitrary strides are read in place as well
+    v = x3.permute(0, 2, 1).contiguous().permute(0, 2, 1).requires_grad_(True)
+    assert not v.is_contiguous()
+    loss, results = chain_loss(v, g, s, l2_regularize=0.01, leaky_hmm_coefficient=0.1)
+    loss.backward()
+    a = x3.clone().requires_grad_(True)
+    loss2, _ = chain_loss(to2d(a), g, s, l2_regularize=0.01, leaky_hmm_coefficient=0.1)
+    loss2.backward()
+    assert float(loss) == pytest.approx(float(loss2), rel=1e-6)
+    assert deriv_err(v.grad.cpu().numpy(), a.grad.cpu().numpy().astype(np.float64)) < 1e-5
+
+
+@pytest.mark.parametrize("B,P,T", [(1, 1, 2), (3, 5, 7), (4, 33, 50), (2, 64, 256), (5, 70, 300), (128, 96, 50),
+                                   (2, 31, 1599)])
+def test_gpu_relayout_kernels_equal_permute(B, P, T):
+    """torchain_to2d / torchain_from2d are bit-exact copies of the reference's to2d
+    (functions.py:118-125) and of the permute its backward applies to the gradient."""
+    import torch
+    from torchain_b200.functions import to2d
+    x = torch.randn(B, P, T, device="cuda")
+    want = x.permute(2, 0, 1).contiguous().view(-1, P)
+    xg = x.clone().requires_grad_(True)
+    rows = to2d(xg)
+    assert rows.shape == (T * B, P) and torch.equal(rows, want)
+    w = torch.randn_like(rows)
+    (rows * w).sum().backward()
+    assert torch.equal(xg.grad, w.view(T, B, P).permute(1, 2, 0))
+    # padded row stride and scaling through the C ABI
+    lib = _lib.load()
+    pad = torch.full((T * B, P + 3), 7.0, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.torchain_to2d(x.data_ptr(), B, P, T, pad.data_ptr(), P + 3, 0, st) == 1, _lib.last_error()
+    assert torch.equal(pad[:, :P], want) and bool((pad[:, P:] == 7.0).all())
+    back = torch.empty_like(x)
+    assert lib.torchain_from2d(pad.data_ptr(), P + 3, B, P, T, back.data_ptr(), -2.0, 0, st) == 1, _lib.last_error()
+    assert torch.equal(back, -2.0 * x)
+    assert lib.torchain_to2d(x.data_ptr(), B, P, T, pad.data_ptr(), P - 1, 0, st) == 0

@@ -49,6 +49,11 @@ SIGNATURES = {
     "torchain_ComputeChainObjfAndDeriv_ex": (
         _c_i, [_c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_i64,
                _c_f, _c_f, _c_f, _c_f, _c_i, _c_p]),
+    "torchain_ComputeChainObjfAndDeriv_strided": (
+        _c_i, [_c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p,
+               _c_f, _c_f, _c_f, _c_f, _c_i, _c_p]),
+    "torchain_to2d": (_c_i, [_c_p, _c_i64, _c_i64, _c_i64, _c_p, _c_i64, _c_i, _c_p]),
+    "torchain_from2d": (_c_i, [_c_p, _c_i64, _c_i64, _c_i64, _c_i64, _c_p, _c_f, _c_i, _c_p]),
     "torchain_ComputeChainObjfAndDeriv_host": (
         _c_i, [_c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_p, _c_p, _c_i64, _c_p, _c_i64,
                _c_f, _c_f, _c_f, _c_i]),

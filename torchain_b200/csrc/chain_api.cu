@@ -927,9 +927,13 @@ struct ChunkedInput {
 
 // The whole loss, enqueued on `stream`: forward launch -> numerator -> backward launch ->
 // final scalars.  results_host may be null (then nothing synchronises).
-int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t cols, int64_t ystride,
-            float* results_host, float* results_dev_user, float* deriv, int64_t dstride, float* xent,
-            int64_t xstride, float l2, float leaky, float xent_regularize, float deriv_scale, int device,
+// Matrices are described by tb::Layout3 (element strides over frame / sequence / pdf): the
+// reference's (T*B, P) form and a network output left in (B, P, T) go through the same kernels.
+tb::Layout3 row_layout(int B, int64_t row_stride) { return tb::Layout3{(int64_t)B * row_stride, row_stride, 1}; }
+
+int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t cols, tb::Layout3 yl,
+            float* results_host, float* results_dev_user, float* deriv, tb::Layout3 dl, float* xent,
+            tb::Layout3 xl, float l2, float leaky, float xent_regularize, float deriv_scale, int device,
             cudaStream_t stream, ChunkedInput chunked = ChunkedInput()) {
   if (!g || !sup) return fail("null den_graph / supervision handle");
   if (!y) return fail("null nnet_output");
@@ -937,7 +941,9 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   if (rows != (int64_t)B * T) return fail("nnet_output rows != num_sequences * frames_per_sequence");
   if (cols != P) return fail("nnet_output cols != den_graph.NumPdfs()");
   if (sup->P != P) return fail("supervision.label_dim != den_graph.NumPdfs()");
-  if (ystride < cols || (deriv && dstride < cols) || (xent && xstride < cols)) return fail("row stride < cols");
+  if (yl.t < 0 || yl.s < 0 || yl.p < 0) return fail("negative nnet_output stride");
+  if ((deriv && (dl.t <= 0 || dl.s <= 0 || dl.p <= 0)) || (xent && (xl.t <= 0 || xl.s <= 0 || xl.p <= 0)))
+    return fail("derivative strides must be positive");
   if (!(leaky > 0.f && leaky < 1.f)) return fail("leaky_hmm_coefficient must be in (0, 1)");
   if ((int64_t)N * tb::kCtxBP * 4 >= (1ll << 32) || (int64_t)P * tb::kCtxBP * 4 >= (1ll << 32))
     return fail("graph too large for 32-bit row byte offsets");
@@ -955,7 +961,7 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   if (!deriv) {  // objective only: derivatives go to scratch
     CUDA_OK(ws->scratch_deriv.reserve(sizeof(float) * (size_t)rows * cols));
     deriv = ws->scratch_deriv.as<float>();
-    dstride = cols;
+    dl = row_layout(B, cols);
   }
 
   // ---- numerator scratch
@@ -978,8 +984,9 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   np.arc_row = sd->arc_row.as<int>();
   np.arc_pdf = sd->arc_pdf.as<int>();
   np.arc_cost = sd->arc_cost.as<float>();
+  np.B = B;
   np.y = y;
-  np.ystride = ystride;
+  np.yl = yl;
   np.arc_val = reinterpret_cast<double*>(nb + off_arcval);
   np.log_alpha = reinterpret_cast<double*>(nb + off_la);
   np.log_beta = reinterpret_cast<double*>(nb + off_lb);
@@ -1038,9 +1045,9 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   dp.Btot = B;
   dp.T = T;
   dp.y = y;
-  dp.ystride = ystride;
+  dp.yl = yl;
   dp.deriv = deriv;
-  dp.dstride = dstride;
+  dp.dl = dl;
   dp.scalars = reinterpret_cast<double*>(zb + z_scal);
   dp.leaky = leaky;
   dp.sum_pi = (float)g->sum_pi;
@@ -1134,7 +1141,7 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
 
   // ---- final pass
   float* res_dev = reinterpret_cast<float*>(zb + z_res);
-  if (want_xent) CUDA_OK(cudaMemset2DAsync(xent, sizeof(float) * xstride, 0, sizeof(float) * cols, rows, stream));
+  if (want_xent) CUDA_OK(tb::launch_zero(xent, xl, T, B, P, stream));
   tb::FinalParams fp;
   fp.den_scalars = dp.scalars;
   fp.chain_logprob = np.chain_logprob;
@@ -1146,11 +1153,11 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   fp.deriv_scale = deriv_scale;
   fp.results_dev = res_dev;
   fp.deriv = deriv;
-  fp.dstride = dstride;
+  fp.dl = dl;
   fp.xent = want_xent ? xent : nullptr;
-  fp.xstride = xstride;
+  fp.xl = xl;
   fp.y = y;
-  fp.ystride = ystride;
+  fp.yl = yl;
   fp.rows = rows;
   fp.cols = cols;
   fp.num_arcs = sup->A;
@@ -1388,9 +1395,29 @@ int torchain_ComputeChainObjfAndDeriv_ex(void* den, void* sup, const float* y, i
                                          int64_t ystride, float* results, float* results_dev, float* deriv,
                                          int64_t dstride, float* xent, int64_t xstride, float l2, float leaky,
                                          float xent_regularize, float deriv_scale, int device, void* stream) {
-  return compute(static_cast<DenGraph*>(den), static_cast<Supervision*>(sup), y, rows, cols, ystride, results,
-                 results_dev, deriv, dstride, xent, xstride, l2, leaky, xent_regularize, deriv_scale, device,
-                 static_cast<cudaStream_t>(stream));
+  if (!sup) return fail("null den_graph / supervision handle");
+  if (ystride < cols || (deriv && dstride < cols) || (xent && xstride < cols)) return fail("row stride < cols");
+  const int B = static_cast<Supervision*>(sup)->B;
+  return compute(static_cast<DenGraph*>(den), static_cast<Supervision*>(sup), y, rows, cols, row_layout(B, ystride),
+                 results, results_dev, deriv, row_layout(B, dstride), xent, row_layout(B, xstride), l2, leaky,
+                 xent_regularize, deriv_scale, device, static_cast<cudaStream_t>(stream));
+}
+
+int torchain_ComputeChainObjfAndDeriv_strided(void* den, void* sup, const float* y, int64_t num_frames,
+                                              int64_t num_sequences, int64_t num_pdfs, const int64_t* y_strides,
+                                              float* results, float* results_dev, float* deriv,
+                                              const int64_t* deriv_strides, float* xent, const int64_t* xent_strides,
+                                              float l2, float leaky, float xent_regularize, float deriv_scale,
+                                              int device, void* stream) {
+  if (!sup) return fail("null den_graph / supervision handle");
+  auto* sp = static_cast<Supervision*>(sup);
+  if (num_frames != sp->T || num_sequences != sp->B)
+    return fail("nnet_output frames / sequences != supervision frames_per_sequence / num_sequences");
+  if (!y_strides || (deriv && !deriv_strides) || (xent && !xent_strides)) return fail("null stride triple");
+  auto lay = [](const int64_t* st) { return st ? tb::Layout3{st[0], st[1], st[2]} : tb::Layout3{0, 0, 0}; };
+  return compute(static_cast<DenGraph*>(den), sp, y, num_frames * num_sequences, num_pdfs, lay(y_strides), results,
+                 results_dev, deriv, lay(deriv_strides), xent, lay(xent_strides), l2, leaky, xent_regularize,
+                 deriv_scale, device, static_cast<cudaStream_t>(stream));
 }
 
 int my_lib_ComputeChainObjfAndDeriv(void* den, void* sup, const float* y, int64_t rows, int64_t cols,
@@ -1398,9 +1425,36 @@ int my_lib_ComputeChainObjfAndDeriv(void* den, void* sup, const float* y, int64_
                                     int64_t xstride, float l2, float leaky, float xent_regularize, int device,
                                     void* stream) {
   if (!results) return fail("null results");
-  return compute(static_cast<DenGraph*>(den), static_cast<Supervision*>(sup), y, rows, cols, ystride, results,
-                 nullptr, deriv, dstride, xent, xstride, l2, leaky, xent_regularize, 1.0f, device,
-                 static_cast<cudaStream_t>(stream));
+  if (!sup) return fail("null den_graph / supervision handle");
+  if (ystride < cols || (deriv && dstride < cols) || (xent && xstride < cols)) return fail("row stride < cols");
+  const int B = static_cast<Supervision*>(sup)->B;
+  return compute(static_cast<DenGraph*>(den), static_cast<Supervision*>(sup), y, rows, cols, row_layout(B, ystride),
+                 results, nullptr, deriv, row_layout(B, dstride), xent, row_layout(B, xstride), l2, leaky,
+                 xent_regularize, 1.0f, device, static_cast<cudaStream_t>(stream));
+}
+
+int torchain_to2d(const float* x_bpt, int64_t B, int64_t P, int64_t T, float* out_rows, int64_t out_stride, int device,
+                  void* stream) {
+  if (!x_bpt || !out_rows) return fail("null tensor");
+  if (B < 0 || P < 0 || T < 0 || out_stride < P) return fail("bad shape / row stride < cols");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail("cannot select CUDA device");
+  cudaError_t e = tb::launch_to2d(x_bpt, out_rows, (int)B, (int)P, (int)T, out_stride, static_cast<cudaStream_t>(stream));
+  if (e == cudaErrorInvalidValue) return fail("to2d: frames_per_sequence or num_sequences too large for the tiled kernel");
+  CUDA_OK(e);
+  return 1;
+}
+
+int torchain_from2d(const float* rows, int64_t in_stride, int64_t B, int64_t P, int64_t T, float* out_bpt, float scale,
+                    int device, void* stream) {
+  if (!rows || !out_bpt) return fail("null tensor");
+  if (B < 0 || P < 0 || T < 0 || in_stride < P) return fail("bad shape / row stride < cols");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail("cannot select CUDA device");
+  cudaError_t e = tb::launch_from2d(rows, out_bpt, (int)B, (int)P, (int)T, in_stride, scale, static_cast<cudaStream_t>(stream));
+  if (e == cudaErrorInvalidValue) return fail("from2d: frames_per_sequence or num_sequences too large for the tiled kernel");
+  CUDA_OK(e);
+  return 1;
 }
 
 int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_host, int64_t rows, int64_t cols,
@@ -1415,6 +1469,8 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
   auto* sp = static_cast<Supervision*>(sup);
   if (rows != (int64_t)sp->B * sp->T) return fail("nnet_output rows != num_sequences * frames_per_sequence");
   if (cols != g->P) return fail("nnet_output cols != den_graph.NumPdfs()");
+  if (ystride < cols || (deriv_host && dstride < cols) || (xent_host && xstride < cols))
+    return fail("row stride < cols");
   HostPath& h = g_host;
   if (h.device != device) {
     if (h.compute) cudaStreamDestroy(h.compute);
@@ -1483,9 +1539,9 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
     CUDA_OK(res_buf.reserve(4 * sizeof(float)));
     res_dev = res_buf.as<float>();
   }
-  if (!compute(g, sp, h.y.as<float>(), rows, cols, cols, nullptr, res_dev, deriv_dev, deriv_dev_stride,
-               want_xent ? h.xent.as<float>() : nullptr, cols, l2, leaky, xent_regularize, 1.0f, device, h.compute,
-               ci))
+  if (!compute(g, sp, h.y.as<float>(), rows, cols, row_layout(B, cols), nullptr, res_dev, deriv_dev,
+               row_layout(B, deriv_dev_stride), want_xent ? h.xent.as<float>() : nullptr, row_layout(B, cols), l2,
+               leaky, xent_regularize, 1.0f, device, h.compute, ci))
     return 0;
   auto copy_chunk = [&](int k, cudaStream_t st) -> cudaError_t {
     const int64_t r0 = (int64_t)k * chunk_frames * B;

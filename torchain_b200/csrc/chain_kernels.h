@@ -6,6 +6,14 @@
 
 namespace tb {
 
+// Where element (frame t, sequence s, pdf c) of a caller matrix lives: base + t*st_t + s*st_s + c*st_p
+// (in floats).  The reference's 2-D form (T*B rows, row = t*B + s, /root/reference/torchain/functions.py:118-125)
+// is {B*row_stride, row_stride, 1}; a network output left in its native (B, P, T) shape is {1, P*T, T},
+// which lets the kernels read it and write its gradient in place of to2d's permute+contiguous copy.
+struct Layout3 {
+  int64_t t, s, p;
+};
+
 // ---------------------------------------------------------------------------
 // Denominator (persistent alpha / beta+derivative kernel)
 // ---------------------------------------------------------------------------
@@ -50,9 +58,9 @@ struct DenParams {
   int seq0;     // first sequence of this pass
   int T;
   const float* y;
-  int64_t ystride;
+  Layout3 yl;
   float* deriv;
-  int64_t dstride;
+  Layout3 dl;
   float* alpha;      // (T+1) x N x BP   un-mixed alphas (Kaldi stores alpha-dash; we mix on the fly)
   float* beta;       // 3 x N x BP       beta-dash rotation (write / gather / re-zero)
   float* etile;      // 2 x P x BP       exp(y) of one frame, sequence-innermost
@@ -119,8 +127,9 @@ struct NumParams {
   const int* arc_row;           // [A] row of nnet_output (frame*B + seq)
   const int* arc_pdf;           // [A]
   const float* arc_cost;        // [A]
+  int B;                        // sequences in the minibatch (row -> frame = row / B, seq = row % B)
   const float* y;
-  int64_t ystride;
+  Layout3 yl;
   double* arc_val;              // [A] scratch: y - cost
   double* log_alpha;            // [S]
   double* log_beta;             // [S]
@@ -141,12 +150,12 @@ struct FinalParams {
   float* results_dev;           // [4]: objf, l2_term, weight, ok
   // derivative fix-up
   float* deriv;
-  int64_t dstride;
+  Layout3 dl;
   float* xent;                  // may be null
-  int64_t xstride;
+  Layout3 xl;
   const float* y;
-  int64_t ystride;
-  int64_t rows, cols;
+  Layout3 yl;
+  int64_t rows, cols;           // rows = B*T
   // numerator occupancies per arc (only needed for the optional xent output)
   int num_arcs;
   const int* arc_row;
@@ -154,6 +163,15 @@ struct FinalParams {
   const float* arc_post;
 };
 cudaError_t launch_final(const FinalParams& p, cudaStream_t stream);
+// x(t, s, c) = 0 over T x B x P elements of a strided matrix (the xent output accumulates with atomics)
+cudaError_t launch_zero(float* x, Layout3 l, int T, int B, int P, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------
+// Relayout of the network output / gradient (layout_kernel.cu): x (B, P, T) contiguous <-> rows t*B + s
+// ---------------------------------------------------------------------------
+cudaError_t launch_to2d(const float* x_bpt, float* y_rows, int B, int P, int T, int64_t stride, cudaStream_t stream);
+cudaError_t launch_from2d(const float* y_rows, float* x_bpt, int B, int P, int T, int64_t stride, float scale,
+                          cudaStream_t stream);
 
 // kernels launched by this library so far (process-wide)
 void count_launch(int n = 1);

@@ -177,15 +177,12 @@ __device__ __forceinline__ void stage_exp_tile(const DenParams& p, int t, float*
                                                bool want_sq, double& sumsq) {
   const int BP = p.BP;
   const int nts = BP >> 5;
-  const float* yrow0 = p.y + ((int64_t)t * p.Btot + p.seq0) * p.ystride;
   const int s0 = (i % nts) << 5, p0 = (i / nts) << 5;
   const int pdf = p0 + lane;
+  const float* ycol = p.y + (int64_t)t * p.yl.t + (int64_t)(p.seq0 + s0) * p.yl.s + (int64_t)pdf * p.yl.p;
   float v[32];
 #pragma unroll
-  for (int j = 0; j < 32; j++) {
-    const int s = s0 + j;
-    v[j] = (s < p.B && pdf < p.P) ? __ldg(yrow0 + (int64_t)s * p.ystride + pdf) : 0.f;
-  }
+  for (int j = 0; j < 32; j++) v[j] = (s0 + j < p.B && pdf < p.P) ? __ldg(ycol + (int64_t)j * p.yl.s) : 0.f;
 #pragma unroll
   for (int j = 0; j < 32; j++) {
     if (want_sq) sumsq += (double)v[j] * (double)v[j];
@@ -207,28 +204,33 @@ __device__ __forceinline__ void flush_gamma_tile(const DenParams& p, int frame, 
                                                  int lane, bool want_sum, double& gsum) {
   const int BP = p.BP;
   const int nts = BP >> 5;
-  const int64_t row0 = (int64_t)frame * p.Btot + p.seq0;
   const int s0 = (i % nts) << 5, p0 = (i / nts) << 5;
   const int pdf = p0 + lane;
+  const float* ycol = p.y + (int64_t)frame * p.yl.t + (int64_t)(p.seq0 + s0) * p.yl.s + (int64_t)pdf * p.yl.p;
+  float* dcol = p.deriv + (int64_t)frame * p.dl.t + (int64_t)(p.seq0 + s0) * p.dl.s + (int64_t)pdf * p.dl.p;
   float g[32], yv[32];
 #pragma unroll
   for (int k = 0; k < 32; k++) g[k] = (p0 + k < p.P) ? __ldcg(gtile + (size_t)(p0 + k) * BP + s0 + lane) : 0.f;
   const bool want_y = p.scale_y != 0.f;
 #pragma unroll
   for (int j = 0; j < 32; j++)
-    yv[j] = (want_y && s0 + j < p.B && pdf < p.P) ? __ldg(p.y + (row0 + s0 + j) * p.ystride + pdf) : 0.f;
+    yv[j] = (want_y && s0 + j < p.B && pdf < p.P) ? __ldg(ycol + (int64_t)j * p.yl.s) : 0.f;
 #pragma unroll
   for (int k = 0; k < 32; k++) {
     if (p0 + k < p.P) gtile[(size_t)(p0 + k) * BP + s0 + lane] = 0.f;
     tile[k * 33 + lane] = g[k];
   }
   __syncwarp();
+  // pdf-innermost rows are written whole (streaming, evict-first); with any other layout a 32 B
+  // sector is completed over several frames and has to stay in L2 until then
+  const bool stream_out = p.dl.p == 1;
 #pragma unroll
   for (int j = 0; j < 32; j++) {
-    const int s = s0 + j;
-    if (s < p.B && pdf < p.P) {
+    if (s0 + j < p.B && pdf < p.P) {
       const float gg = tile[lane * 33 + j];
-      __stcs(p.deriv + (row0 + s) * p.dstride + pdf, fmaf(p.scale_y, yv[j], p.scale_gamma * gg));
+      const float d = fmaf(p.scale_y, yv[j], p.scale_gamma * gg);
+      if (stream_out) __stcs(dcol + (int64_t)j * p.dl.s, d);
+      else dcol[(int64_t)j * p.dl.s] = d;
       if (want_sum) gsum += (double)gg;
     }
   }

@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(kNumThreads) num_fb_kernel(const __grid_consta
   // 1. gather y - cost for every arc of the chain
   const int a0 = p.chain_arc_off[chain], a1 = p.chain_arc_off[chain + 1];
   for (int a = a0 + lane; a < a1; a += 32) {
-    const float yv = __ldg(p.y + (int64_t)p.arc_row[a] * p.ystride + p.arc_pdf[a]);
+    const int row = p.arc_row[a], fr = row / p.B;
+    const float yv = __ldg(p.y + fr * p.yl.t + (row - fr * p.B) * p.yl.s + p.arc_pdf[a] * p.yl.p);
     p.arc_val[a] = (double)yv - (double)p.arc_cost[a];
   }
   __syncwarp();
@@ -147,17 +148,40 @@ __global__ void __launch_bounds__(256) final_deriv_kernel(const __grid_constant_
   if (ok) {
     if (p.xent) {
       const float wscale = p.deriv_scale * p.sup_weight;
-      for (int64_t a = tid; a < p.num_arcs; a += nthreads)
-        atomicAdd(p.xent + (int64_t)p.arc_row[a] * p.xstride + p.arc_pdf[a], wscale * p.arc_post[a]);
+      for (int64_t a = tid; a < p.num_arcs; a += nthreads) {
+        const int row = p.arc_row[a], fr = row / p.B;
+        atomicAdd(p.xent + fr * p.xl.t + (row - fr * p.B) * p.xl.s + p.arc_pdf[a] * p.xl.p, wscale * p.arc_post[a]);
+      }
     }
   } else {
     const float sy = -p.deriv_scale * p.sup_weight * p.l2;
     const int64_t total = p.rows * p.cols;
     for (int64_t i = tid; i < total; i += nthreads) {
-      const int64_t r = i / p.cols, c = i - r * p.cols;
-      if (p.deriv) p.deriv[r * p.dstride + c] = (p.l2 != 0.f) ? sy * p.y[r * p.ystride + c] : 0.f;
-      if (p.xent) p.xent[r * p.xstride + c] = 0.f;
+      const int64_t r = i / p.cols, c = i - r * p.cols, fr = r / p.B, sq = r - fr * p.B;
+      if (p.deriv)
+        p.deriv[fr * p.dl.t + sq * p.dl.s + c * p.dl.p] =
+            (p.l2 != 0.f) ? sy * p.y[fr * p.yl.t + sq * p.yl.s + c * p.yl.p] : 0.f;
+      if (p.xent) p.xent[fr * p.xl.t + sq * p.xl.s + c * p.xl.p] = 0.f;
     }
+  }
+}
+
+// zero a T x B x P strided matrix; the index with the smallest stride runs fastest
+__global__ void __launch_bounds__(256) zero_kernel(float* x, Layout3 l, int T, int B, int P) {
+  const int64_t total = (int64_t)T * B * P;
+  const bool t_inner = l.t < l.p;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t t, s, c;
+    if (t_inner) {  // (s, c, t)
+      t = i % T;
+      c = (i / T) % P;
+      s = i / ((int64_t)T * P);
+    } else {  // (t, s, c)
+      c = i % P;
+      s = (i / P) % B;
+      t = i / ((int64_t)P * B);
+    }
+    x[t * l.t + s * l.s + c * l.p] = 0.f;
   }
 }
 
@@ -171,6 +195,12 @@ cudaError_t launch_numerator(const NumParams& p, cudaStream_t stream) {
   const int chains_per_cta = kNumThreads / 32;
   const int grid = (p.num_chains + chains_per_cta - 1) / chains_per_cta;
   num_fb_kernel<<<grid, kNumThreads, 0, stream>>>(p);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_zero(float* x, Layout3 l, int T, int B, int P, cudaStream_t stream) {
+  zero_kernel<<<148 * 8, 256, 0, stream>>>(x, l, T, B, P);
   count_launch();
   return cudaGetLastError();
 }
