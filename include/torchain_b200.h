@@ -229,6 +229,10 @@ double torchain_microbench_l2_gather(int device, int64_t table_bytes, int row_by
 double torchain_microbench_l2_red(int device, int64_t table_bytes, int row_bytes, int iters);
 /* Mean latency in microseconds of the software grid barrier at one CTA per SM. */
 double torchain_microbench_grid_barrier(int device, int iters);
+/* Feasibility probe of a sequence-sliced recurrence: CTAs own 8 or 16 sequences with
+ * exp(y) (mode 1: and the occupancies) in shared memory, 32 / 64-byte state gathers from L2, streamed arcs.
+ * Returns microseconds per frame on a synthetic graph of config 2's shape; <0 on error. */
+double torchain_microbench_sliced(int device, int seqs_per_cta, int depth, int mode, int frames);
 /* The forward recurrence's gather pattern (5 MB + 1.5 MB tables, 512-byte rows) with `warps` warps per SM
  * and `depth` (8, 12, 16 or 24) gathers in flight per warp; GB/s. */
 double torchain_microbench_pattern(int device, int warps, int depth, int iters);

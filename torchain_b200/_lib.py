@@ -65,6 +65,7 @@ SIGNATURES = {
     "torchain_microbench_l2_red": (_c_d, [_c_i, _c_i64, _c_i, _c_i]),
     "torchain_microbench_grid_barrier": (_c_d, [_c_i, _c_i]),
     "torchain_microbench_pattern": (_c_d, [_c_i, _c_i, _c_i, _c_i]),
+    "torchain_microbench_sliced": (_c_d, [_c_i, _c_i, _c_i, _c_i, _c_i]),
 }
 
 _lib = None

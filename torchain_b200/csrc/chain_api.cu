@@ -1641,4 +1641,8 @@ double torchain_microbench_pattern(int device, int warps, int depth, int iters) 
   return tb::microbench_pattern(device, warps, depth, iters);
 }
 
+double torchain_microbench_sliced(int device, int seqs_per_cta, int depth, int mode, int frames) {
+  return tb::microbench_sliced(device, seqs_per_cta, depth, mode, frames);
+}
+
 }  // extern "C"

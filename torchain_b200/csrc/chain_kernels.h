@@ -182,5 +182,6 @@ double microbench_l2_gather(int device, int64_t table_bytes, int row_bytes, int 
 double microbench_l2_red(int device, int64_t table_bytes, int row_bytes, int iters);
 double microbench_grid_barrier(int device, int iters);
 double microbench_pattern(int device, int warps, int depth, int iters);
+double microbench_sliced(int device, int S, int depth, int mode, int frames);
 
 }  // namespace tb

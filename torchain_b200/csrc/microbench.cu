@@ -4,6 +4,10 @@
 
 #include "chain_kernels.h"
 
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
 namespace tb {
 namespace {
 
@@ -102,6 +106,255 @@ __global__ void __launch_bounds__(1024) pattern_kernel(const float4* __restrict_
   }
   if (acc.x + acc.y + acc.z + acc.w == 123.456f) *sink = acc.x;
 }
+
+
+// ---------------------------------------------------------------------------
+// Feasibility probe for the sequence-sliced recurrence: a CTA owns S = 8 or
+// 16 sequences and 1/M of the arcs (G = 128/S groups of M = 148/G CTAs); exp(y_t) of its sequences lives in
+// shared memory ([pdf][S], re-staged every frame), alpha / beta rows are gathered from L2 as ONE 4*S-byte
+// segment per arc, arc records are streamed from global memory (interleaved so that a warp step is one
+// coalesced load), 4 lanes (S = 16) or 2 lanes (S = 8) walk one arc stream with float4 vectors, i.e. a warp
+// advances 8 / 16 streams at once.  MODE 1 adds the backward pass's occupancy accumulation as shared-memory
+// atomics into a [pdf][S] slice that is RED-ed into the global tile at the end of the frame (S = 8 only:
+// two slices must fit).  Synthetic graph of config 2's shape; the numbers mean nothing, the time does.
+// ---------------------------------------------------------------------------
+struct SlicedArgs {
+  const float* table;   // [2][N][128] alpha (or beta) ping-pong
+  float* table_w;
+  const float* y;       // [frames][128][P]
+  const int* src;       // [M][steps*streams_per_cta] row index of the other state, stream-interleaved per warp
+  const int4* rec;      // same order: {pdf, prob | end-of-state flag, this state, pi bits}
+  float* gtile;         // [P][128] occupancy tile (MODE 1)
+  unsigned* barriers;   // [G][32]
+  int N, P, frames, steps, M;
+  int stage_once;  // 1: exp(y) is staged for frame 0 only (separates the staging cost from the gather phase)
+};
+
+template <int S, int DEPTH, int MODE>
+__global__ void __launch_bounds__(512, 1) sliced_kernel(const __grid_constant__ SlicedArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int L = S / 4, STREAMS = 32 / L, G = 128 / S;
+  float* esm = sm;                 // [P][S]
+  float* gsm = sm + (size_t)a.P * S;  // [P][S] (MODE 1)
+  if ((int)blockIdx.x >= G * a.M) return;
+  const int g = blockIdx.x % G, m = blockIdx.x / G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int li = lane % L;
+  const int nwarps = blockDim.x >> 5;
+  // element (step k, this lane's stream) of this warp's interleaved arc arrays
+  const size_t wbase = ((size_t)m * nwarps + warp) * a.steps * STREAMS + lane / L;
+  unsigned epoch = 0;
+  float4 keep = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (MODE >= 1)
+    for (int i = threadIdx.x; i < a.P * S; i += blockDim.x) gsm[i] = 0.f;
+  for (int t = 0; t < a.frames; t++) {
+    // stage exp(y_t) of sequences [g*S, g*S+S): coalesced along pdf, 16-byte chunks swizzled by pdf
+    for (int i = threadIdx.x; i < ((a.stage_once && t > 0) ? 0 : a.P * S); i += blockDim.x) {
+      const int s = i / a.P, pdf = i - s * a.P;
+      const float v = __ldg(a.y + ((size_t)t * 128 + g * S + s) * a.P + pdf);
+      esm[pdf * S + (((s >> 2) ^ (pdf & (L - 1))) << 2) + (s & 3)] = __expf(v * 0.01f);
+    }
+    __syncthreads();
+    const float* tr = a.table + (size_t)(t & 1) * a.N * 128 + g * S + li * 4;
+    float* tw = a.table_w + (size_t)((t + 1) & 1) * a.N * 128 + g * S + li * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float lam = 1e-3f, occ = 0.5f;
+    float4 av[2][DEPTH];
+    int4 rc[2][DEPTH];
+    int sn[2][DEPTH];  // row indices, fetched two batches ahead of their gathers
+    auto issue = [&](int b, int k) {  // gathers + records of batch k (its row indices are in sn[b])
+#pragma unroll
+      for (int u = 0; u < DEPTH; u++) {
+        av[b][u] = __ldcg(reinterpret_cast<const float4*>(tr + (size_t)sn[b][u] * 128));
+        rc[b][u] = __ldg(a.rec + wbase + (size_t)(k + u) * STREAMS);
+      }
+    };
+    auto fetch_src = [&](int b, int k) {
+#pragma unroll
+      for (int u = 0; u < DEPTH; u++) sn[b][u] = (k + u < a.steps) ? __ldg(a.src + wbase + (size_t)(k + u) * STREAMS) : 0;
+    };
+    auto consume = [&](int b) {
+#pragma unroll
+      for (int u = 0; u < DEPTH; u++) {
+        const int4 r = rc[b][u];
+        const float pr = fabsf(__int_as_float(r.y)), pi = __int_as_float(r.w);
+        const float4 e = *reinterpret_cast<const float4*>(esm + r.x * S + ((li ^ (r.x & (L - 1))) << 2));
+        const float4 x = av[b][u];
+        if (MODE == 0) {
+          acc.x = fmaf(fmaf(pi, lam, x.x) * pr, e.x, acc.x);
+          acc.y = fmaf(fmaf(pi, lam, x.y) * pr, e.y, acc.y);
+          acc.z = fmaf(fmaf(pi, lam, x.z) * pr, e.z, acc.z);
+          acc.w = fmaf(fmaf(pi, lam, x.w) * pr, e.w, acc.w);
+        } else {
+          const float v0 = pr * (x.x + lam) * e.x, v1 = pr * (x.y + lam) * e.y, v2 = pr * (x.z + lam) * e.z,
+                      v3 = pr * (x.w + lam) * e.w;
+          acc.x += v0; acc.y += v1; acc.z += v2; acc.w += v3;
+          float* gp = gsm + r.x * S + ((li ^ (r.x & (L - 1))) << 2);
+          if (MODE == 1) {  // fp32 shared atomics: ATOMS.CAST.SPIN loops on sm_100a
+            atomicAdd(gp + 0, v0 * occ);
+            atomicAdd(gp + 1, v1 * occ);
+            atomicAdd(gp + 2, v2 * occ);
+            atomicAdd(gp + 3, v3 * occ);
+          } else {  // MODE 2: 2^-30 fixed point (occupancies are probabilities), native integer ATOMS.ADD
+            int* ip = reinterpret_cast<int*>(gp);
+            const float fx = 1073741824.f * occ;
+            atomicAdd(ip + 0, __float2int_rn(v0 * fx));
+            atomicAdd(ip + 1, __float2int_rn(v1 * fx));
+            atomicAdd(ip + 2, __float2int_rn(v2 * fx));
+            atomicAdd(ip + 3, __float2int_rn(v3 * fx));
+          }
+        }
+        if (r.y < 0) {  // last arc of this state
+          *reinterpret_cast<float4*>(tw + (size_t)r.z * 128) = acc;
+          keep.x += acc.x;
+          acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    fetch_src(0, 0);
+    fetch_src(1, DEPTH);
+    issue(0, 0);
+    fetch_src(0, 2 * DEPTH);
+    for (int k = 0; k < a.steps; k += 2 * DEPTH) {  // steps is a multiple of 2*DEPTH
+      issue(1, k + DEPTH);
+      fetch_src(1, k + 3 * DEPTH);
+      consume(0);
+      if (k + 2 * DEPTH < a.steps) issue(0, k + 2 * DEPTH);
+      fetch_src(0, k + 4 * DEPTH);
+      consume(1);
+    }
+    if (MODE >= 1) {  // this CTA's partial occupancies of its S sequences -> global tile, slice cleared
+      __syncthreads();
+      for (int i = threadIdx.x; i < a.P * L; i += blockDim.x) {
+        const int pdf = i / L, c = i - pdf * L;
+        float4* sp = reinterpret_cast<float4*>(gsm + pdf * S + ((c ^ (pdf & (L - 1))) << 2));
+        const float4 v = *sp;
+        *sp = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* dst = a.gtile + (size_t)pdf * 128 + g * S + c * 4;
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
+      }
+    }
+    // barrier over the M CTAs of this sequence group
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      epoch += a.M;
+      __threadfence();
+      atomicAdd(a.barriers + g * 32, 1u);
+      unsigned v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.barriers + g * 32) : "memory");
+      } while (v < epoch);
+    }
+    __syncthreads();
+  }
+  if (keep.x == 123.456f) a.table_w[0] = keep.x;
+}
+
+template <int S, int DEPTH, int MODE>
+cudaError_t launch_sliced(const SlicedArgs& a, int sms, size_t smem) {
+  auto kern = sliced_kernel<S, DEPTH, MODE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  void* args[] = {const_cast<SlicedArgs*>(&a)};
+  e = cudaLaunchCooperativeKernel((void*)kern, dim3(sms), dim3(512), args, smem, 0);
+  count_launch();
+  return e;
+}
+
+}  // namespace
+
+// us per frame of the sliced probe; S = 8 | 16 sequences per CTA, depth = 4 | 8 arcs per batch (two batches in
+// flight), mode 0 = forward-like, 1 = backward-like (S = 8).  < 0 on error.
+double microbench_sliced(int device, int S, int depth, int mode, int frames) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+  const int stage_once = mode >= 4 ? 1 : 0;  // mode + 4: stage exp(y) once
+  mode &= 3;
+  if ((S != 8 && S != 16) || (depth != 4 && depth != 8) || (mode < 0 || mode > 2) || (mode >= 1 && S != 8) || frames < 1)
+    return -1.0;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const int N = 10000, P = 2928, deg = 30, A = N * deg;
+  const int G = 128 / S, M = sms / G, L = S / 4, STREAMS = 32 / L, nwarps = 16;
+  if (M < 1) return -1.0;
+  const int streams_cta = nwarps * STREAMS;
+  const int per_cta = (A + M - 1) / M, per_stream = (per_cta + streams_cta - 1) / streams_cta;
+  const int steps = (per_stream + 2 * depth - 1) / (2 * depth) * (2 * depth);
+  std::vector<int> src((size_t)M * streams_cta * steps, 0);
+  std::vector<int4> rec((size_t)M * streams_cta * steps, make_int4(0, 0, 0, 0));
+  unsigned rng = 12345u;
+  auto rnd = [&]() {
+    rng = rng * 1664525u + 1013904223u;
+    return rng >> 8;
+  };
+  for (int m = 0; m < M; m++)
+    for (int w = 0; w < nwarps; w++)
+      for (int st = 0; st < STREAMS; st++)
+        for (int k = 0; k < steps; k++) {
+          const int sidx = w * STREAMS + st;
+          const int arc = m * per_cta + sidx * per_stream + k;  // global arc id (destination-sorted)
+          const size_t o = (((size_t)m * nwarps + w) * steps + k) * STREAMS + st;
+          if (k < per_stream && arc < A) {
+            const int state = arc / deg;
+            float pr = 1.0f / deg, pi = 1e-4f;
+            int prb, pib;
+            std::memcpy(&prb, &pr, 4);
+            std::memcpy(&pib, &pi, 4);
+            if (arc % deg == deg - 1 || k == per_stream - 1) prb |= (int)0x80000000u;
+            src[o] = (int)(rnd() % N);
+            rec[o] = make_int4((int)(rnd() % P), prb, state, pib);
+          }
+        }
+  float *table = nullptr, *y = nullptr, *gtile = nullptr;
+  int* dsrc = nullptr;
+  int4* drec = nullptr;
+  unsigned* bar = nullptr;
+  const size_t tbytes = (size_t)2 * N * 128 * 4, ybytes = (size_t)frames * 128 * P * 4;
+  bool ok = cudaMalloc(&table, tbytes) == cudaSuccess && cudaMalloc(&y, ybytes) == cudaSuccess &&
+            cudaMalloc(&gtile, (size_t)P * 128 * 4) == cudaSuccess && cudaMalloc(&dsrc, src.size() * 4) == cudaSuccess &&
+            cudaMalloc(&drec, rec.size() * 16) == cudaSuccess && cudaMalloc(&bar, G * 32 * 4) == cudaSuccess;
+  double result = -1.0;
+  if (ok) {
+    cudaMemset(table, 0, tbytes);
+    cudaMemset(y, 0, ybytes);
+    cudaMemset(gtile, 0, (size_t)P * 128 * 4);
+    cudaMemcpy(dsrc, src.data(), src.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(drec, rec.data(), rec.size() * 16, cudaMemcpyHostToDevice);
+    SlicedArgs a{table, table, y, dsrc, drec, gtile, bar, N, P, frames, steps, M, stage_once};
+    const size_t smem = (size_t)P * S * 4 * (mode >= 1 ? 2 : 1);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4 && ok; rep++) {
+      cudaMemset(bar, 0, G * 32 * 4);
+      cudaEventRecord(e0);
+      cudaError_t e;
+      if (S == 16) e = depth == 4 ? launch_sliced<16, 4, 0>(a, sms, smem) : launch_sliced<16, 8, 0>(a, sms, smem);
+      else if (mode == 0) e = depth == 4 ? launch_sliced<8, 4, 0>(a, sms, smem) : launch_sliced<8, 8, 0>(a, sms, smem);
+      else if (mode == 1) e = depth == 4 ? launch_sliced<8, 4, 1>(a, sms, smem) : launch_sliced<8, 8, 1>(a, sms, smem);
+      else e = depth == 4 ? launch_sliced<8, 4, 2>(a, sms, smem) : launch_sliced<8, 8, 2>(a, sms, smem);
+      cudaEventRecord(e1);
+      ok = e == cudaSuccess && cudaEventSynchronize(e1) == cudaSuccess;
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (rep > 0) best = std::min(best, ms);
+    }
+    ok = ok && cudaGetLastError() == cudaSuccess;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ok) result = (double)best * 1e3 / frames;
+  }
+  cudaFree(table);
+  cudaFree(y);
+  cudaFree(gtile);
+  cudaFree(dsrc);
+  cudaFree(drec);
+  cudaFree(bar);
+  return result;
+}
+
+namespace {
 
 }  // namespace
 
