@@ -211,14 +211,20 @@ class _To2d(Function):
 
     @staticmethod
     def forward(ctx, x):
-        ctx.like = x.shape
+        ctx.shape = x.shape
         return _rows_of(x)
 
     @staticmethod
     def backward(ctx, grad_rows):
         if grad_rows.stride(1) != 1:
             grad_rows = grad_rows.contiguous()
-        return _rows_to(grad_rows, torch.empty(0, device=grad_rows.device).new_empty(ctx.like))
+        B, P, T = ctx.shape
+        out = grad_rows.new_empty(B, P, T)
+        dev, stream = _stream_args(grad_rows)
+        if _lib.load().torchain_from2d(grad_rows.data_ptr(), grad_rows.stride(0), B, P, T, out.data_ptr(), 1.0,
+                                       dev, stream) != 1:
+            raise RuntimeError("from2d failed: " + _lib.last_error())
+        return out
 
 
 def to2d(x):
