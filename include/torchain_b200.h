@@ -97,6 +97,13 @@ void* torchain_supervision_from_arrays(float weight, int32_t num_sequences,
  * a Kaldi-written file (none is available in the build environment). */
 void* torchain_supervision_from_kaldi_bytes(const void* data, int64_t nbytes, int64_t* consumed);
 
+/* Minibatch assembly: the hot-path part of Kaldi's MergeChainExamples / AppendSupervision, which the
+ * reference runs inside its egs reader (src/my_lib_example_rand.cpp:160).  Appends `n` supervisions
+ * (each with one or more sequences) sequence-major into a new handle whose num_sequences is the sum;
+ * like Kaldi it refuses (NULL) examples of different weight, frames_per_sequence or label_dim.  The
+ * inputs stay valid and owned by the caller. */
+void* torchain_supervision_merge(void* const* supervision_ptrs, int32_t n);
+
 /* The reference's reader-based constructors; egs reading is out of scope, so
  * these always return NULL and set the error string. */
 void* my_lib_supervision_new(void* reader_ptr);

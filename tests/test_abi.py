@@ -207,3 +207,31 @@ def test_supervision_from_kaldi_bytes_round_trip():
         io.Supervision.from_kaldi_bytes(blob[:40])
     with pytest.raises(ValueError):
         io.Supervision.from_kaldi_bytes(b"<Nnet3ChainEg> ")
+
+
+def _sup_handle(sup):
+    return io.Supervision.from_arrays(sup.weight, sup.num_sequences, sup.frames_per_sequence, sup.label_dim,
+                                      sup.arc_begin, sup.arc_dst, sup.arc_label, sup.arc_cost, sup.final_cost)
+
+
+def test_supervision_merge_host_logic():
+    """Minibatch assembly (Kaldi MergeChainExamples, reference src/my_lib_example_rand.cpp:160):
+    sizes add up, chains stay per sequence, inconsistent examples are refused like Kaldi does."""
+    den = synth.make_den_fst(3, 40, 10, mean_deg=3.0)
+    parts = [synth.make_supervision(10 + i, den, b, 5, num_paths=2) for i, b in enumerate((1, 2, 1, 3))]
+    hs = [_sup_handle(p) for p in parts]
+    m = io.Supervision.merge(hs)
+    assert m.shape == (7, 5, 10)
+    assert m.num_chains == sum(h.num_chains for h in hs) == 7
+    assert io.Supervision.merge([hs[1]]).shape == hs[1].shape
+    # the inputs stay usable (the merge copies)
+    del m
+    assert hs[0].shape == (1, 5, 10)
+    with pytest.raises(ValueError, match="empty"):
+        io.Supervision.merge([])
+    other_T = _sup_handle(synth.make_supervision(20, den, 1, 6, num_paths=2))
+    with pytest.raises(ValueError, match="inconsistent"):
+        io.Supervision.merge([hs[0], other_T])
+    other_w = _sup_handle(synth.make_supervision(21, den, 1, 5, num_paths=2, weight=0.5))
+    with pytest.raises(ValueError, match="inconsistent"):
+        io.Supervision.merge([hs[0], other_w])

@@ -644,3 +644,31 @@ def test_gpu_relayout_kernels_equal_permute(B, P, T):
     assert lib.torchain_from2d(pad.data_ptr(), P + 3, B, P, T, back.data_ptr(), -2.0, 0, st) == 1, _lib.last_error()
     assert torch.equal(back, -2.0 * x)
     assert lib.torchain_to2d(x.data_ptr(), B, P, T, pad.data_ptr(), P - 1, 0, st) == 0
+
+
+def test_gpu_supervision_merge_matches_appended_fst():
+    """A minibatch assembled with Supervision.merge from separate examples gives the numbers of the FST
+    Kaldi's AppendSupervision (Concat + RmEpsilon, synth.append_supervisions) would hand to the loss."""
+    den = synth.make_den_fst(5, 120, 30, mean_deg=4.0)
+    T = 7
+    parts = [synth.make_supervision(40 + i, den, b, T, num_paths=3, weight=0.5) for i, b in enumerate((1, 1, 3, 2, 1))]
+    B = sum(p.num_sequences for p in parts)
+    appended = synth.append_supervisions(parts)
+    assert appended.num_sequences == B
+    y = synth.make_nnet_output(9, B, T, den.num_pdfs, scale=1.5)
+    r = ol.chain(ol.OracleDen(den), ol.OracleSup(appended), y, l2=0.01, leaky=0.1, mode="fp64", want_xent=True)
+    g, s_ref = handles(den, appended)
+    hs = [handles(den, p)[1] for p in parts]
+    merged = io.Supervision.merge(hs)
+    assert merged.shape == (B, T, den.num_pdfs) and merged.num_chains == B
+    for s in (merged, s_ref):
+        res, d, x = run_abi(g, s, y, 0.01, 0.1, xent=0.1, want_xent=True)
+        assert rel(res[0], r["objf"]) < OBJF_RTOL
+        assert rel(res[1], r["l2_term"]) < OBJF_RTOL
+        assert res[2] == pytest.approx(r["weight"])
+        assert deriv_err(d, r["deriv"]) < DERIV_RTOL
+        assert deriv_err(x, r["xent"]) < DERIV_RTOL
+    # merging is associative: ((0,1),(2,3,4)) == (0,1,2,3,4)
+    nested = io.Supervision.merge([io.Supervision.merge(hs[:2]), io.Supervision.merge(hs[2:])])
+    res2, d2, _ = run_abi(g, nested, y, 0.01, 0.1)
+    assert rel(res2[0], r["objf"]) < OBJF_RTOL and deriv_err(d2, r["deriv"]) < DERIV_RTOL

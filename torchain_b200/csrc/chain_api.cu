@@ -1385,6 +1385,70 @@ void* my_lib_supervision_new(void*) {
 void* my_lib_supervision_rand_new(void*) {
   return fail_ptr("Kaldi egs readers are outside the chain-loss hot path; use torchain_supervision_from_arrays");
 }
+// Minibatch assembly (the hot-path part of what the reference gets from Kaldi's MergeChainExamples /
+// AppendSupervision, /root/reference/src/my_lib_example_rand.cpp:160): examples with equal weight,
+// frames_per_sequence and label_dim are appended sequence-major; Kaldi concatenates the FSTs and removes
+// the epsilons, which leaves the per-sequence chains independent -- exactly the split representation
+// kept here, so merging is a concatenation of chain lists with shifted state / arc / sequence indices.
+void* torchain_supervision_merge(void* const* sups, int32_t n) {
+  if (!sups || n <= 0) return fail_ptr("supervision merge: empty list");
+  for (int i = 0; i < n; i++)
+    if (!sups[i]) return fail_ptr("supervision merge: null handle");
+  const Supervision* first = static_cast<const Supervision*>(sups[0]);
+  int64_t Btot = 0;
+  for (int i = 0; i < n; i++) {
+    const Supervision* in = static_cast<const Supervision*>(sups[i]);
+    // Kaldi merges only equal weights / lengths and fails the minibatch otherwise
+    // ("Failed to merge 'chain' examples-- inconsistent lengths or weights?")
+    if (in->weight != first->weight || in->T != first->T || in->P != first->P)
+      return fail_ptr("supervision merge: inconsistent weight, frames_per_sequence or label_dim");
+    Btot += in->B;
+  }
+  if (Btot * first->T >= (int64_t)1 << 31) return fail_ptr("supervision merge: too many frames");
+  auto out = std::make_unique<Supervision>();
+  out->weight = first->weight;
+  out->T = first->T;
+  out->P = first->P;
+  out->B = (int)Btot;
+  out->chain_level_off.assign(1, 0);
+  out->chain_arc_off.assign(1, 0);
+  out->in_off.assign(1, 0);
+  out->out_off.assign(1, 0);
+  int seq_off = 0;
+  for (int i = 0; i < n; i++) {
+    const Supervision* in = static_cast<const Supervision*>(sups[i]);
+    const int state_off = out->S, arc_off = out->A, lvl_off = (int)out->level_state_off.size();
+    for (int v : in->level_state_off) out->level_state_off.push_back(v + state_off);
+    for (size_t k = 1; k < in->chain_level_off.size(); k++) out->chain_level_off.push_back(in->chain_level_off[k] + lvl_off);
+    for (size_t k = 1; k < in->chain_arc_off.size(); k++) out->chain_arc_off.push_back(in->chain_arc_off[k] + arc_off);
+    for (size_t k = 1; k < in->in_off.size(); k++) out->in_off.push_back(in->in_off[k] + arc_off);
+    for (size_t k = 1; k < in->out_off.size(); k++) out->out_off.push_back(in->out_off[k] + arc_off);
+    for (const int2& a : in->in_arcs) out->in_arcs.push_back(make_int2(a.x + state_off, a.y + arc_off));
+    for (const int2& a : in->out_arcs) out->out_arcs.push_back(make_int2(a.x + state_off, a.y + arc_off));
+    out->final_cost.insert(out->final_cost.end(), in->final_cost.begin(), in->final_cost.end());
+    out->arc_cost.insert(out->arc_cost.end(), in->arc_cost.begin(), in->arc_cost.end());
+    out->arc_pdf.insert(out->arc_pdf.end(), in->arc_pdf.begin(), in->arc_pdf.end());
+    for (int a = 0; a < in->A; a++) {
+      const int seq = in->arc_seq[a], frame = (in->arc_row[a] - seq) / in->B;  // row = frame * B + seq
+      out->arc_seq.push_back(seq + seq_off);
+      out->arc_row.push_back(frame * out->B + seq + seq_off);
+    }
+    out->num_chains += in->num_chains;
+    out->S += in->S;
+    out->A += in->A;
+    seq_off += in->B;
+  }
+  // arcs ordered by frame, for the backward launch's per-frame numerator scatter
+  const int T = out->T, NA = out->A;
+  out->frame_off.assign(T + 1, 0);
+  for (int a = 0; a < NA; a++) out->frame_off[out->arc_row[a] / out->B + 1]++;
+  for (int t = 0; t < T; t++) out->frame_off[t + 1] += out->frame_off[t];
+  out->frame_arcs.resize(NA);
+  std::vector<int> pos(out->frame_off.begin(), out->frame_off.end() - 1);
+  for (int a = 0; a < NA; a++) out->frame_arcs[pos[out->arc_row[a] / out->B]++] = a;
+  return out.release();
+}
+
 void my_lib_supervision_free(void* p) { delete static_cast<Supervision*>(p); }
 int my_lib_supervision_num_pdf(void* p) { return p ? static_cast<Supervision*>(p)->P : 0; }
 int my_lib_supervision_num_sequence(void* p) { return p ? static_cast<Supervision*>(p)->B : 0; }

@@ -77,6 +77,21 @@ class Supervision:
             raise ValueError("invalid supervision: " + _lib.last_error())
         return cls(ptr), int(consumed.value)
 
+    @classmethod
+    def merge(cls, supervisions):
+        """One minibatch supervision from a list of examples, appended sequence-major: what the
+        reference's egs reader obtains from Kaldi's MergeChainExamples
+        (/root/reference/src/my_lib_example_rand.cpp:160).  Rows of the matching nnet_output are
+        ``t * B_total + (sequences of example 0, then of example 1, ...)``."""
+        sups = list(supervisions)
+        if not sups:
+            raise ValueError("invalid supervision: empty list")
+        arr = (ctypes.c_void_p * len(sups))(*[s.ptr for s in sups])
+        ptr = _lib.load().torchain_supervision_merge(arr, len(sups))
+        if not ptr:
+            raise ValueError("invalid supervision: " + _lib.last_error())
+        return cls(ptr)
+
     @property
     def num_chains(self):
         return _lib.load().torchain_supervision_num_chains(self.ptr)
