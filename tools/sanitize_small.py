@@ -39,3 +39,35 @@ for (B, T, N, P, hubs) in [(5, 4, 60, 17, 0), (40, 3, 80, 21, 1), (70, 3, 90, 33
                                                     P, None, 0, 0.01, 0.1, 0.0, 0)
     assert ok == 1, _lib.last_error()
     print("ok", B, T, N, P, res, float(np.abs(dh - d.cpu().numpy()).max()))
+
+# strided (frame, sequence, pdf) entry on a (B, P, T) tensor, relayout kernels, merged supervision
+for (B, T, N, P) in [(5, 4, 60, 17), (37, 6, 80, 33)]:
+    den = synth.make_den_fst(B + 7, N, P, mean_deg=3.0)
+    parts = [synth.make_supervision(100 + i, den, 1, T, num_paths=2) for i in range(B)]
+    hs = [io.Supervision.from_arrays(p.weight, 1, T, P, p.arc_begin, p.arc_dst, p.arc_label, p.arc_cost, p.final_cost)
+          for p in parts]
+    s = io.Supervision.merge(hs)
+    g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
+                                        den.final_cost, den.num_pdfs)
+    y2 = torch.from_numpy(synth.make_nnet_output(B + 2, B, T, P)).cuda()
+    y3 = y2.view(T, B, P).permute(1, 2, 0).contiguous()
+    d3, x3 = torch.empty_like(y3), torch.empty_like(y3)
+    st3 = (ctypes.c_int64 * 3)(1, P * T, T)
+    res = np.zeros(3, dtype=np.float32)
+    ok = lib.torchain_ComputeChainObjfAndDeriv_strided(g.ptr, s.ptr, y3.data_ptr(), T, B, P, st3,
+                                                       res.ctypes.data_as(ctypes.c_void_p), None, d3.data_ptr(), st3,
+                                                       x3.data_ptr(), st3, 0.01, 0.1, 0.1, 1.0, 0, None)
+    assert ok == 1, _lib.last_error()
+    rows = torch.empty(T * B, P + 1, device="cuda")
+    assert lib.torchain_to2d(y3.data_ptr(), B, P, T, rows.data_ptr(), P + 1, 0, None) == 1, _lib.last_error()
+    back = torch.empty_like(y3)
+    assert lib.torchain_from2d(rows.data_ptr(), P + 1, B, P, T, back.data_ptr(), 1.0, 0, None) == 1, _lib.last_error()
+    torch.cuda.synchronize()
+    d2 = torch.empty_like(y2)
+    res2 = np.zeros(3, dtype=np.float32)
+    ok = lib.my_lib_ComputeChainObjfAndDeriv(g.ptr, s.ptr, y2.data_ptr(), B * T, P, P, res2.ctypes.data_as(ctypes.c_void_p),
+                                             d2.data_ptr(), P, None, 0, 0.01, 0.1, 0.0, 0, None)
+    assert ok == 1, _lib.last_error()
+    torch.cuda.synchronize()
+    print("ok strided/relayout/merge", B, T, N, P, res, res2, bool(torch.equal(back, y3)), bool(torch.equal(rows[:, :P], y2)),
+          float((d3.permute(2, 0, 1).reshape(T * B, P) - d2).abs().max()))
