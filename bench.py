@@ -196,7 +196,7 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args):
@@ -228,10 +228,14 @@ def run_b200(args):
     res_host = np.zeros(3, dtype=np.float32)
     stream = torch.cuda.current_stream(dev)
 
-    def step():
+    def step(host_results=False):
+        # Multi-GPU steps take the results on the device (they are all-reduced first); the warm-up
+        # steps ask for host results on every rank too, because only a synchronising call lets the
+        # library read back its per-warp busy counters and calibrate the partition --
+        # what the Python op (chain_loss) does on every call.
         ok = lib.torchain_ComputeChainObjfAndDeriv_ex(
             g.ptr, s.ptr, y.data_ptr(), T * B, P, y.stride(0),
-            None if world > 1 else res_host.ctypes.data_as(ctypes.c_void_p), res_dev.data_ptr(),
+            res_host.ctypes.data_as(ctypes.c_void_p) if (world == 1 or host_results) else None, res_dev.data_ptr(),
             deriv.data_ptr(), deriv.stride(0), None, 0,
             c["l2"], c["leaky"], 0.0, -1.0, local, ctypes.c_void_p(stream.cuda_stream))
         if ok != 1:
@@ -246,7 +250,7 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
 
     for _ in range(max(args.warmup, 3)):
-        step()
+        step(host_results=True)
     sync_all()
     lib.torchain_profile_enable(1)
     dummy_ms, dummy_n = ctypes.c_double(0), ctypes.c_int64(0)
@@ -352,12 +356,35 @@ def run_b200(args):
     }
     if cpu:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_OUT_FD = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line, but native libraries print there too (NCCL writes
+    "NCCL version ..." with printf during init): keep the real stdout for the result line and point
+    file descriptor 1 at stderr for everything else."""
+    global _OUT_FD
+    sys.stdout.flush()
+    _OUT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _OUT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_OUT_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
