@@ -672,3 +672,37 @@ def test_gpu_supervision_merge_matches_appended_fst():
     nested = io.Supervision.merge([io.Supervision.merge(hs[:2]), io.Supervision.merge(hs[2:])])
     res2, d2, _ = run_abi(g, nested, y, 0.01, 0.1)
     assert rel(res2[0], r["objf"]) < OBJF_RTOL and deriv_err(d2, r["deriv"]) < DERIV_RTOL
+
+
+def test_gpu_async_calls_calibrate_and_stay_correct():
+    """Calls that never synchronise (results = NULL) still feed the partition autotuner: each leaves
+    an event behind and a later call harvests the per-warp counters and re-deals the states.  Every
+    call, before and after each re-partition and with back-to-back launches in flight, must match."""
+    import torch
+    lib = _lib.load()
+    B, T, N, P = 128, 30, 3000, 300
+    den = synth.make_den_fst(21, N, P, mean_deg=20.0)
+    sup = synth.make_supervision(22, den, B, T, num_paths=2)
+    y_np = synth.make_nnet_output(23, B, T, P, scale=1.5)
+    r = ol.chain(ol.OracleDen(den), ol.OracleSup(sup), y_np, l2=5e-5, leaky=0.1, mode="fp64", threads=8)
+    g, s = handles(den, sup)
+    y = torch.from_numpy(y_np).cuda()
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    outs = []
+    for i in range(8):
+        d = torch.full_like(y, float("nan"))
+        res_dev = torch.zeros(3, device="cuda")
+        ok = lib.torchain_ComputeChainObjfAndDeriv_ex(
+            g.ptr, s.ptr, y.data_ptr(), y.shape[0], P, P, None, res_dev.data_ptr(), d.data_ptr(), P, None, 0,
+            5e-5, 0.1, 0.0, 1.0, 0, stream)
+        assert ok == 1, _lib.last_error()
+        outs.append((res_dev, d))
+        if i % 2 == 1:   # every other call is enqueued while the previous one is still running
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    for res_dev, d in outs:
+        rr = res_dev.cpu().numpy()
+        assert rel(rr[0], r["objf"]) < OBJF_RTOL and rel(rr[1], r["l2_term"]) < OBJF_RTOL
+        assert deriv_err(d.cpu().numpy(), r["deriv"]) < DERIV_RTOL
+    res, d, _ = run_abi(g, s, y_np, 5e-5, 0.1)   # and a synchronising call afterwards
+    assert rel(res[0], r["objf"]) < OBJF_RTOL and deriv_err(d, r["deriv"]) < DERIV_RTOL

@@ -125,6 +125,14 @@ struct DenDevice {  // per (device) state
   std::vector<double> speed[2];
   int calib_rounds_done = 0;
   DevBuf warp_busy;  // [2][grid][kDenWarps] cycles, written by the last launch pair
+  // A call that does not synchronise (no host results) cannot read the counters back itself: it
+  // records this event behind its launch pair and a later call harvests the round once it completed.
+  cudaEvent_t calib_ev = nullptr;
+  bool calib_pending = false;
+  const DenPartition* calib_part = nullptr;  // the partition the pending counters were measured on
+  ~DenDevice() {
+    if (calib_ev) cudaEventDestroy(calib_ev);
+  }
 };
 constexpr int kCalibRounds = 3;
 
@@ -807,12 +815,18 @@ int get_den_device(DenGraph* g, int device, DenDevice** out) {
 // from frame to frame and call to call (profiles/r01_summary.md), so after each of the first
 // kCalibRounds synchronised calls the measured per-warp busy cycles of the last launch pair
 // turn into speed estimates (assigned work / busy time) and the states are re-dealt.
-int autotune_partition(DenGraph* g, DenDevice* d) {
+int autotune_partition(DenGraph* g, DenDevice* d, cudaStream_t copy_stream = nullptr) {
   std::lock_guard<std::mutex> lock(g->mu);
   if (d->calib_rounds_done >= kCalibRounds) return 1;
   const size_t n = 2 * (size_t)d->grid * tb::kDenWarps;
   std::vector<unsigned long long> busy(n);
-  CUDA_OK(cudaMemcpy(busy.data(), d->warp_busy.ptr, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
+  if (copy_stream) {  // harvesting behind an asynchronous call: do not touch the caller's streams
+    CUDA_OK(cudaMemcpyAsync(busy.data(), d->warp_busy.ptr, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost,
+                            copy_stream));
+    CUDA_OK(cudaStreamSynchronize(copy_stream));
+  } else {
+    CUDA_OK(cudaMemcpy(busy.data(), d->warp_busy.ptr, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost));
+  }
   for (int dir = 0; dir < 2; dir++) {
     const size_t bins = (size_t)d->grid * tb::kDenMainWarps;
     std::vector<double> est(bins, 0.0);
@@ -1032,13 +1046,32 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
     }
     dp.has_split = part->has_split ? 1 : 0;
   };
-  // only a synchronising single-pass call on the full-width partition can feed the autotuner
+  // a calibration round left behind by an earlier asynchronous call, if its launches have finished
+  {
+    bool harvest = false;
+    {
+      std::lock_guard<std::mutex> lock(g->mu);
+      if (dd->calib_pending) {
+        const cudaError_t q = cudaEventQuery(dd->calib_ev);
+        if (q == cudaSuccess) {
+          dd->calib_pending = false;
+          harvest = dd->calib_part == dd->cur;
+        } else {
+          (void)cudaGetLastError();  // cudaErrorNotReady is not an error
+        }
+      }
+    }
+    if (harvest && !autotune_partition(g, dd, ws->side)) return 0;
+  }
+  // only a single-pass call on the full-width partition can feed the autotuner; a synchronising call
+  // reads its counters back at the end, any other leaves them for a later call (calib_ev)
   bool calibrating;
   {
     std::lock_guard<std::mutex> lock(g->mu);
     calibrating = B <= tb::kMaxBP && tb::den_subs(BPmax) == 1 && dd->calib_rounds_done < kCalibRounds &&
-                  results_host != nullptr;
+                  !dd->calib_pending;
   }
+  const bool calib_async = calibrating && results_host == nullptr;
   dp.warp_busy = calibrating ? dd->warp_busy.as<unsigned long long>() : nullptr;
   dp.N = N;
   dp.P = P;
@@ -1132,6 +1165,15 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
       numerator_done = true;
     }
     CUDA_OK(tb::launch_den(batch, 1, dd->grid, stream));
+    if (calib_async) {
+      std::lock_guard<std::mutex> lock(g->mu);
+      if (!dd->calib_pending) {
+        if (!dd->calib_ev) CUDA_OK(cudaEventCreateWithFlags(&dd->calib_ev, cudaEventDisableTiming));
+        CUDA_OK(cudaEventRecord(dd->calib_ev, stream));
+        dd->calib_part = part;
+        dd->calib_pending = true;
+      }
+    }
     if (e0) {
       CUDA_OK(cudaEventRecord(e1, stream));
       std::lock_guard<std::mutex> lock(g->mu);
@@ -1173,7 +1215,7 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
     results_host[0] = ws->pinned[0];
     results_host[1] = ws->pinned[1];
     results_host[2] = ws->pinned[2];
-    if (calibrating && !autotune_partition(g, dd)) return 0;
+    if (calibrating && !calib_async && !autotune_partition(g, dd)) return 0;
   }
   return 1;
 }
