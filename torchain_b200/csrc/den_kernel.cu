@@ -104,6 +104,36 @@ __device__ __forceinline__ float* row_ptr(float* base, int idx, unsigned rowbyte
   return reinterpret_cast<float*>(addr);
 }
 
+// Packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2 through the PTX .f32x2 forms): the gather loops are
+// sensitive to their instruction count, and four sequences per lane are two natural pairs.
+#ifndef DEN_PACKED_MATH
+#define DEN_PACKED_MATH 1
+#endif
+using u64 = unsigned long long;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(u64 p, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p));
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* ptr) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
@@ -354,10 +384,20 @@ __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __res
         {
           const int2 ar = *(reinterpret_cast<const int2*>(a + k + u) + 1);  // {prob | end flag, pi[source]}
           const float pr = fabsf(__int_as_float(ar.x)), pi = __int_as_float(ar.y);
+          if constexpr (DEN_PACKED_MATH && V == 4) {
+            const u64 pr2 = pk2(pr, pr), pi2 = pk2(pi, pi);
 #pragma unroll
-          for (int v = 0; v < V; v++) {
-            const float ad = fmaf(pi, lamS[v], buf.a[u][v]);
-            acc[v] = fmaf(ad * pr, buf.e[u][v], acc[v]);
+            for (int h = 0; h < 2; h++) {
+              const u64 ad = fma2(pi2, pk2(lamS[2 * h], lamS[2 * h + 1]), pk2(buf.a[u][2 * h], buf.a[u][2 * h + 1]));
+              const u64 r = fma2(mul2(ad, pr2), pk2(buf.e[u][2 * h], buf.e[u][2 * h + 1]), pk2(acc[2 * h], acc[2 * h + 1]));
+              upk2(r, acc[2 * h], acc[2 * h + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+              const float ad = fmaf(pi, lamS[v], buf.a[u][v]);
+              acc[v] = fmaf(ad * pr, buf.e[u][v], acc[v]);
+            }
           }
           if (ar.x < 0) {  // sign bit of the probability = last arc of this state (warp-uniform branch)
             const int4 tk = tasks[task++];
@@ -455,11 +495,22 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
           const int4 ar = a[k + u];
           const float pr = fabsf(__int_as_float(ar.z));
           float g[V];
+          if constexpr (DEN_PACKED_MATH && V == 4) {
+            const u64 pr2 = pk2(pr, pr);
 #pragma unroll
-          for (int v = 0; v < V; v++) {
-            const float vf = pr * (buf.a[u][v] + bv[v]) * buf.e[u][v];
-            X[v] += vf;
-            g[v] = vf * occ[v];
+            for (int h = 0; h < 2; h++) {
+              const u64 sum = add2(pk2(buf.a[u][2 * h], buf.a[u][2 * h + 1]), pk2(bv[2 * h], bv[2 * h + 1]));
+              const u64 vf = mul2(mul2(pr2, sum), pk2(buf.e[u][2 * h], buf.e[u][2 * h + 1]));
+              upk2(add2(pk2(X[2 * h], X[2 * h + 1]), vf), X[2 * h], X[2 * h + 1]);
+              upk2(mul2(vf, pk2(occ[2 * h], occ[2 * h + 1])), g[2 * h], g[2 * h + 1]);
+            }
+          } else {
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+              const float vf = pr * (buf.a[u][v] + bv[v]) * buf.e[u][v];
+              X[v] += vf;
+              g[v] = vf * occ[v];
+            }
           }
           red_add<V>(reinterpret_cast<float*>(ug + (unsigned)ar.y), g);
           if (ar.z < 0) {  // sign bit of the probability = last arc of this state
