@@ -152,3 +152,52 @@ def test_oracle_rejects_bad_inputs():
         ol.chain(oden, osup, c["y"][:-1], leaky=0.1)          # wrong number of rows
     with pytest.raises(ValueError):
         ol.chain(oden, osup, c["y"], leaky=0.0)               # Kaldi asserts 0 < leaky < 1
+
+
+@pytest.mark.parametrize("kind", ["uniform", "tied", "mostly_tied"])
+def test_state_splitting_by_incoming_pdf_preserves_the_loss(kind):
+    """Groundwork for the tied-pdf recurrence: giving every state one copy per distinct
+    incoming pdf (copies repeat the out-arcs) leaves objf and the derivative unchanged -- copies have identical
+    futures and their forward mass adds up, Kaldi's initial-probability iteration included."""
+    P = 30
+    if kind == "uniform":
+        den = synth.make_den_fst(11, 150, P, mean_deg=5.0)
+    else:
+        den = synth.make_den_fst_tied(11, 150, P, mean_deg=5.0, untied_frac=0.0 if kind == "tied" else 0.15)
+    split, copy_of = synth.split_states_by_in_pdf(den)
+    runs, with_in = synth.in_pdf_runs(den)
+    assert split.num_states == runs + (den.num_states - with_in)
+    if kind == "tied":
+        assert runs <= 2 * den.num_states          # forward pdf + self-loop pdf
+    # strictly tied now: one incoming pdf per state
+    assert synth.in_pdf_runs(split)[0] == np.unique(split.dst).shape[0]
+    assert np.array_equal(np.sort(np.unique(copy_of)), np.arange(den.num_states))
+    B, T = 4, 7
+    sup = synth.make_supervision(12, den, B, T, num_paths=3)
+    y = synth.make_nnet_output(13, B, T, P, scale=1.5)
+    a = ol.chain(ol.OracleDen(den), ol.OracleSup(sup), y, l2=0.0, leaky=0.1, mode="fp64")
+    b = ol.chain(ol.OracleDen(split), ol.OracleSup(sup), y, l2=0.0, leaky=0.1, mode="fp64")
+    assert abs(a["objf"] - b["objf"]) < 1e-8 * abs(a["objf"])      # initial probs are rounded to fp32 (Kaldi)
+    assert np.abs(a["deriv"] - b["deriv"]).max() < 1e-7
+
+
+def test_run_based_recurrence_matches_oracle():
+    """tools/tied_pdf_study.py: the run-based ((state, incoming pdf)) form of the denominator recurrence --
+    exp(y) once per run, one 4-byte gather per arc backward, one occupancy update per run -- is algebraically
+    the per-arc recurrence: same log-probability, same occupancies, on tied and on uniform graphs."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "tied_pdf_study", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools",
+                                       "tied_pdf_study.py"))
+    study = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(study)
+    P, B, T = 25, 3, 6
+    for den in (synth.make_den_fst(31, 120, P, mean_deg=5.0), synth.make_den_fst_tied(31, 120, P, mean_deg=5.0)):
+        sup = synth.make_supervision(32, den, B, T, num_paths=2, weight=0.5)
+        y = synth.make_nnet_output(33, B, T, P, scale=1.5)
+        r = ol.chain(ol.OracleDen(den), ol.OracleSup(sup), y, l2=0.0, leaky=0.1, mode="fp64", want_xent=True)
+        logp, gamma, runs = study.tied_gamma(den, y, B, T, 0.1)
+        gamma_den = (r["xent"] - r["deriv"]) / sup.weight      # deriv = w (gamma_num - gamma_den), xent = w gamma_num
+        assert np.abs(gamma - gamma_den).max() < 1e-9
+        assert np.abs(gamma.sum(axis=1) - 1.0).max() < 1e-9

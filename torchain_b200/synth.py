@@ -312,3 +312,65 @@ def make_config(name, seed=1234, B=None, T=None, y_scale=2.0, with_y=True):
     y = make_nnet_output(seed + 2, c["B"], c["T"], c["P"], scale=y_scale) if with_y else None
     c.update(den=den, sup=sup, y=y)
     return c
+
+
+# ---------------------------------------------------------------------------
+# Tied-pdf graphs: in a real den.fst the pdf of an arc belongs to the HMM state
+# being entered, so the in-arcs of a state carry very few distinct pdfs.  These helpers build such graphs
+# and turn ANY graph into a strictly tied one (exactly one incoming pdf per state) without changing the loss.
+# ---------------------------------------------------------------------------
+def make_den_fst_tied(seed, num_states, num_pdfs, mean_deg=28.0, final_prob=0.05, untied_frac=0.0):
+    """Like make_den_fst, but every arc into state j carries pdf_of[j] (self-loops carry their own
+    pdf_loop[j], as in the 2-pdf chain topology); `untied_frac` of the arcs get a random pdf instead."""
+    den = make_den_fst(seed, num_states, num_pdfs, mean_deg=mean_deg, final_prob=final_prob)
+    rng = np.random.default_rng(seed + 7919)
+    N = den.num_states
+    pdf_of = rng.integers(0, num_pdfs, size=N)
+    pdf_loop = rng.integers(0, num_pdfs, size=N)
+    dst = den.dst.astype(np.int64)
+    pdf = np.where(den.src == den.dst, pdf_loop[dst], pdf_of[dst])
+    if untied_frac > 0:
+        odd = rng.random(pdf.shape[0]) < untied_frac
+        pdf = np.where(odd, rng.integers(0, num_pdfs, size=pdf.shape[0]), pdf)
+    den.ilabel = (pdf + 1).astype(np.int32)
+    return den
+
+
+def in_pdf_runs(den):
+    """(number of distinct (state, incoming pdf) pairs, number of states with in-arcs)."""
+    key = den.dst.astype(np.int64) * (den.num_pdfs + 1) + den.ilabel.astype(np.int64)
+    return int(np.unique(key).shape[0]), int(np.unique(den.dst).shape[0])
+
+
+def split_states_by_in_pdf(den):
+    """Strictly tied equivalent of `den`: state j becomes one copy per distinct incoming pdf q; copy (j, q)
+    receives the in-arcs of j labelled q and repeats ALL out-arcs (and the final cost) of j.  Copies of a state
+    have identical futures and the copies' forward mass adds up to the original state's, so objf and the
+    derivative w.r.t. nnet_output are unchanged (Kaldi's initial-probability iteration included: it is linear).
+    Returns (split DenFst, copy_of: original state of every new state)."""
+    N, A = den.num_states, den.src.shape[0]
+    src, dst, lab = den.src.astype(np.int64), den.dst.astype(np.int64), den.ilabel.astype(np.int64)
+    key = dst * (den.num_pdfs + 1) + lab
+    uniq, inv = np.unique(key, return_inverse=True)          # one new state per (dst, pdf) pair
+    copy_state = uniq // (den.num_pdfs + 1)
+    have = np.zeros(N, dtype=bool)
+    have[copy_state] = True
+    orphans = np.nonzero(~have)[0]                           # states without in-arcs keep one copy
+    copy_of = np.concatenate([copy_state, orphans])
+    M = copy_of.shape[0]
+    # out-arcs of every copy = out-arcs of its original, each pointed at the copy (dst, pdf) it enters
+    order = np.argsort(src, kind="stable")
+    begin = np.zeros(N + 1, dtype=np.int64)
+    np.cumsum(np.bincount(src, minlength=N), out=begin[1:])
+    deg = (begin[1:] - begin[:-1])[copy_of]
+    new_src = np.repeat(np.arange(M), deg)
+    offs = np.concatenate([[0], np.cumsum(deg)])[:-1]
+    within = np.arange(int(deg.sum())) - np.repeat(offs, deg)
+    arc = order[np.repeat(begin[copy_of], deg) + within]
+    new_dst = inv[arc]
+    first_copy = np.full(N, -1, dtype=np.int64)
+    first_copy[copy_of[::-1]] = np.arange(M)[::-1]           # lowest-numbered copy of every original state
+    out = DenFst(int(M), den.num_pdfs, int(first_copy[den.start]), new_src.astype(np.int32), new_dst.astype(np.int32),
+                 den.ilabel[arc].astype(np.int32), den.cost[arc].astype(np.float32),
+                 den.final_cost[copy_of].astype(np.float32))
+    return out, copy_of
