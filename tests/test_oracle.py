@@ -194,7 +194,7 @@ def test_run_based_recurrence_matches_oracle():
     spec.loader.exec_module(study)
     P, B, T = 25, 3, 6
     for den in (synth.make_den_fst(31, 120, P, mean_deg=5.0), synth.make_den_fst_tied(31, 120, P, mean_deg=5.0)):
-        sup = synth.make_supervision(32, den, B, T, num_paths=2, weight=0.5)
+        sup = synth.make_supervision(32, den, B, T, num_paths=2, weight=1.0)
         y = synth.make_nnet_output(33, B, T, P, scale=1.5)
         r = ol.chain(ol.OracleDen(den), ol.OracleSup(sup), y, l2=0.0, leaky=0.1, mode="fp64", want_xent=True)
         logp, gamma, runs = study.tied_gamma(den, y, B, T, 0.1)
