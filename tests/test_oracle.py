@@ -199,5 +199,6 @@ def test_run_based_recurrence_matches_oracle():
         r = ol.chain(ol.OracleDen(den), ol.OracleSup(sup), y, l2=0.0, leaky=0.1, mode="fp64", want_xent=True)
         logp, gamma, runs = study.tied_gamma(den, y, B, T, 0.1)
         gamma_den = (r["xent"] - r["deriv"]) / sup.weight      # deriv = w (gamma_num - gamma_den), xent = w gamma_num
-        assert np.abs(gamma - gamma_den).max() < 1e-9
+        # both sides round the initial probabilities to fp32 (Kaldi) from independently computed doubles: 1 ulp
+        assert np.abs(gamma - gamma_den).max() < 2e-7
         assert np.abs(gamma.sum(axis=1) - 1.0).max() < 1e-9
