@@ -284,3 +284,50 @@ def test_binary_parsers_reject_corrupt_input_without_crashing(seed, tmp_path):
         except (ValueError, RuntimeError, OSError):
             pass
     assert accepted < 400   # most mutations must be caught
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_array_constructors_reject_corrupt_input_without_crashing(seed):
+    """Out-of-range indices, broken CSR offsets (regression: arc_begin[0] = INT_MIN used to be dereferenced),
+    absurd sizes and non-finite costs in the array constructors: an error or a valid handle, never a crash."""
+    rng = np.random.default_rng(seed)
+    den = synth.make_den_fst(3, 40, 10, mean_deg=3.0)
+    sup = synth.make_supervision(4, den, 3, 5, num_paths=2)
+    ints = [-1, -2 ** 31, 2 ** 31 - 1, 0, 10 ** 6, 7, den.num_states]
+    for _ in range(300):
+        d = dict(N=den.num_states, src=den.src.copy(), dst=den.dst.copy(), il=den.ilabel.copy(), cost=den.cost.copy(),
+                 start=den.start, P=den.num_pdfs)
+        k, i, v = rng.integers(0, 7), rng.integers(0, den.src.shape[0]), int(rng.choice(ints))
+        if k == 0: d["src"][i] = v
+        elif k == 1: d["dst"][i] = v
+        elif k == 2: d["il"][i] = v
+        elif k == 3: d["cost"][i] = rng.choice([np.nan, np.inf, -np.inf, 1e30, -1e30])
+        elif k == 4: d["start"] = v
+        elif k == 5: d["N"] = int(rng.choice([0, -1, 1, 10 ** 6, den.num_states - 1]))
+        else: d["P"] = int(rng.choice([0, -1, 1, 5]))
+        try:
+            io.DenominatorGraph.from_arrays(d["N"], d["src"], d["dst"], d["il"], d["cost"], d["start"],
+                                            den.final_cost, d["P"])
+        except (ValueError, RuntimeError, AssertionError):
+            pass
+    for _ in range(300):
+        ab, ad, al = sup.arc_begin.copy(), sup.arc_dst.copy(), sup.arc_label.copy()
+        ac, fc = sup.arc_cost.copy(), sup.final_cost.copy()
+        B, T = sup.num_sequences, sup.frames_per_sequence
+        k, v = rng.integers(0, 7), int(rng.choice(ints))
+        if k == 0: ab[rng.integers(0, ab.shape[0])] = v
+        elif k == 1: ad[rng.integers(0, ad.shape[0])] = v
+        elif k == 2: al[rng.integers(0, al.shape[0])] = v
+        elif k == 3: ac[rng.integers(0, ac.shape[0])] = rng.choice([np.nan, np.inf, -np.inf])
+        elif k == 4: fc[rng.integers(0, fc.shape[0])] = rng.choice([np.nan, 0.0, -np.inf])
+        elif k == 5: B = int(rng.choice([0, -1, 1, 4, 10 ** 6]))
+        else: T = int(rng.choice([0, -1, 1, 4, 10 ** 6]))
+        try:
+            io.Supervision.from_arrays(sup.weight, B, T, sup.label_dim, ab, ad, al, ac, fc)
+        except (ValueError, RuntimeError, AssertionError):
+            pass
+    with pytest.raises(ValueError, match="arc_begin"):
+        ab = sup.arc_begin.copy()
+        ab[0] = -2 ** 31
+        io.Supervision.from_arrays(sup.weight, sup.num_sequences, sup.frames_per_sequence, sup.label_dim, ab,
+                                   sup.arc_dst, sup.arc_label, sup.arc_cost, sup.final_cost)

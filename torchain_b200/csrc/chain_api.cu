@@ -530,6 +530,16 @@ Supervision* make_supervision(float weight, int32_t B, int32_t T, int32_t label_
     g_error = "supervision: bad sizes";
     return nullptr;
   }
+  // the CSR offsets are checked as a whole before anything is indexed with them
+  if (arc_begin[0] != 0) {
+    g_error = "supervision: arc_begin[0] != 0";
+    return nullptr;
+  }
+  for (int s = 0; s < S; s++)
+    if (arc_begin[s + 1] < arc_begin[s]) {
+      g_error = "supervision: arc_begin not monotone";
+      return nullptr;
+    }
   const int A = arc_begin[S];
   // --- state times (Kaldi ComputeFstStateTimes): unique time per state, arcs advance by one
   std::vector<int> time(S, -1);
