@@ -199,7 +199,10 @@ int torchain_from2d(const float* rows, int64_t in_stride, int64_t num_sequences,
 /* Host-buffer form (what a non-torch host binding would call): nnet_output,
  * nnet_output_deriv (and xent_output_deriv, may be NULL) are HOST pointers,
  * ideally pinned; the call copies the input to the device, runs the loss and
- * copies derivatives and results back before returning. */
+ * copies derivatives and results back before returning.  Both copies are chunked
+ * by whole frames and overlap the forward / backward recurrence; when the numeric
+ * guard trips (objf = -10 * weight) the derivative delivered is the guard's
+ * (l2 part only), as in the device form. */
 int torchain_ComputeChainObjfAndDeriv_host(void* den_graph_ptr, void* supervision_ptr,
                                            const float* nnet_output_host, int64_t rows, int64_t cols,
                                            int64_t nnet_output_stride,
@@ -208,6 +211,11 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den_graph_ptr, void* supervisio
                                            float* xent_output_deriv_host, int64_t xent_stride,
                                            float l2_regularize, float leaky_hmm_coefficient,
                                            float xent_regularize, int device);
+/* The frame boundaries of the chunks the host-buffer form moves a minibatch of num_frames frames in
+ * (about 16 chunks of whole frames, single frames at both ends so that the copies that cannot overlap
+ * the recurrences are short): writes up to max_entries of [0, ..., num_frames] and returns the number
+ * of boundaries (chunks + 1), 0 if num_frames < 1.  Host logic only; no device is touched. */
+int torchain_host_chunk_bounds(int num_frames, int* bounds, int max_entries);
 
 /* ---- measurement helpers (used by bench.py; not part of the reference API) -- */
 

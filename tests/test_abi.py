@@ -331,3 +331,25 @@ def test_array_constructors_reject_corrupt_input_without_crashing(seed):
         ab[0] = -2 ** 31
         io.Supervision.from_arrays(sup.weight, sup.num_sequences, sup.frames_per_sequence, sup.label_dim, ab,
                                    sup.arc_dst, sup.arc_label, sup.arc_cost, sup.final_cost)
+
+
+def test_host_chunk_bounds_schedule():
+    """Chunk boundaries of the host-buffer entry: a partition of [0, T) into whole-frame chunks,
+    about 16 of them, single frames at both ends once there are more than 16 frames."""
+    import ctypes
+    lib = _lib.load()
+    assert lib.torchain_host_chunk_bounds(0, None, 0) == 0
+    for T in list(range(1, 300)) + [500, 1000, 1599, 5000]:
+        n = lib.torchain_host_chunk_bounds(T, None, 0)
+        buf = (ctypes.c_int * n)()
+        assert lib.torchain_host_chunk_bounds(T, buf, n) == n
+        b = list(buf)
+        assert b[0] == 0 and b[-1] == T
+        sizes = [b[i + 1] - b[i] for i in range(n - 1)]
+        assert all(sz >= 1 for sz in sizes)
+        assert len(sizes) <= 16 + 2 * 12
+        base = max(1, (T + 15) // 16)
+        assert max(sizes) <= base
+        if T > 32:
+            assert sizes[0] == 1 and sizes[-1] == 1
+            assert sizes == sizes[::-1] or sizes[:3] == sizes[::-1][:3]

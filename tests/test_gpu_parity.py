@@ -187,6 +187,60 @@ def test_host_buffer_entry():
     assert deriv_err(d, c["deriv"]) < DERIV_RTOL
 
 
+def _host_entry(g, s, y, l2, leaky, pinned=True):
+    """torchain_ComputeChainObjfAndDeriv_host on (pinned) host buffers; returns results, derivative."""
+    import torch
+    lib = _lib.load()
+    rows, cols = y.shape
+    yh = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32))
+    dh = torch.full((rows, cols), float("nan"))
+    if pinned:
+        yh, dh = yh.pin_memory(), dh.pin_memory()
+    res = np.zeros(3, dtype=np.float32)
+    ok = lib.torchain_ComputeChainObjfAndDeriv_host(g.ptr, s.ptr, yh.data_ptr(), rows, cols, cols,
+                                                    res.ctypes.data_as(ctypes.c_void_p), dh.data_ptr(), cols,
+                                                    None, 0, l2, leaky, 0.0, 0)
+    assert ok == 1, _lib.last_error()
+    return res, dh.numpy().copy()
+
+
+@pytest.mark.parametrize("T", [1, 2, 17, 50, 77])
+def test_host_buffer_entry_chunk_schedules(T):
+    """The host-buffer form moves the minibatch in chunks of whole frames of DIFFERENT sizes (single
+    frames at both ends, torchain_host_chunk_bounds); every schedule must deliver what the device form
+    computes from the same input."""
+    den = synth.make_den_fst(5, 1500, 200, mean_deg=8.0)
+    B = 48
+    sup = synth.make_supervision(6, den, B, T, num_paths=2, weight=1.0)
+    y = synth.make_nnet_output(7, B, T, den.num_pdfs, scale=1.5)
+    g, s = handles(den, sup)
+    r_dev, d_dev, _ = run_abi(g, s, y, 5e-5, 0.1)
+    r_host, d_host = _host_entry(g, s, y, 5e-5, 0.1)
+    assert rel(r_host[0], r_dev[0]) < OBJF_RTOL and rel(r_host[1], r_dev[1]) < OBJF_RTOL and r_host[2] == r_dev[2]
+    assert np.isfinite(d_host).all()
+    assert deriv_err(d_host, d_dev.astype(np.float64)) < 1e-5
+
+
+def test_host_buffer_entry_guard_rewrites_early_chunks():
+    """When the numeric guard trips, the final pass rewrites the derivative (l2 part only) AFTER the
+    host-buffer form has already copied the chunks of the late frames out during the backward launch:
+    those chunks have to be delivered again (Kaldi: objf = -10 * weight, deriv = -w * l2 * nnet_output)."""
+    den = synth.make_den_fst(8, 4000, 300, mean_deg=12.0)
+    B, T = 128, 60  # a backward launch long enough for chunks to leave early
+    sup = synth.make_supervision(9, den, B, T, num_paths=2, weight=0.5)
+    y = synth.make_nnet_output(10, B, T, den.num_pdfs, scale=1.0)
+    y[3, 7] = np.nan
+    g, s = handles(den, sup)
+    l2 = 0.01
+    for _ in range(2):
+        res, d = _host_entry(g, s, y, l2, 0.1)
+        assert res[0] == pytest.approx(-10.0 * res[2]) and res[2] == pytest.approx(0.5 * B * T)
+        want = -0.5 * l2 * y
+        fin = np.isfinite(y)
+        assert np.isnan(d[~fin]).all()
+        np.testing.assert_allclose(d[fin], want[fin], rtol=1e-6, atol=0)
+
+
 def test_large_config_properties():
     """BASELINE.json cfg 2 at full size: size-independent properties (the oracle's fp64
     pass is too slow for the GPU suite at this size; bench.py times a bounded sample)."""

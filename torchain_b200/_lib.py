@@ -58,6 +58,7 @@ SIGNATURES = {
     "torchain_ComputeChainObjfAndDeriv_host": (
         _c_i, [_c_p, _c_p, _c_p, _c_i64, _c_i64, _c_i64, _c_p, _c_p, _c_i64, _c_p, _c_i64,
                _c_f, _c_f, _c_f, _c_i]),
+    "torchain_host_chunk_bounds": (_c_i, [_c_i, _c_p, _c_i]),
     "torchain_profile_enable": (None, [_c_i]),
     "torchain_profile_read": (_c_i, [_c_p, _c_p, _c_p, _c_i]),
     "torchain_profile_timeline": (_c_i, [_c_p, _c_p, _c_i]),

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -946,8 +947,34 @@ struct ChunkedInput {
   const unsigned* flags = nullptr;
   int chunk_frames = 0;
   cudaEvent_t all_landed = nullptr;  // recorded on the copy stream after the last chunk
+  cudaEvent_t all_landed2 = nullptr; // same for the second copy stream (experiment), or null
   unsigned* deriv_progress = nullptr;  // device pointer of a mapped pinned counter (see DenParams)
+  float* results4_dev = nullptr;       // device float[4]: objf, l2_term, weight, ok flag of the numeric guard
 };
+
+// Frame boundaries of the chunks the host-buffer entry moves nnet_output / the derivative in:
+// about 16 chunks of `base` whole frames, with shorter ones (1, 1, 2, 4, ... frames) at BOTH ends.
+// What the host waits for with nothing left to overlap is the work behind the last chunk in (the
+// frames it holds still have to go through the forward recurrence) and the copy of the last chunk out
+// (frame 0, which is complete only when the backward launch ends), so those chunks are single frames.
+std::vector<int> chunk_bounds(int T) {
+  const int base = std::max(1, (T + 15) / 16);
+  std::vector<int> head, tail;
+  int lo = 0, hi = T;
+  for (int s = 1, rep = 0; s < base && hi - lo >= 2 * s + base;) {
+    head.push_back(s);
+    tail.push_back(s);
+    lo += s;
+    hi -= s;
+    if (s > 1 || ++rep == 2) s *= 2;
+  }
+  std::vector<int> b(1, 0);
+  for (int s : head) b.push_back(b.back() + s);
+  while (b.back() + base < hi) b.push_back(b.back() + base);
+  if (b.back() < hi) b.push_back(hi);
+  for (auto it = tail.rbegin(); it != tail.rend(); ++it) b.push_back(b.back() + *it);
+  return b;  // b.front() == 0, b.back() == T, strictly increasing
+}
 
 // The whole loss, enqueued on `stream`: forward launch -> numerator -> backward launch ->
 // final scalars.  results_host may be null (then nothing synchronises).
@@ -1162,6 +1189,7 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
       // last chunk has landed in the host-buffer entry (event recorded on the copy stream).
       if (chunked.all_landed) {
         CUDA_OK(cudaStreamWaitEvent(ws->side, chunked.all_landed, 0));
+        if (chunked.all_landed2) CUDA_OK(cudaStreamWaitEvent(ws->side, chunked.all_landed2, 0));
       } else {
         CUDA_OK(cudaEventRecord(ws->ev_fork, stream));
         CUDA_OK(cudaStreamWaitEvent(ws->side, ws->ev_fork, 0));
@@ -1219,6 +1247,8 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   CUDA_OK(tb::launch_final(fp, stream));
   if (results_dev_user)
     CUDA_OK(cudaMemcpyAsync(results_dev_user, res_dev, 3 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  if (chunked.results4_dev)
+    CUDA_OK(cudaMemcpyAsync(chunked.results4_dev, res_dev, 4 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   if (results_host) {
     CUDA_OK(cudaMemcpyAsync(ws->pinned, res_dev, 4 * sizeof(float), cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaStreamSynchronize(stream));
@@ -1233,10 +1263,11 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
 // Per-thread resources of the host-buffer entry.
 struct HostPath {
   int device = -1;
-  cudaStream_t compute = nullptr, copy = nullptr;
-  cudaEvent_t ready = nullptr, landed = nullptr;
+  cudaStream_t compute = nullptr, copy = nullptr, copy2 = nullptr;
+  cudaEvent_t ready = nullptr, landed = nullptr, landed2 = nullptr;
   DevBuf y, deriv, xent, flags;
-  unsigned* one = nullptr;       // pinned constant 1
+  unsigned* ones = nullptr;      // pinned constant 1s, one per frame flag of a chunk
+  int ones_cap = 0;
   unsigned* progress = nullptr;  // pinned, device-mapped: frames of the derivative already complete
 };
 thread_local HostPath g_host;
@@ -1591,17 +1622,19 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
   if (h.device != device) {
     if (h.compute) cudaStreamDestroy(h.compute);
     if (h.copy) cudaStreamDestroy(h.copy);
+    if (h.copy2) cudaStreamDestroy(h.copy2);
     if (h.ready) cudaEventDestroy(h.ready);
     if (h.landed) cudaEventDestroy(h.landed);
-    if (h.one) cudaFreeHost(h.one);
+    if (h.landed2) cudaEventDestroy(h.landed2);
+    if (h.ones) cudaFreeHost(h.ones);
     if (h.progress) cudaFreeHost(h.progress);
     h = HostPath();
     CUDA_OK(cudaStreamCreateWithFlags(&h.compute, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&h.copy, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&h.copy2, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreateWithFlags(&h.ready, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&h.landed, cudaEventDisableTiming));
-    CUDA_OK(cudaMallocHost(&h.one, sizeof(unsigned)));
-    *h.one = 1u;
+    CUDA_OK(cudaEventCreateWithFlags(&h.landed2, cudaEventDisableTiming));
     CUDA_OK(cudaHostAlloc(&h.progress, sizeof(unsigned), cudaHostAllocMapped));
     h.device = device;
   }
@@ -1620,28 +1653,82 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
     CUDA_OK(h.deriv.reserve(bytes));
     deriv_dev = h.deriv.as<float>();
   }
-  // nnet_output goes up in chunks of whole frames; the forward launch starts as soon as the
-  // first chunk has landed and waits (per frame) on the flag of the chunk it needs next.
+  // nnet_output goes up in chunks of whole frames (chunk_bounds); the forward launch starts as soon
+  // as the first chunk has landed and waits, per frame, on the flag of the frame it stages next.
   const int T = sp->T, B = sp->B;
-  const int chunk_frames = std::max(1, (T + 15) / 16);  // ~16 chunks: short first-in / last-out latency
-  const int nchunks = (T + chunk_frames - 1) / chunk_frames;
-  CUDA_OK(h.flags.reserve(sizeof(unsigned) * (size_t)nchunks));
-  CUDA_OK(cudaMemsetAsync(h.flags.ptr, 0, sizeof(unsigned) * nchunks, h.compute));
+  // TORCHAIN_HOST_TRACE=1: one line per call on stderr with the host-side times (us since entry) at which
+  // everything was enqueued, the first / last early chunk left, the compute stream and the copies ended
+  static const bool trace = getenv("TORCHAIN_HOST_TRACE") != nullptr;
+  auto now_us = [] {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  };
+  const double tr0 = trace ? now_us() : 0.0;
+  double tr_enq = 0.0, tr_first = -1.0, tr_last = -1.0, tr_sync = 0.0;
+  std::vector<int> cb = chunk_bounds(T);
+  if (getenv("TORCHAIN_HOST_UNIFORM_CHUNKS")) {  // experiment: equal chunks of ~T/16 frames
+    const int cf = std::max(1, (T + 15) / 16);
+    cb.clear();
+    for (int f = 0; f < T; f += cf) cb.push_back(f);
+    cb.push_back(T);
+  }
+  const int nchunks = (int)cb.size() - 1;
+  if (h.ones_cap < T) {  // no copy of an earlier call is in flight: every call ends with a sync of h.copy
+    if (h.ones) cudaFreeHost(h.ones);
+    h.ones = nullptr;
+    h.ones_cap = 0;
+    const int cap = std::max(T, 64);
+    CUDA_OK(cudaMallocHost(&h.ones, sizeof(unsigned) * (size_t)cap));
+    for (int i = 0; i < cap; i++) h.ones[i] = 1u;
+    h.ones_cap = cap;
+  }
+  CUDA_OK(h.flags.reserve(sizeof(unsigned) * (size_t)T));
+  CUDA_OK(cudaMemsetAsync(h.flags.ptr, 0, sizeof(unsigned) * (size_t)T, h.compute));
   CUDA_OK(cudaEventRecord(h.ready, h.compute));
   CUDA_OK(cudaStreamWaitEvent(h.copy, h.ready, 0));
+  // Experiments (profiles/r01_host_trace.txt: the input phase takes ~1.72 ms where the copy alone takes
+  // 1.35 ms; the suspect is the copy-engine pipeline break at every chunk's 4-byte flag copy):
+  //   TORCHAIN_HOST_COPY_STREAMS=2     chunks alternate between two copy streams
+  //   TORCHAIN_HOST_FLAG_MODE=memset   frame flags set by cudaMemsetAsync instead of a copy of pinned 1s
+  //   TORCHAIN_HOST_FLAG_MODE=write    frame flags set by stream memory operations (cuStreamWriteValue32)
+  int copy_streams = 1, flag_mode = 0;
+  if (const char* e = getenv("TORCHAIN_HOST_COPY_STREAMS")) copy_streams = atoi(e) == 2 ? 2 : 1;
+  if (const char* e = getenv("TORCHAIN_HOST_FLAG_MODE")) flag_mode = !strcmp(e, "memset") ? 1 : (!strcmp(e, "write") ? 2 : 0);
+  typedef int (*WriteValue32)(cudaStream_t, unsigned long long, unsigned, unsigned);
+  static WriteValue32 write_value = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &st) != cudaSuccess ||
+        st != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    (void)cudaGetLastError();
+    return reinterpret_cast<WriteValue32>(fn);
+  }();
+  if (flag_mode == 2 && !write_value) flag_mode = 0;
+  if (copy_streams == 2) CUDA_OK(cudaStreamWaitEvent(h.copy2, h.ready, 0));
   for (int k = 0; k < nchunks; k++) {
-    const int64_t r0 = (int64_t)k * chunk_frames * B;
-    const int64_t nr = std::min<int64_t>((int64_t)chunk_frames * B, rows - r0);
+    const int64_t r0 = (int64_t)cb[k] * B, nr = (int64_t)(cb[k + 1] - cb[k]) * B;
+    const cudaStream_t st = (copy_streams == 2 && (k & 1)) ? h.copy2 : h.copy;
     CUDA_OK(cudaMemcpy2DAsync(h.y.as<float>() + r0 * cols, sizeof(float) * cols, y_host + r0 * ystride,
-                              sizeof(float) * ystride, sizeof(float) * cols, nr, cudaMemcpyHostToDevice, h.copy));
-    CUDA_OK(cudaMemcpyAsync(h.flags.as<unsigned>() + k, h.one, sizeof(unsigned), cudaMemcpyHostToDevice, h.copy));
+                              sizeof(float) * ystride, sizeof(float) * cols, nr, cudaMemcpyHostToDevice, st));
+    unsigned* const fl = h.flags.as<unsigned>() + cb[k];
+    const int nf = cb[k + 1] - cb[k];
+    if (flag_mode == 1) {
+      CUDA_OK(cudaMemsetAsync(fl, 1, sizeof(unsigned) * (size_t)nf, st));  // 0x01010101: any non-zero value will do
+    } else if (flag_mode == 2 && nf <= 8) {
+      for (int f = 0; f < nf; f++)
+        if (write_value(st, (unsigned long long)(uintptr_t)(fl + f), 1u, 0u) != 0) return fail("cuStreamWriteValue32 failed");
+    } else {
+      CUDA_OK(cudaMemcpyAsync(fl, h.ones, sizeof(unsigned) * (size_t)nf, cudaMemcpyHostToDevice, st));
+    }
   }
   CUDA_OK(cudaEventRecord(h.landed, h.copy));
+  if (copy_streams == 2) CUDA_OK(cudaEventRecord(h.landed2, h.copy2));
   ChunkedInput ci;
   ci.flags = h.flags.as<unsigned>();
-  ci.chunk_frames = chunk_frames;
+  ci.chunk_frames = 1;  // one flag per frame
   ci.all_landed = h.landed;
-  const bool pipelined_out = deriv_host != nullptr && B <= tb::kMaxBP;
+  ci.all_landed2 = copy_streams == 2 ? h.landed2 : nullptr;
+  const bool pipelined_out = deriv_host != nullptr && B <= tb::kMaxBP && !getenv("TORCHAIN_HOST_NO_PIPELINED_OUT");
   if (pipelined_out) {
     *reinterpret_cast<volatile unsigned*>(h.progress) = 0u;
     unsigned* dptr = nullptr;
@@ -1649,27 +1736,26 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
     ci.deriv_progress = dptr;
   }
   // enqueue everything without synchronising (results are fetched below)
-  float* res_dev = nullptr;
   {
     static thread_local DevBuf res_buf;
     CUDA_OK(res_buf.reserve(4 * sizeof(float)));
-    res_dev = res_buf.as<float>();
+    ci.results4_dev = res_buf.as<float>();
   }
-  if (!compute(g, sp, h.y.as<float>(), rows, cols, row_layout(B, cols), nullptr, res_dev, deriv_dev,
+  if (!compute(g, sp, h.y.as<float>(), rows, cols, row_layout(B, cols), nullptr, nullptr, deriv_dev,
                row_layout(B, deriv_dev_stride), want_xent ? h.xent.as<float>() : nullptr, row_layout(B, cols), l2,
                leaky, xent_regularize, 1.0f, device, h.compute, ci))
     return 0;
   auto copy_chunk = [&](int k, cudaStream_t st) -> cudaError_t {
-    const int64_t r0 = (int64_t)k * chunk_frames * B;
-    const int64_t nr = std::min<int64_t>((int64_t)chunk_frames * B, rows - r0);
+    const int64_t r0 = (int64_t)cb[k] * B, nr = (int64_t)(cb[k + 1] - cb[k]) * B;
     return cudaMemcpy2DAsync(deriv_host + r0 * dstride, sizeof(float) * dstride, deriv_dev + r0 * cols,
                              sizeof(float) * cols, sizeof(float) * cols, nr, cudaMemcpyDeviceToHost, st);
   };
   int next = nchunks - 1;
+  if (trace) tr_enq = now_us() - tr0;
   if (pipelined_out) {
-    // frames >= T - progress are complete; chunk k covers frames [k*chunk_frames, ...)
+    // frames >= T - progress are complete; chunk k covers frames [cb[k], cb[k+1])
     while (next >= 1) {
-      const unsigned need = (unsigned)(T - next * chunk_frames);
+      const unsigned need = (unsigned)(T - cb[next]);
       bool done = false;
       while (*reinterpret_cast<volatile unsigned*>(h.progress) < need) {
         if (cudaStreamQuery(h.compute) != cudaErrorNotReady) {
@@ -1679,22 +1765,45 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
       }
       if (done) break;
       CUDA_OK(copy_chunk(next, h.copy));
+      if (trace) {
+        tr_last = now_us() - tr0;
+        if (tr_first < 0.0) tr_first = tr_last;
+      }
       next--;
     }
   }
+  const int first_early = next + 1;  // chunks [first_early, nchunks) left before the final pass had run
   CUDA_OK(cudaStreamSynchronize(h.compute));
+  if (copy_streams == 2) CUDA_OK(cudaStreamSynchronize(h.copy2));  // long done: the forward launch consumed its chunks
+  if (trace) tr_sync = now_us() - tr0;
   if (deriv_host)
     for (; next >= 0; next--) CUDA_OK(copy_chunk(next, h.copy));
   if (want_xent)
     CUDA_OK(cudaMemcpy2DAsync(xent_host, sizeof(float) * xstride, h.xent.ptr, sizeof(float) * cols,
                               sizeof(float) * cols, rows, cudaMemcpyDeviceToHost, h.copy));
-  float res_host[3];
-  CUDA_OK(cudaMemcpyAsync(res_host, res_dev, sizeof(res_host), cudaMemcpyDeviceToHost, h.copy));
+  float res_host[4];
+  CUDA_OK(cudaMemcpyAsync(res_host, ci.results4_dev, sizeof(res_host), cudaMemcpyDeviceToHost, h.copy));
   CUDA_OK(cudaStreamSynchronize(h.copy));
+  if (trace)
+    fprintf(stderr, "host_trace T=%d chunks=%d early=%d enqueued=%.0f first_early=%.0f last_early=%.0f compute_done=%.0f end=%.0f us\n",
+            T, nchunks, nchunks - first_early, tr_enq, tr_first, tr_last, tr_sync, now_us() - tr0);
+  if (deriv_host && first_early < nchunks && res_host[3] == 0.f) {
+    // The numeric guard tripped (Kaldi: objf = -10 * weight, derivative reset to the l2 part): the final
+    // pass rewrote the derivative AFTER the early chunks had left, so they go out again.
+    for (int k = first_early; k < nchunks; k++) CUDA_OK(copy_chunk(k, h.copy));
+    CUDA_OK(cudaStreamSynchronize(h.copy));
+  }
   results[0] = res_host[0];
   results[1] = res_host[1];
   results[2] = res_host[2];
   return 1;
+}
+
+int torchain_host_chunk_bounds(int num_frames, int* bounds, int max_entries) {
+  if (num_frames < 1) return 0;
+  const std::vector<int> b = chunk_bounds(num_frames);
+  for (int i = 0; i < (int)b.size() && i < max_entries && bounds; i++) bounds[i] = b[i];
+  return (int)b.size();
 }
 
 void torchain_profile_enable(int on) { g_profile.store(on); }

@@ -841,8 +841,12 @@ __device__ __forceinline__ void den_chain_body(const DenBatch& batch) {
         }
         if (ci == NCTX - 1 && t < T - 1 && p0.deriv_progress && blockIdx.x == 0 && threadIdx.x == 0) {
           // the derivative rows of frames > t+1 are complete in every context
+          // A plain posted store: the rows it announces were made visible by the grid barrier this
+          // thread has just acquired, and nothing after it depends on when it lands.  (A system-scope
+          // fence here kept thread 0 of CTA 0 -- and with it every frame -- waiting for the PCIe write:
+          // 65 us per call, profiles/r01_host_trace.txt.)
           *reinterpret_cast<volatile unsigned*>(p0.deriv_progress) = (unsigned)(T - 2 - t);
-          __threadfence_system();
+          if (p0.debug_flags & 2) __threadfence_system();
         }
         if (is_aux) {
           if (!(p.debug_flags & 1))
