@@ -760,3 +760,24 @@ def test_gpu_async_calls_calibrate_and_stay_correct():
         assert deriv_err(d.cpu().numpy(), r["deriv"]) < DERIV_RTOL
     res, d, _ = run_abi(g, s, y_np, 5e-5, 0.1)   # and a synchronising call afterwards
     assert rel(res[0], r["objf"]) < OBJF_RTOL and deriv_err(d, r["deriv"]) < DERIV_RTOL
+
+
+def test_host_buffer_entry_padded_rows():
+    """Host buffers whose row stride exceeds the row length (pitched 2-D copies; densely packed rows go as
+    one linear copy): same results, and the padding of the derivative buffer is left alone."""
+    lib = _lib.load()
+    c = load_golden(GOLDEN[2])
+    g, s = handles(c["den"], c["sup"])
+    y = np.ascontiguousarray(c["y"], dtype=np.float32)
+    rows, cols = y.shape
+    yp = np.zeros((rows, cols + 5), dtype=np.float32)
+    yp[:, :cols] = y
+    dp = np.full((rows, cols + 3), np.nan, dtype=np.float32)
+    res = np.zeros(3, dtype=np.float32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    ok = lib.torchain_ComputeChainObjfAndDeriv_host(g.ptr, s.ptr, p(yp), rows, cols, cols + 5, p(res),
+                                                    p(dp), cols + 3, None, 0, c["l2"], c["leaky"], 0.0, 0)
+    assert ok == 1, _lib.last_error()
+    assert rel(res[0], c["objf"]) < OBJF_RTOL
+    assert deriv_err(dp[:, :cols], c["deriv"]) < DERIV_RTOL
+    assert np.isnan(dp[:, cols:]).all()

@@ -1260,6 +1260,15 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   return 1;
 }
 
+// Rows of `width` bytes between pitched buffers; densely packed rows go as ONE linear copy (the copy
+// engine then moves a single contiguous range instead of `rows` lines).
+cudaError_t copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t rows,
+                      cudaMemcpyKind kind, cudaStream_t st) {
+  if (rows == 0 || width == 0) return cudaSuccess;
+  if (dpitch == width && spitch == width) return cudaMemcpyAsync(dst, src, width * rows, kind, st);
+  return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, st);
+}
+
 // Per-thread resources of the host-buffer entry.
 struct HostPath {
   int device = -1;
@@ -1708,7 +1717,7 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
   for (int k = 0; k < nchunks; k++) {
     const int64_t r0 = (int64_t)cb[k] * B, nr = (int64_t)(cb[k + 1] - cb[k]) * B;
     const cudaStream_t st = (copy_streams == 2 && (k & 1)) ? h.copy2 : h.copy;
-    CUDA_OK(cudaMemcpy2DAsync(h.y.as<float>() + r0 * cols, sizeof(float) * cols, y_host + r0 * ystride,
+    CUDA_OK(copy_rows(h.y.as<float>() + r0 * cols, sizeof(float) * cols, y_host + r0 * ystride,
                               sizeof(float) * ystride, sizeof(float) * cols, nr, cudaMemcpyHostToDevice, st));
     unsigned* const fl = h.flags.as<unsigned>() + cb[k];
     const int nf = cb[k + 1] - cb[k];
@@ -1747,7 +1756,7 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
     return 0;
   auto copy_chunk = [&](int k, cudaStream_t st) -> cudaError_t {
     const int64_t r0 = (int64_t)cb[k] * B, nr = (int64_t)(cb[k + 1] - cb[k]) * B;
-    return cudaMemcpy2DAsync(deriv_host + r0 * dstride, sizeof(float) * dstride, deriv_dev + r0 * cols,
+    return copy_rows(deriv_host + r0 * dstride, sizeof(float) * dstride, deriv_dev + r0 * cols,
                              sizeof(float) * cols, sizeof(float) * cols, nr, cudaMemcpyDeviceToHost, st);
   };
   int next = nchunks - 1;
@@ -1779,7 +1788,7 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
   if (deriv_host)
     for (; next >= 0; next--) CUDA_OK(copy_chunk(next, h.copy));
   if (want_xent)
-    CUDA_OK(cudaMemcpy2DAsync(xent_host, sizeof(float) * xstride, h.xent.ptr, sizeof(float) * cols,
+    CUDA_OK(copy_rows(xent_host, sizeof(float) * xstride, h.xent.ptr, sizeof(float) * cols,
                               sizeof(float) * cols, rows, cudaMemcpyDeviceToHost, h.copy));
   float res_host[4];
   CUDA_OK(cudaMemcpyAsync(res_host, ci.results4_dev, sizeof(res_host), cudaMemcpyDeviceToHost, h.copy));
