@@ -1703,15 +1703,18 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
   if (const char* e = getenv("TORCHAIN_HOST_COPY_STREAMS")) copy_streams = atoi(e) == 2 ? 2 : 1;
   if (const char* e = getenv("TORCHAIN_HOST_FLAG_MODE")) flag_mode = !strcmp(e, "memset") ? 1 : (!strcmp(e, "write") ? 2 : 0);
   typedef int (*WriteValue32)(cudaStream_t, unsigned long long, unsigned, unsigned);
-  static WriteValue32 write_value = [] {
+  static std::atomic<WriteValue32> write_value_fn{nullptr};
+  WriteValue32 write_value = write_value_fn.load();
+  if (flag_mode == 2 && !write_value) {  // looked up only when the experiment asks for it
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult st;
     if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &st) != cudaSuccess ||
         st != cudaDriverEntryPointSuccess)
       fn = nullptr;
     (void)cudaGetLastError();
-    return reinterpret_cast<WriteValue32>(fn);
-  }();
+    write_value = reinterpret_cast<WriteValue32>(fn);
+    write_value_fn.store(write_value);
+  }
   if (flag_mode == 2 && !write_value) flag_mode = 0;
   if (copy_streams == 2) CUDA_OK(cudaStreamWaitEvent(h.copy2, h.ready, 0));
   for (int k = 0; k < nchunks; k++) {
