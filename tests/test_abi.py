@@ -353,3 +353,37 @@ def test_host_chunk_bounds_schedule():
         if T > 32:
             assert sizes[0] == 1 and sizes[-1] == 1
             assert sizes == sizes[::-1] or sizes[:3] == sizes[::-1][:3]
+
+
+def test_text_fst_and_dead_end_graphs_end_in_errors(tmp_path):
+    """Hostile text FSTs (negative or huge state ids, a size field that cannot be allocated) and a graph
+    whose probability mass dies out end in ValueError with a message -- no out-of-bounds write, no
+    exception through the C ABI, no NaN initial probabilities."""
+    cases = {
+        "neg_final.txt": "0 1 1 1 0.5\n1 0 1 1 0.5\n-7 0.0\n",
+        "neg_arc.txt": "0 -3 1 1 0.5\n0 0.0\n",
+        "huge_state.txt": "0 2000000000 1 1 0.5\n0 0.0\n",
+        "huge_final.txt": "0 0 1 1 0.5\n2147483647 0.0\n",
+    }
+    for name, text in cases.items():
+        p = str(tmp_path / name)
+        with open(p, "w") as f:
+            f.write(text)
+        with pytest.raises(ValueError):
+            io.DenominatorGraph(p, 4)
+        assert _lib.last_error() != ""
+    # binary header announcing 2^30 states in a 100-byte file
+    p = str(tmp_path / "liar.fst")
+    with open(p, "wb") as f:
+        f.write(struct.pack("<i", 2125659606))
+        for s in (b"vector", b"standard"):
+            f.write(struct.pack("<i", len(s)) + s)
+        f.write(struct.pack("<iiQqqq", 2, 0, 0, 0, 1 << 30, 5))
+        f.write(b"\0" * 20)
+    with pytest.raises(ValueError):
+        io.DenominatorGraph(p, 4)
+    # start state -> dead end: Kaldi's SetInitialProbs would divide by zero
+    with pytest.raises(ValueError, match="no outgoing arcs"):
+        io.DenominatorGraph.from_arrays(2, np.array([0], dtype=np.int32), np.array([1], dtype=np.int32),
+                                        np.array([1], dtype=np.int32), np.array([0.1], dtype=np.float32), 0,
+                                        np.array([np.inf, 0.0], dtype=np.float32), 1)

@@ -360,6 +360,10 @@ DenGraph* make_den_graph(int32_t N, int32_t A, const int32_t* src, const int32_t
     }
     double sum = 0.0;
     for (int s = 0; s < N; s++) sum += nxt[s];
+    if (!(sum > 0.0) || !std::isfinite(sum)) {  // Kaldi would go on with NaN initial probabilities
+      g_error = "denominator graph: the states reachable from the start state have no outgoing arcs";
+      return nullptr;
+    }
     for (int s = 0; s < N; s++) {
       cur[s] = nxt[s] / sum;
       nxt[s] = 0.0;
@@ -477,6 +481,10 @@ bool read_fst_file(const char* path, std::vector<int32_t>* src, std::vector<int3
       } else {
         int32_t s = std::stoi(tok[0]);
         float w = tok.size() >= 2 ? std::stof(tok[1]) : 0.f;
+        if (s < 0) {
+          g_error = std::string("negative state id in text FST: ") + path;
+          return false;
+        }
         if (first) *start = s;
         finals.emplace_back(s, w);
         max_state = std::max(max_state, s);
@@ -489,6 +497,10 @@ bool read_fst_file(const char* path, std::vector<int32_t>* src, std::vector<int3
   }
   if (max_state < 0) {
     g_error = std::string("empty FST: ") + path;
+    return false;
+  }
+  if (max_state >= (1 << 27)) {
+    g_error = std::string("text FST has an implausible state id: ") + path;
     return false;
   }
   final_cost->assign(max_state + 1, kInf);
@@ -1408,6 +1420,23 @@ Supervision* parse_kaldi_supervision(const void* data, int64_t nbytes, int64_t* 
                           arc_cost.data(), final_cost.data());
 }
 
+// Nothing may propagate through the C ABI: a std::bad_alloc / std::length_error from a corrupt size field
+// or an exhausted host ends as an error return with torchain_last_error() set.
+int abi_exception_int() {
+  try {
+    throw;
+  } catch (const std::exception& e) {
+    g_error = std::string("internal error: ") + e.what();
+  } catch (...) {
+    g_error = "internal error: unknown exception";
+  }
+  return 0;
+}
+void* abi_exception_ptr() {
+  abi_exception_int();
+  return nullptr;
+}
+
 }  // namespace
 
 // ===========================================================================
@@ -1428,13 +1457,15 @@ int my_lib_set_kaldi_device(int device) {
 
 void* torchain_denominator_graph_from_arrays(int32_t num_states, int32_t num_arcs, const int32_t* src,
                                              const int32_t* dst, const int32_t* ilabel, const float* cost,
-                                             int32_t start, const float* final_cost, int32_t num_pdfs) {
+                                             int32_t start, const float* final_cost, int32_t num_pdfs) try {
   if (num_arcs > 0 && (!src || !dst || !ilabel || !cost)) return fail_ptr("denominator graph: null arc arrays");
   if (!final_cost) return fail_ptr("denominator graph: null final_cost");
   return make_den_graph(num_states, num_arcs, src, dst, ilabel, cost, start, final_cost, num_pdfs);
+} catch (...) {
+  return abi_exception_ptr();
 }
 
-void* my_lib_denominator_graph_new(const char* rxfilename, int num_pdf) {
+void* my_lib_denominator_graph_new(const char* rxfilename, int num_pdf) try {
   if (!rxfilename) return fail_ptr("null rxfilename");
   std::vector<int32_t> src, dst, il;
   std::vector<float> cost, fin;
@@ -1442,33 +1473,41 @@ void* my_lib_denominator_graph_new(const char* rxfilename, int num_pdf) {
   if (!read_fst_file(rxfilename, &src, &dst, &il, &cost, &start, &fin)) return nullptr;
   return make_den_graph((int32_t)fin.size(), (int32_t)src.size(), src.data(), dst.data(), il.data(), cost.data(),
                         start, fin.data(), num_pdf);
+} catch (...) {
+  return abi_exception_ptr();
 }
 
 void my_lib_denominator_graph_free(void* p) { delete static_cast<DenGraph*>(p); }
 int torchain_denominator_graph_num_states(void* p) { return p ? static_cast<DenGraph*>(p)->N : 0; }
 int torchain_denominator_graph_num_arcs(void* p) { return p ? static_cast<DenGraph*>(p)->A : 0; }
 int torchain_denominator_graph_num_pdfs(void* p) { return p ? static_cast<DenGraph*>(p)->P : 0; }
-int torchain_denominator_graph_initial_probs(void* p, float* out) {
+int torchain_denominator_graph_initial_probs(void* p, float* out) try {
   if (!p || !out) return fail("null argument");
   auto* g = static_cast<DenGraph*>(p);
   std::memcpy(out, g->pi.data(), sizeof(float) * g->N);
   return 1;
+} catch (...) {
+  return abi_exception_int();
 }
 
 void* torchain_supervision_from_arrays(float weight, int32_t num_sequences, int32_t frames_per_sequence,
                                        int32_t label_dim, int32_t num_states, const int32_t* arc_begin,
                                        const int32_t* arc_dst, const int32_t* arc_label, const float* arc_cost,
-                                       const float* final_cost) {
+                                       const float* final_cost) try {
   if (!arc_begin || !final_cost) return fail_ptr("supervision: null arrays");
   if (arc_begin[num_states > 0 ? num_states : 0] > 0 && (!arc_dst || !arc_label || !arc_cost))
     return fail_ptr("supervision: null arc arrays");
   return make_supervision(weight, num_sequences, frames_per_sequence, label_dim, num_states, arc_begin, arc_dst,
                           arc_label, arc_cost, final_cost);
+} catch (...) {
+  return abi_exception_ptr();
 }
 
-void* torchain_supervision_from_kaldi_bytes(const void* data, int64_t nbytes, int64_t* consumed) {
+void* torchain_supervision_from_kaldi_bytes(const void* data, int64_t nbytes, int64_t* consumed) try {
   if (!data || nbytes <= 0) return fail_ptr("supervision: null / empty buffer");
   return parse_kaldi_supervision(data, nbytes, consumed);
+} catch (...) {
+  return abi_exception_ptr();
 }
 
 void* my_lib_supervision_new(void*) {
@@ -1482,7 +1521,7 @@ void* my_lib_supervision_rand_new(void*) {
 // frames_per_sequence and label_dim are appended sequence-major; Kaldi concatenates the FSTs and removes
 // the epsilons, which leaves the per-sequence chains independent -- exactly the split representation
 // kept here, so merging is a concatenation of chain lists with shifted state / arc / sequence indices.
-void* torchain_supervision_merge(void* const* sups, int32_t n) {
+void* torchain_supervision_merge(void* const* sups, int32_t n) try {
   if (!sups || n <= 0) return fail_ptr("supervision merge: empty list");
   for (int i = 0; i < n; i++)
     if (!sups[i]) return fail_ptr("supervision merge: null handle");
@@ -1539,6 +1578,8 @@ void* torchain_supervision_merge(void* const* sups, int32_t n) {
   std::vector<int> pos(out->frame_off.begin(), out->frame_off.end() - 1);
   for (int a = 0; a < NA; a++) out->frame_arcs[pos[out->arc_row[a] / out->B]++] = a;
   return out.release();
+} catch (...) {
+  return abi_exception_ptr();
 }
 
 void my_lib_supervision_free(void* p) { delete static_cast<Supervision*>(p); }
@@ -1550,13 +1591,15 @@ int torchain_supervision_num_chains(void* p) { return p ? static_cast<Supervisio
 int torchain_ComputeChainObjfAndDeriv_ex(void* den, void* sup, const float* y, int64_t rows, int64_t cols,
                                          int64_t ystride, float* results, float* results_dev, float* deriv,
                                          int64_t dstride, float* xent, int64_t xstride, float l2, float leaky,
-                                         float xent_regularize, float deriv_scale, int device, void* stream) {
+                                         float xent_regularize, float deriv_scale, int device, void* stream) try {
   if (!sup) return fail("null den_graph / supervision handle");
   if (ystride < cols || (deriv && dstride < cols) || (xent && xstride < cols)) return fail("row stride < cols");
   const int B = static_cast<Supervision*>(sup)->B;
   return compute(static_cast<DenGraph*>(den), static_cast<Supervision*>(sup), y, rows, cols, row_layout(B, ystride),
                  results, results_dev, deriv, row_layout(B, dstride), xent, row_layout(B, xstride), l2, leaky,
                  xent_regularize, deriv_scale, device, static_cast<cudaStream_t>(stream));
+} catch (...) {
+  return abi_exception_int();
 }
 
 int torchain_ComputeChainObjfAndDeriv_strided(void* den, void* sup, const float* y, int64_t num_frames,
@@ -1564,7 +1607,7 @@ int torchain_ComputeChainObjfAndDeriv_strided(void* den, void* sup, const float*
                                               float* results, float* results_dev, float* deriv,
                                               const int64_t* deriv_strides, float* xent, const int64_t* xent_strides,
                                               float l2, float leaky, float xent_regularize, float deriv_scale,
-                                              int device, void* stream) {
+                                              int device, void* stream) try {
   if (!sup) return fail("null den_graph / supervision handle");
   auto* sp = static_cast<Supervision*>(sup);
   if (num_frames != sp->T || num_sequences != sp->B)
@@ -1574,12 +1617,14 @@ int torchain_ComputeChainObjfAndDeriv_strided(void* den, void* sup, const float*
   return compute(static_cast<DenGraph*>(den), sp, y, num_frames * num_sequences, num_pdfs, lay(y_strides), results,
                  results_dev, deriv, lay(deriv_strides), xent, lay(xent_strides), l2, leaky, xent_regularize,
                  deriv_scale, device, static_cast<cudaStream_t>(stream));
+} catch (...) {
+  return abi_exception_int();
 }
 
 int my_lib_ComputeChainObjfAndDeriv(void* den, void* sup, const float* y, int64_t rows, int64_t cols,
                                     int64_t ystride, float* results, float* deriv, int64_t dstride, float* xent,
                                     int64_t xstride, float l2, float leaky, float xent_regularize, int device,
-                                    void* stream) {
+                                    void* stream) try {
   if (!results) return fail("null results");
   if (!sup) return fail("null den_graph / supervision handle");
   if (ystride < cols || (deriv && dstride < cols) || (xent && xstride < cols)) return fail("row stride < cols");
@@ -1587,10 +1632,12 @@ int my_lib_ComputeChainObjfAndDeriv(void* den, void* sup, const float* y, int64_
   return compute(static_cast<DenGraph*>(den), static_cast<Supervision*>(sup), y, rows, cols, row_layout(B, ystride),
                  results, nullptr, deriv, row_layout(B, dstride), xent, row_layout(B, xstride), l2, leaky,
                  xent_regularize, 1.0f, device, static_cast<cudaStream_t>(stream));
+} catch (...) {
+  return abi_exception_int();
 }
 
 int torchain_to2d(const float* x_bpt, int64_t B, int64_t P, int64_t T, float* out_rows, int64_t out_stride, int device,
-                  void* stream) {
+                  void* stream) try {
   if (!x_bpt || !out_rows) return fail("null tensor");
   if (B < 0 || P < 0 || T < 0 || out_stride < P) return fail("bad shape / row stride < cols");
   DeviceGuard guard(device);
@@ -1599,10 +1646,12 @@ int torchain_to2d(const float* x_bpt, int64_t B, int64_t P, int64_t T, float* ou
   if (e == cudaErrorInvalidValue) return fail("to2d: frames_per_sequence or num_sequences too large for the tiled kernel");
   CUDA_OK(e);
   return 1;
+} catch (...) {
+  return abi_exception_int();
 }
 
 int torchain_from2d(const float* rows, int64_t in_stride, int64_t B, int64_t P, int64_t T, float* out_bpt, float scale,
-                    int device, void* stream) {
+                    int device, void* stream) try {
   if (!rows || !out_bpt) return fail("null tensor");
   if (B < 0 || P < 0 || T < 0 || in_stride < P) return fail("bad shape / row stride < cols");
   DeviceGuard guard(device);
@@ -1611,12 +1660,14 @@ int torchain_from2d(const float* rows, int64_t in_stride, int64_t B, int64_t P, 
   if (e == cudaErrorInvalidValue) return fail("from2d: frames_per_sequence or num_sequences too large for the tiled kernel");
   CUDA_OK(e);
   return 1;
+} catch (...) {
+  return abi_exception_int();
 }
 
 int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_host, int64_t rows, int64_t cols,
                                            int64_t ystride, float* results, float* deriv_host, int64_t dstride,
                                            float* xent_host, int64_t xstride, float l2, float leaky,
-                                           float xent_regularize, int device) {
+                                           float xent_regularize, int device) try {
   if (!den || !sup) return fail("null den_graph / supervision handle");
   if (!y_host || !results) return fail("null nnet_output / results");
   DeviceGuard guard(device);
@@ -1809,13 +1860,17 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
   results[1] = res_host[1];
   results[2] = res_host[2];
   return 1;
+} catch (...) {
+  return abi_exception_int();
 }
 
-int torchain_host_chunk_bounds(int num_frames, int* bounds, int max_entries) {
+int torchain_host_chunk_bounds(int num_frames, int* bounds, int max_entries) try {
   if (num_frames < 1) return 0;
   const std::vector<int> b = chunk_bounds(num_frames);
   for (int i = 0; i < (int)b.size() && i < max_entries && bounds; i++) bounds[i] = b[i];
   return (int)b.size();
+} catch (...) {
+  return abi_exception_int();
 }
 
 void torchain_profile_enable(int on) { g_profile.store(on); }
