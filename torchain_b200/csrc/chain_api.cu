@@ -60,8 +60,14 @@ const float kInf = std::numeric_limits<float>::infinity();
 struct DevBuf {
   void* ptr = nullptr;
   size_t bytes = 0;
-  ~DevBuf() {
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
     if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    bytes = 0;
   }
   cudaError_t reserve(size_t n) {
     if (n <= bytes) return cudaSuccess;
@@ -1290,6 +1296,31 @@ struct HostPath {
   unsigned* ones = nullptr;      // pinned constant 1s, one per frame flag of a chunk
   int ones_cap = 0;
   unsigned* progress = nullptr;  // pinned, device-mapped: frames of the derivative already complete
+  HostPath() = default;
+  HostPath(const HostPath&) = delete;
+  HostPath& operator=(const HostPath&) = delete;
+  // No destructor on purpose: a thread_local of the main thread dies during process teardown, when the
+  // CUDA runtime may already be gone; streams and events of an ending thread are left to the driver.
+  void release() {  // everything belongs to `device`; called when the thread moves to another device
+    if (compute) cudaStreamDestroy(compute);
+    if (copy) cudaStreamDestroy(copy);
+    if (copy2) cudaStreamDestroy(copy2);
+    if (ready) cudaEventDestroy(ready);
+    if (landed) cudaEventDestroy(landed);
+    if (landed2) cudaEventDestroy(landed2);
+    if (ones) cudaFreeHost(ones);
+    if (progress) cudaFreeHost(progress);
+    compute = copy = copy2 = nullptr;
+    ready = landed = landed2 = nullptr;
+    ones = nullptr;
+    ones_cap = 0;
+    progress = nullptr;
+    y.release();
+    deriv.release();
+    xent.release();
+    flags.release();
+    device = -1;
+  }
 };
 thread_local HostPath g_host;
 
@@ -1680,15 +1711,7 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
     return fail("row stride < cols");
   HostPath& h = g_host;
   if (h.device != device) {
-    if (h.compute) cudaStreamDestroy(h.compute);
-    if (h.copy) cudaStreamDestroy(h.copy);
-    if (h.copy2) cudaStreamDestroy(h.copy2);
-    if (h.ready) cudaEventDestroy(h.ready);
-    if (h.landed) cudaEventDestroy(h.landed);
-    if (h.landed2) cudaEventDestroy(h.landed2);
-    if (h.ones) cudaFreeHost(h.ones);
-    if (h.progress) cudaFreeHost(h.progress);
-    h = HostPath();
+    h.release();
     CUDA_OK(cudaStreamCreateWithFlags(&h.compute, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&h.copy, cudaStreamNonBlocking));
     CUDA_OK(cudaStreamCreateWithFlags(&h.copy2, cudaStreamNonBlocking));
