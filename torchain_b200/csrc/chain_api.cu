@@ -545,7 +545,7 @@ struct RawArc {
 Supervision* make_supervision(float weight, int32_t B, int32_t T, int32_t label_dim, int32_t S,
                               const int32_t* arc_begin, const int32_t* arc_dst, const int32_t* arc_label,
                               const float* arc_cost, const float* final_cost) {
-  if (B <= 0 || T <= 0 || label_dim <= 0 || S <= 0) {
+  if (B <= 0 || T <= 0 || label_dim <= 0 || S <= 0 || (int64_t)B * T > (int64_t)(1 << 30)) {
     g_error = "supervision: bad sizes";
     return nullptr;
   }
