@@ -387,3 +387,36 @@ def test_text_fst_and_dead_end_graphs_end_in_errors(tmp_path):
         io.DenominatorGraph.from_arrays(2, np.array([0], dtype=np.int32), np.array([1], dtype=np.int32),
                                         np.array([1], dtype=np.int32), np.array([0.1], dtype=np.float32), 0,
                                         np.array([np.inf, 0.0], dtype=np.float32), 1)
+
+
+def test_header_is_plain_c_and_links_from_a_c_host(tmp_path):
+    """The boundary is a C ABI: include/torchain_b200.h must compile as C99 (no C++-isms, no torch or CUDA
+    types) and a C host must be able to link the library and call it -- here the device-free entry points."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "torchain_b200.h"
+int main(void) {
+  int b[64];
+  int n = torchain_host_chunk_bounds(50, b, 64);
+  if (torchain_abi_version() < 1 || n < 2 || b[0] != 0 || b[n - 1] != 50) return 1;
+  /* error convention: NULL / 0 plus a message, never an abort */
+  if (my_lib_denominator_graph_new("/nonexistent/den.fst", 10) != NULL) return 2;
+  if (strlen(torchain_last_error()) == 0) return 3;
+  if (my_lib_supervision_num_pdf(NULL) != 0) return 4;
+  printf("ok %d\n", n);
+  return 0;
+}
+''')
+    exe = str(tmp_path / "host")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.dirname(HEADER), str(src),
+                    "-o", exe, "-L", libdir, "-l:libtorchain_b200.so", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert out.startswith("ok ")
