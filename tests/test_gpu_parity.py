@@ -781,3 +781,16 @@ def test_host_buffer_entry_padded_rows():
     assert rel(res[0], c["objf"]) < OBJF_RTOL
     assert deriv_err(dp[:, :cols], c["deriv"]) < DERIV_RTOL
     assert np.isnan(dp[:, cols:]).all()
+
+
+def test_reference_training_loop():
+    """The reference's integration test (test/test.py:19-78: Conv1d model with LF-MMI and xent heads, 11 SGD
+    steps, l2 0.01, xent 0.01, kaldi_way=True, (B, C, T) model outputs handed to chain_loss as they are) on
+    synthetic data, with the assertions tests/training_smoke.py adds; the CPU suite pins the same
+    expectations with an oracle-backed loss (tests/test_oracle.py)."""
+    import training_smoke as ts
+    from torchain_b200.functions import chain_loss
+    den, sup, x = ts.make_task()
+    g, s = handles(den, sup)
+    hist = ts.run_sgd(chain_loss, g, s, x, den.num_pdfs, "cuda")
+    ts.check_history(hist, sup.num_sequences, sup.frames_per_sequence)

@@ -202,3 +202,41 @@ def test_run_based_recurrence_matches_oracle():
         # both sides round the initial probabilities to fp32 (Kaldi) from independently computed doubles: 1 ulp
         assert np.abs(gamma - gamma_den).max() < 2e-7
         assert np.abs(gamma.sum(axis=1) - 1.0).max() < 1e-9
+
+
+def test_reference_training_loop_with_oracle_backed_loss():
+    """tests/training_smoke.py (the reference's test/test.py loop) driven by an oracle-backed autograd
+    function on the CPU: pins the expectations the GPU suite then holds the CUDA path to
+    (tests/test_gpu_parity.py::test_reference_training_loop)."""
+    import torch
+    from torch.autograd import Function
+    import training_smoke as ts
+    from torchain_b200.functions import ChainResults
+
+    den, sup, x = ts.make_task()
+    oden, osup = ol.OracleDen(den), ol.OracleSup(sup)
+    B, T, P = sup.num_sequences, sup.frames_per_sequence, den.num_pdfs
+
+    class OracleLoss(Function):
+        @staticmethod
+        def forward(ctx, inp, xent_inp, results, l2, leaky, xent_reg):
+            y = inp.detach().permute(2, 0, 1).reshape(T * B, P).double().numpy()
+            r = ol.chain(oden, osup, y, l2=l2, leaky=leaky, mode="fp64", want_xent=True)
+            results.data[0], results.data[1], results.data[2] = r["objf"], r["l2_term"], r["weight"]
+            back = lambda d: torch.from_numpy(d).view(T, B, P).permute(1, 2, 0).to(inp.dtype)
+            ctx.g, ctx.gx = -back(r["deriv"]), -xent_reg * back(r["xent"])
+            return inp.new_tensor([float(results.loss)])
+
+        @staticmethod
+        def backward(ctx, grad_output):
+            return ctx.g, ctx.gx, None, None, None, None
+
+    def loss_fn(pred, den_graph, supervision, l2_regularize=0.0, leaky_hmm_coefficient=1e-5,
+                xent_regularize=0.0, xent_input=None, kaldi_way=False):
+        assert kaldi_way and xent_input is not None
+        results = ChainResults()
+        return OracleLoss.apply(pred, xent_input, results, l2_regularize, leaky_hmm_coefficient,
+                                xent_regularize), results
+
+    hist = ts.run_sgd(loss_fn, None, None, x, P, "cpu")
+    ts.check_history(hist, B, T)
