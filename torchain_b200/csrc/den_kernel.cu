@@ -140,19 +140,6 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* ptr) {
   return v;
 }
 
-// All CTAs of the (co-resident) grid meet here.  `epoch` lives in thread 0.
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& epoch) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    epoch += gridDim.x;
-    __threadfence();  // release everything this CTA wrote (cumulative over the bar.sync above)
-    atomicAdd(counter, 1u);
-    while (ld_acquire(counter) < epoch) {
-    }
-  }
-  __syncthreads();
-}
-
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
