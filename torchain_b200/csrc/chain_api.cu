@@ -1829,8 +1829,13 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
   }
   if (!compute(g, sp, h.y.as<float>(), rows, cols, row_layout(B, cols), nullptr, nullptr, deriv_dev,
                row_layout(B, deriv_dev_stride), want_xent ? h.xent.as<float>() : nullptr, row_layout(B, cols), l2,
-               leaky, xent_regularize, 1.0f, device, h.compute, ci))
+               leaky, xent_regularize, 1.0f, device, h.compute, ci)) {
+    // nothing may still be reading the caller's buffer (or waiting for its chunks) once this returns
+    cudaStreamSynchronize(h.copy);
+    if (copy_streams == 2) cudaStreamSynchronize(h.copy2);
+    cudaStreamSynchronize(h.compute);
     return 0;
+  }
   auto copy_chunk = [&](int k, cudaStream_t st) -> cudaError_t {
     const int64_t r0 = (int64_t)cb[k] * B, nr = (int64_t)(cb[k + 1] - cb[k]) * B;
     return copy_rows(deriv_host + r0 * dstride, sizeof(float) * dstride, deriv_dev + r0 * cols,
