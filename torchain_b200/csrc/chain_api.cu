@@ -517,8 +517,21 @@ bool read_fst_file(const char* path, std::vector<int32_t>* src, std::vector<int3
 // ---------------------------------------------------------------------------
 // Supervision handle
 // ---------------------------------------------------------------------------
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// The device copy of a supervision is ONE allocation filled by ONE copy: a training loop builds a new
+// Supervision for every minibatch, and 14 separate arrays cost 14 x (cudaMalloc + synchronous cudaMemcpy) on
+// first use and 14 x cudaFree (each an implicit device synchronisation) when the handle dies.
+struct DevView {  // a typed window into SupDevice::blob
+  void* ptr = nullptr;
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(ptr);
+  }
+};
 struct SupDevice {
-  DevBuf chain_level_off, level_state_off, chain_arc_off, in_off, in_arcs, out_off, out_arcs, final_cost, arc_row,
+  DevBuf blob;
+  DevView chain_level_off, level_state_off, chain_arc_off, in_off, in_arcs, out_off, out_arcs, final_cost, arc_row,
       arc_pdf, arc_cost, arc_seq, frame_off, frame_arcs;
 };
 
@@ -896,20 +909,33 @@ int get_sup_device(Supervision* s, int device, SupDevice** out) {
     return 1;
   }
   auto d = std::make_unique<SupDevice>();
-  CUDA_OK(upload(d->chain_level_off, s->chain_level_off));
-  CUDA_OK(upload(d->level_state_off, s->level_state_off));
-  CUDA_OK(upload(d->chain_arc_off, s->chain_arc_off));
-  CUDA_OK(upload(d->in_off, s->in_off));
-  CUDA_OK(upload(d->in_arcs, s->in_arcs));
-  CUDA_OK(upload(d->out_off, s->out_off));
-  CUDA_OK(upload(d->out_arcs, s->out_arcs));
-  CUDA_OK(upload(d->final_cost, s->final_cost));
-  CUDA_OK(upload(d->arc_row, s->arc_row));
-  CUDA_OK(upload(d->arc_pdf, s->arc_pdf));
-  CUDA_OK(upload(d->arc_cost, s->arc_cost));
-  CUDA_OK(upload(d->arc_seq, s->arc_seq));
-  CUDA_OK(upload(d->frame_off, s->frame_off));
-  CUDA_OK(upload(d->frame_arcs, s->frame_arcs));
+  // lay the arrays out back to back (256-byte slots), stage them in one host buffer, upload once
+  std::vector<char> stage;
+  std::vector<std::pair<DevView*, size_t>> slots;
+  auto add = [&](DevView& view, const void* src, size_t nbytes) {
+    const size_t off = stage.size();
+    stage.resize(off + align_up(std::max<size_t>(nbytes, 16), 256));
+    if (nbytes) std::memcpy(stage.data() + off, src, nbytes);
+    slots.emplace_back(&view, off);
+  };
+  auto add_vec = [&](DevView& view, const auto& v) { add(view, v.data(), sizeof(v[0]) * v.size()); };
+  add_vec(d->chain_level_off, s->chain_level_off);
+  add_vec(d->level_state_off, s->level_state_off);
+  add_vec(d->chain_arc_off, s->chain_arc_off);
+  add_vec(d->in_off, s->in_off);
+  add_vec(d->in_arcs, s->in_arcs);
+  add_vec(d->out_off, s->out_off);
+  add_vec(d->out_arcs, s->out_arcs);
+  add_vec(d->final_cost, s->final_cost);
+  add_vec(d->arc_row, s->arc_row);
+  add_vec(d->arc_pdf, s->arc_pdf);
+  add_vec(d->arc_cost, s->arc_cost);
+  add_vec(d->arc_seq, s->arc_seq);
+  add_vec(d->frame_off, s->frame_off);
+  add_vec(d->frame_arcs, s->frame_arcs);
+  CUDA_OK(d->blob.reserve(stage.size()));
+  CUDA_OK(cudaMemcpy(d->blob.ptr, stage.data(), stage.size(), cudaMemcpyHostToDevice));
+  for (auto& sl : slots) sl.first->ptr = d->blob.as<char>() + sl.second;
   *out = d.get();
   s->dev[device] = std::move(d);
   return 1;
@@ -951,7 +977,6 @@ void harvest_profile(DenGraph* g) {
   }
 }
 
-size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int pad_batch(int b) {
   if (b <= 32) return 32;
