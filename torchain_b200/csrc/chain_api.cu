@@ -152,6 +152,8 @@ struct Workspace {
   char* timeline_dev = nullptr;
   int timeline_len = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;  // around each denominator launch (profiling only)
+  int in_use = 0;                // calls currently between get_workspace and their return (guarded by DenGraph::mu)
+  unsigned long long last_use = 0;  // DenGraph::ws_clock at the last get_workspace
   ~Workspace() {
     for (auto& pr : prof) {
       cudaEventDestroy(pr.first);
@@ -173,7 +175,12 @@ struct DenGraph {
   std::mutex mu;
   std::map<int, std::unique_ptr<DenDevice>> dev;
   std::map<std::pair<int, void*>, std::unique_ptr<Workspace>> ws;
+  unsigned long long ws_clock = 0;
 };
+// A workspace holds the alpha store (261 MB at config 2).  Callers that hop between streams (torch hands
+// out 32 pooled streams per device) must not accumulate one per stream: beyond this many per device the
+// least recently used idle one is dropped (its buffers are freed, which waits for the device).
+constexpr int kMaxWorkspacesPerDevice = 4;
 
 // Longest-processing-time-first assignment of weighted items to bins of different speeds:
 // each item (heaviest first) goes to the bin that would finish it earliest.
@@ -946,6 +953,8 @@ int get_workspace(DenGraph* g, int device, void* stream, Workspace** out) {
   auto key = std::make_pair(device, stream);
   auto it = g->ws.find(key);
   if (it != g->ws.end()) {
+    it->second->in_use++;
+    it->second->last_use = ++g->ws_clock;
     *out = it->second.get();
     return 1;
   }
@@ -954,10 +963,34 @@ int get_workspace(DenGraph* g, int device, void* stream, Workspace** out) {
   CUDA_OK(cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming));
   CUDA_OK(cudaMallocHost(&w->pinned, 4 * sizeof(float)));
+  // make room first: drop idle workspaces of this device, least recently used first
+  for (;;) {
+    int count = 0;
+    auto lru = g->ws.end();
+    for (auto jt = g->ws.begin(); jt != g->ws.end(); ++jt) {
+      if (jt->first.first != device) continue;
+      count++;
+      if (jt->second->in_use == 0 && (lru == g->ws.end() || jt->second->last_use < lru->second->last_use)) lru = jt;
+    }
+    if (count < kMaxWorkspacesPerDevice || lru == g->ws.end()) break;
+    g->ws.erase(lru);
+  }
+  w->in_use = 1;
+  w->last_use = ++g->ws_clock;
   *out = w.get();
   g->ws[key] = std::move(w);
   return 1;
 }
+
+// Marks the end of a call's use of its workspace (every return path of compute()).
+struct WorkspaceLease {
+  DenGraph* g;
+  Workspace* w;
+  ~WorkspaceLease() {
+    std::lock_guard<std::mutex> lock(g->mu);
+    w->in_use--;
+  }
+};
 
 // Resolve and clear the profiling events of every workspace of this graph.
 void harvest_profile(DenGraph* g) {
@@ -1050,6 +1083,7 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   if (!get_den_device(g, device, &dd)) return 0;
   if (!get_sup_device(sup, device, &sd)) return 0;
   if (!get_workspace(g, device, (void*)stream, &ws)) return 0;
+  WorkspaceLease lease{g, ws};
   const bool want_xent = xent != nullptr && xent_regularize != 0.f;
 
   if (!deriv) {  // objective only: derivatives go to scratch
