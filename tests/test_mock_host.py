@@ -1,0 +1,221 @@
+"""Host logic of libtorchain_b200 end to end on the CPU.
+
+tests/mock_cuda links the library's OWN object files against a host-memory stand-in for the CUDA runtime
+(device memory = host memory, copies = memcpy, kernel launches only recorded).  Nothing is computed -- the
+arithmetic is the GPU suite's business -- but everything the host does around the kernels runs for real:
+handle uploads, workspace management, the launch sequence and geometry, the chunk loops of the host-buffer
+entry.  The mock is test infrastructure; the product library never links it."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from torchain_b200 import _lib, synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MOCK_DIR = os.path.join(HERE, "mock_cuda")
+MOCK_LIB = os.path.join(MOCK_DIR, "libtorchain_b200_mock.so")
+
+
+class NumParams(ctypes.Structure):  # torchain_b200/csrc/chain_kernels.h, tb::NumParams
+    _fields_ = [("num_chains", ctypes.c_int)] + \
+               [(n, ctypes.c_void_p) for n in ("chain_level_off", "level_state_off", "chain_arc_off", "in_off", "in_arcs",
+                                               "out_off", "out_arcs", "final_cost", "arc_row", "arc_pdf", "arc_cost")] + \
+               [("B", ctypes.c_int), ("y", ctypes.c_void_p), ("yl", ctypes.c_int64 * 3)] + \
+               [(n, ctypes.c_void_p) for n in ("arc_val", "log_alpha", "log_beta", "arc_post", "chain_logprob")]
+
+
+@pytest.fixture(scope="module")
+def mock():
+    objs = os.path.join(os.path.dirname(_lib.LIB_PATH), "csrc", "chain_api.o")
+    if not os.path.exists(objs):
+        pytest.skip("library objects not built (run __graft_entry__.build())")
+    subprocess.run(["make", "-C", MOCK_DIR, "-s"], check=True)
+    lib = ctypes.CDLL(MOCK_LIB)
+    for name, (restype, argtypes) in _lib.SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = restype, argtypes
+    lib.mock_launch_name.restype = ctypes.c_char_p
+    lib.mock_launch_param0.restype = ctypes.c_void_p
+    lib.mock_stat.restype = ctypes.c_long
+    lib.mock_set_param_capture.argtypes = [ctypes.c_size_t]
+    lib.mock_set_param_capture(ctypes.sizeof(NumParams))
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _handles(lib, den, sup):
+    keep = [np.ascontiguousarray(x) for x in (den.src, den.dst, den.ilabel, den.cost, den.final_cost, sup.arc_begin,
+                                              sup.arc_dst, sup.arc_label, sup.arc_cost, sup.final_cost)]
+    g = lib.torchain_denominator_graph_from_arrays(den.num_states, den.num_arcs, _p(keep[0]), _p(keep[1]), _p(keep[2]),
+                                                   _p(keep[3]), den.start, _p(keep[4]), den.num_pdfs)
+    s = lib.torchain_supervision_from_arrays(sup.weight, sup.num_sequences, sup.frames_per_sequence, sup.label_dim,
+                                             sup.num_states, _p(keep[5]), _p(keep[6]), _p(keep[7]), _p(keep[8]),
+                                             _p(keep[9]))
+    assert g and s, lib.torchain_last_error()
+    return g, s
+
+
+def _compute(lib, g, s, y, stream=None):
+    d = np.full_like(y, np.nan)
+    res = np.full(3, np.nan, dtype=np.float32)
+    ok = lib.my_lib_ComputeChainObjfAndDeriv(g, s, _p(y), y.shape[0], y.shape[1], y.shape[1], _p(res), _p(d), y.shape[1],
+                                             None, 0, 5e-5, 0.1, 0.0, 0, stream)
+    assert ok == 1, lib.torchain_last_error()
+    return res, d
+
+
+def _launches(lib):
+    out = []
+    for i in range(lib.mock_launch_count()):
+        grid, block, coop, smem = ctypes.c_uint(), ctypes.c_uint(), ctypes.c_int(), ctypes.c_ulonglong()
+        lib.mock_launch_info(i, ctypes.byref(grid), ctypes.byref(block), ctypes.byref(coop), None, ctypes.byref(smem))
+        out.append((lib.mock_launch_name(i).decode(), grid.value, block.value, coop.value, smem.value))
+    return out
+
+
+def _kernel(name):
+    for k in ("num_fb_kernel", "den_forward_kernel", "den_backward_kernel", "final_scalars_kernel", "final_deriv_kernel",
+              "zero_kernel"):
+        if k in name:
+            return k
+    return name
+
+
+@pytest.mark.parametrize("B,subs,passes", [(16, 4, [1]), (64, 2, [1]), (128, 1, [1]), (200, 1, [2]), (300, 1, [2, 1])])
+def test_launch_sequence_and_geometry(mock, B, subs, passes):
+    """One call = numerator (side stream) + one forward / backward launch pair per pass of <= 256 sequences +
+    the two final kernels; the denominator launches are cooperative, one CTA of 512 threads per SM, and their
+    template instantiation follows the batch geometry (lane groups per warp, one or two contexts)."""
+    den = synth.make_den_fst(1, 300, 40, mean_deg=4.0)
+    T = 5
+    sup = synth.make_supervision(2, den, B, T, num_paths=2, weight=1.0)
+    y = synth.make_nnet_output(3, B, T, den.num_pdfs).astype(np.float32)
+    g, s = _handles(mock, den, sup)
+    try:
+        mock.mock_reset_launches()
+        n0 = mock.torchain_kernel_launch_count()
+        _compute(mock, g, s, y)
+        ls = _launches(mock)
+        assert mock.torchain_kernel_launch_count() - n0 == len(ls) == 3 + 2 * len(passes)
+        assert [_kernel(l[0]) for l in ls] == (["num_fb_kernel"] + ["den_forward_kernel", "den_backward_kernel"] * len(passes) +
+                                               ["final_scalars_kernel", "final_deriv_kernel"])
+        den_ls = [l for l in ls if "den_" in l[0]]
+        for (name, grid, block, coop, smem), nctx in zip(den_ls, [c for c in passes for _ in range(2)]):
+            assert (grid, block, coop) == (148, 512, 1)
+            sub_of_pass = subs if len(passes) == 1 else (1 if nctx == 2 else 2)   # second pass of B=300: 44 -> BP 64
+            assert "kernelILi%dELb1ELb0ELi%dEE" % (sub_of_pass, nctx) in name     # <SUBS, STAGED, SPLIT, NCTX>
+            assert 0 < smem <= 227 * 1024
+    finally:
+        mock.my_lib_supervision_free(s)
+        mock.my_lib_denominator_graph_free(g)
+
+
+def test_supervision_device_image_is_one_allocation_with_the_right_contents(mock):
+    den = synth.make_den_fst(4, 80, 20, mean_deg=3.0)
+    B, T = 1, 9      # one sequence: the device arcs are the FST's arcs one to one
+    sup = synth.make_supervision(5, den, B, T, num_paths=3, weight=1.0)
+    y = synth.make_nnet_output(6, B, T, den.num_pdfs).astype(np.float32)
+    g, s = _handles(mock, den, sup)
+    try:
+        _compute(mock, g, s, y)                      # builds the graph's device state and the workspace
+        s2 = _handles(mock, den, sup)[1]
+        m0, f0 = mock.mock_stat(0), mock.mock_stat(1)
+        mock.mock_reset_launches()
+        _compute(mock, g, s2, y)                     # only the new supervision has to be uploaded
+        assert mock.mock_stat(0) - m0 == 1           # ONE allocation ...
+        names = [mock.mock_launch_name(i).decode() for i in range(mock.mock_launch_count())]
+        i_num = [i for i, n in enumerate(names) if "num_fb_kernel" in n][0]
+        npar = NumParams.from_address(mock.mock_launch_param0(i_num))
+        A, S = sup.num_arcs, sup.num_states
+        arr = lambda ptr, ct, n: np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ct)), shape=(n,)).copy()
+        assert npar.num_chains == 1 and npar.B == B
+        assert list(arr(npar.chain_arc_off, ctypes.c_int, 2)) == [0, A]
+        in_off, out_off = arr(npar.in_off, ctypes.c_int, S + 1), arr(npar.out_off, ctypes.c_int, S + 1)
+        assert in_off[0] == 0 and in_off[-1] == A and (np.diff(in_off) >= 0).all()
+        assert np.array_equal(out_off, sup.arc_begin)
+        # time of an arc's source state = frame (one sequence): row = frame * B + 0
+        time = np.zeros(S, dtype=np.int64)
+        for st in range(S):
+            for a in range(sup.arc_begin[st], sup.arc_begin[st + 1]):
+                time[sup.arc_dst[a]] = time[st] + 1
+        src = np.repeat(np.arange(S), np.diff(sup.arc_begin))
+        assert np.array_equal(arr(npar.arc_row, ctypes.c_int, A), time[src] * B)
+        assert np.array_equal(arr(npar.arc_pdf, ctypes.c_int, A), sup.arc_label - 1)
+        assert np.array_equal(arr(npar.arc_cost, ctypes.c_float, A), sup.arc_cost)
+        assert np.array_equal(arr(npar.final_cost, ctypes.c_float, S), sup.final_cost)
+        out_arcs = arr(npar.out_arcs, ctypes.c_int, 2 * A).reshape(A, 2)
+        assert np.array_equal(out_arcs[:, 0], sup.arc_dst) and np.array_equal(out_arcs[:, 1], np.arange(A))
+        in_arcs = arr(npar.in_arcs, ctypes.c_int, 2 * A).reshape(A, 2)
+        assert np.array_equal(np.sort(in_arcs[:, 1]), np.arange(A)) and np.array_equal(in_arcs[:, 0], src[in_arcs[:, 1]])
+        assert np.array_equal(arr(npar.y, ctypes.c_float, y.size).reshape(y.shape), y)
+        mock.my_lib_supervision_free(s2)
+        assert mock.mock_stat(1) - f0 == 1           # ... and ONE free
+    finally:
+        mock.my_lib_supervision_free(s)
+        mock.my_lib_denominator_graph_free(g)
+
+
+def test_workspaces_are_capped_per_device(mock):
+    """A caller hopping between streams (torch pools 32 per device) keeps at most 4 workspaces alive."""
+    den = synth.make_den_fst(7, 120, 16, mean_deg=3.0)
+    B, T = 8, 6
+    sup = synth.make_supervision(8, den, B, T, num_paths=2, weight=1.0)
+    y = synth.make_nnet_output(9, B, T, den.num_pdfs).astype(np.float32)
+    g, s = _handles(mock, den, sup)
+    try:
+        streams0 = mock.mock_stat(5)
+        live = []
+        for k in range(1, 13):
+            _compute(mock, g, s, y, ctypes.c_void_p(0x1000 * k))   # stream handles are opaque tokens to the mock
+            live.append((mock.mock_stat(5) - streams0, mock.mock_stat(2)))
+        assert [n for n, _ in live] == [1, 2, 3, 4] + [4] * 8       # one side stream per workspace
+        assert len({b for _, b in live[3:]}) == 1                   # device memory stops growing
+        _compute(mock, g, s, y, ctypes.c_void_p(0x1000 * 12))        # the most recent one is still there
+        assert mock.mock_stat(5) - streams0 == 4
+    finally:
+        mock.my_lib_supervision_free(s)
+        mock.my_lib_denominator_graph_free(g)
+    assert mock.mock_stat(5) == streams0
+
+
+@pytest.mark.parametrize("env", [{}, {"TORCHAIN_HOST_COPY_STREAMS": "2"}, {"TORCHAIN_HOST_FLAG_MODE": "memset"},
+                                 {"TORCHAIN_HOST_FLAG_MODE": "write"}, {"TORCHAIN_HOST_UNIFORM_CHUNKS": "1"},
+                                 {"TORCHAIN_HOST_NO_PIPELINED_OUT": "1"}],
+                         ids=lambda e: "-".join(e.values()) or "default")
+@pytest.mark.parametrize("T,pad", [(1, 0), (3, 0), (17, 4), (50, 0), (77, 3)])
+def test_host_buffer_entry_moves_every_row_once(mock, monkeypatch, env, T, pad):
+    """Chunk loops of the host-buffer entry for every schedule and experiment mode: all of nnet_output reaches
+    the device buffer, every row of the derivative (zeros here: no kernel ran) reaches the host buffer, the
+    padding of pitched buffers is left alone."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    den = synth.make_den_fst(10, 60, 12, mean_deg=3.0)
+    B = 5
+    sup = synth.make_supervision(11, den, B, T, num_paths=2, weight=1.0)
+    y = synth.make_nnet_output(12, B, T, den.num_pdfs).astype(np.float32)
+    rows, cols = y.shape
+    yp = np.full((rows, cols + pad), 7.0, dtype=np.float32)
+    yp[:, :cols] = y
+    dp = np.full((rows, cols + pad), np.nan, dtype=np.float32)
+    res = np.full(3, np.nan, dtype=np.float32)
+    g, s = _handles(mock, den, sup)
+    try:
+        mock.mock_reset_launches()
+        ok = mock.torchain_ComputeChainObjfAndDeriv_host(g, s, _p(yp), rows, cols, cols + pad, _p(res), _p(dp),
+                                                         cols + pad, None, 0, 5e-5, 0.1, 0.0, 0)
+        assert ok == 1, mock.torchain_last_error()
+        assert np.all(dp[:, :cols] == 0.0) and np.isnan(dp[:, cols:]).all()
+        assert np.all(res == 0.0)
+        names = [mock.mock_launch_name(i).decode() for i in range(mock.mock_launch_count())]
+        npar = NumParams.from_address(mock.mock_launch_param0([i for i, n in enumerate(names) if "num_fb_kernel" in n][0]))
+        y_dev = np.ctypeslib.as_array(ctypes.cast(npar.y, ctypes.POINTER(ctypes.c_float)), shape=(rows, cols))
+        assert np.array_equal(y_dev, y)
+    finally:
+        mock.my_lib_supervision_free(s)
+        mock.my_lib_denominator_graph_free(g)
