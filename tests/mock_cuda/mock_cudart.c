@@ -143,8 +143,23 @@ cudaError_t cudaMalloc(void** p, size_t n) {
   return cudaSuccess;
 }
 cudaError_t cudaFree(void* p) { if (p) { g_live_bytes -= (long)tracked_free(p); g_frees++; } return cudaSuccess; }
-cudaError_t cudaHostAlloc(void** p, size_t n, unsigned flags) { (void)flags; *p = tracked_alloc(n ? n : 1); g_host_allocs++; return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
-cudaError_t cudaFreeHost(void* p) { if (p) tracked_free(p); return cudaSuccess; }
+/* The host-buffer entry polls a mapped pinned counter that the backward kernel advances.  With
+ * mock_set_auto_progress(limit) every cudaStreamQuery stands in for one frame of kernel progress: it bumps the
+ * most recently allocated MAPPED pinned word and answers "not ready" until the counter has reached `limit`. */
+static volatile unsigned* g_mapped_word = NULL;
+static unsigned g_auto_progress = 0;
+void mock_set_auto_progress(unsigned limit) { g_auto_progress = limit; }
+cudaError_t cudaHostAlloc(void** p, size_t n, unsigned flags) {
+  *p = tracked_alloc(n ? n : 1);
+  g_host_allocs++;
+  if (*p && (flags & 2u) && n == sizeof(unsigned)) g_mapped_word = (volatile unsigned*)*p;
+  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+cudaError_t cudaFreeHost(void* p) {
+  if (p == (void*)g_mapped_word) g_mapped_word = NULL;
+  if (p) tracked_free(p);
+  return cudaSuccess;
+}
 cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned flags) { (void)flags; *d = h; return cudaSuccess; }
 cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int kind) { (void)kind; memmove(d, s, n); g_memcpys++; return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int kind, cudaStream_t st) { (void)st; return cudaMemcpy(d, s, n, kind); }
@@ -160,7 +175,14 @@ cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st) { (void)s
 /* ---- streams and events: tokens; everything "completes" at once ---- */
 cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags) { (void)flags; *s = malloc(8); g_streams_live++; return cudaSuccess; }
 cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); g_streams_live--; return cudaSuccess; }
-cudaError_t cudaStreamQuery(cudaStream_t s) { (void)s; return cudaSuccess; }
+cudaError_t cudaStreamQuery(cudaStream_t s) {
+  (void)s;
+  if (g_auto_progress && g_mapped_word && *g_mapped_word < g_auto_progress) {
+    (*g_mapped_word)++;
+    return 600; /* cudaErrorNotReady */
+  }
+  return cudaSuccess;
+}
 cudaError_t cudaStreamSynchronize(cudaStream_t s) { (void)s; return cudaSuccess; }
 cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned flags) { (void)s; (void)e; (void)flags; return cudaSuccess; }
 cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = malloc(8); return cudaSuccess; }

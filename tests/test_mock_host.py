@@ -219,3 +219,42 @@ def test_host_buffer_entry_moves_every_row_once(mock, monkeypatch, env, T, pad):
     finally:
         mock.my_lib_supervision_free(s)
         mock.my_lib_denominator_graph_free(g)
+
+
+def test_host_buffer_entry_redelivers_early_chunks_when_the_guard_tripped(mock):
+    """With the mock standing in for the backward kernel's progress counter (one frame per stream query, up to
+    the T-2 the kernel publishes) the chunks of frames >= 2 leave early; the mock's final pass reports
+    ok = 0 (zeroed results), i.e. a tripped numeric guard, so exactly those chunks must be copied a second time."""
+    den = synth.make_den_fst(10, 60, 12, mean_deg=3.0)
+    B, T = 5, 50
+    sup = synth.make_supervision(11, den, B, T, num_paths=2, weight=1.0)
+    y = synth.make_nnet_output(12, B, T, den.num_pdfs).astype(np.float32)
+    rows, cols = y.shape
+    res = np.zeros(3, dtype=np.float32)
+    g, s = _handles(mock, den, sup)
+    n = mock.torchain_host_chunk_bounds(T, None, 0)
+    bounds = (ctypes.c_int * n)()
+    mock.torchain_host_chunk_bounds(T, bounds, n)
+    early = sum(1 for k in range(n - 1) if T - bounds[k] <= T - 2)   # chunks whose frames are all >= 2
+
+    def call():
+        d = np.full_like(y, np.nan)
+        c0 = mock.mock_stat(3)
+        ok = mock.torchain_ComputeChainObjfAndDeriv_host(g, s, _p(y), rows, cols, cols, _p(res), _p(d), cols, None, 0,
+                                                         5e-5, 0.1, 0.0, 0)
+        assert ok == 1, mock.torchain_last_error()
+        assert np.all(d == 0.0)
+        return mock.mock_stat(3) - c0
+
+    try:
+        call()                       # one-off uploads
+        plain = call()               # the stream "finishes" at once: nothing leaves early
+        mock.mock_set_auto_progress(T - 2)
+        try:
+            piped = call()
+        finally:
+            mock.mock_set_auto_progress(0)
+        assert early == 15 and piped - plain == early
+    finally:
+        mock.my_lib_supervision_free(s)
+        mock.my_lib_denominator_graph_free(g)
