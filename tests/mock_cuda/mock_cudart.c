@@ -31,7 +31,8 @@ typedef struct {
   unsigned char param0[PARAM_BYTES];
 } MockLaunch;
 static MockLaunch g_launches[MAX_LAUNCHES];
-static int g_nlaunches = 0;
+static int g_nlaunches = 0, g_nlaunches_total = 0;
+static __thread int g_last_slot = 0;
 static long g_mallocs = 0, g_frees = 0, g_live_bytes = 0, g_memcpys = 0, g_host_allocs = 0;
 static int g_device = 0, g_device_count = 1;
 static long g_streams_live = 0;
@@ -51,7 +52,7 @@ static size_t tracked_free(void* q) {
 }
 
 int mock_launch_count(void) { return g_nlaunches; }
-void mock_reset_launches(void) { g_nlaunches = 0; }
+void mock_reset_launches(void) { g_nlaunches = 0; g_nlaunches_total = 0; }
 const char* mock_launch_name(int i) { return (i >= 0 && i < g_nlaunches && g_launches[i].name) ? g_launches[i].name : ""; }
 int mock_launch_info(int i, unsigned* grid, unsigned* block, int* cooperative, void** stream, unsigned long long* smem) {
   if (i < 0 || i >= g_nlaunches) return 0;
@@ -89,9 +90,9 @@ void __cudaRegisterFunction(void** h, const char* hostFun, char* deviceFun, cons
     g_nfuncs++;
   }
 }
-static dim3 g_cfg_grid, g_cfg_block;
-static size_t g_cfg_smem;
-static void* g_cfg_stream;
+static __thread dim3 g_cfg_grid, g_cfg_block;
+static __thread size_t g_cfg_smem;
+static __thread void* g_cfg_stream;
 unsigned __cudaPushCallConfiguration(dim3 grid, dim3 block, size_t smem, void* stream) {
   g_cfg_grid = grid; g_cfg_block = block; g_cfg_smem = smem; g_cfg_stream = stream;
   return 0;
@@ -101,8 +102,13 @@ cudaError_t __cudaPopCallConfiguration(dim3* grid, dim3* block, size_t* smem, vo
   return cudaSuccess;
 }
 static cudaError_t record_launch(const void* func, dim3 grid, dim3 block, void** args, size_t smem, void* stream, int coop) {
-  if (g_nlaunches >= MAX_LAUNCHES) return cudaSuccess;
-  MockLaunch* l = &g_launches[g_nlaunches++];
+  /* launches may come from several host threads: reserve a slot atomically; when the log is full the
+   * last slot is overwritten (the count keeps running, readers clamp) */
+  int slot = __atomic_fetch_add(&g_nlaunches_total, 1, __ATOMIC_RELAXED);
+  if (slot >= MAX_LAUNCHES) slot = MAX_LAUNCHES - 1;
+  else __atomic_fetch_add(&g_nlaunches, 1, __ATOMIC_RELAXED);
+  MockLaunch* l = &g_launches[slot];
+  g_last_slot = slot;
   l->name = "?";
   for (int i = 0; i < g_nfuncs; i++)
     if (g_funcs[i].host_fun == func) l->name = g_funcs[i].name;
@@ -117,12 +123,12 @@ static size_t g_param_bytes = 0;
 void mock_set_param_capture(size_t nbytes) { g_param_bytes = nbytes > PARAM_BYTES ? PARAM_BYTES : nbytes; }
 cudaError_t cudaLaunchKernel(const void* func, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t stream) {
   cudaError_t e = record_launch(func, grid, block, args, smem, stream, 0);
-  if (g_param_bytes && args && args[0] && g_nlaunches > 0) memcpy(g_launches[g_nlaunches - 1].param0, args[0], g_param_bytes);
+  if (g_param_bytes && args && args[0]) memcpy(g_launches[g_last_slot].param0, args[0], g_param_bytes);
   return e;
 }
 cudaError_t cudaLaunchCooperativeKernel(const void* func, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t stream) {
   cudaError_t e = record_launch(func, grid, block, args, smem, stream, 1);
-  if (g_param_bytes && args && args[0] && g_nlaunches > 0) memcpy(g_launches[g_nlaunches - 1].param0, args[0], g_param_bytes);
+  if (g_param_bytes && args && args[0]) memcpy(g_launches[g_last_slot].param0, args[0], g_param_bytes);
   return e;
 }
 cudaError_t cudaFuncSetAttribute(const void* f, int attr, int value) { (void)f; (void)attr; (void)value; return cudaSuccess; }
@@ -139,10 +145,10 @@ cudaError_t cudaGetLastError(void) { return cudaSuccess; }
 cudaError_t cudaMalloc(void** p, size_t n) {
   *p = tracked_alloc(n ? n : 1);
   if (!*p) return cudaErrorMemoryAllocation;
-  g_mallocs++; g_live_bytes += (long)n;
+  __atomic_fetch_add(&g_mallocs, 1, __ATOMIC_RELAXED); __atomic_fetch_add(&g_live_bytes, (long)n, __ATOMIC_RELAXED);
   return cudaSuccess;
 }
-cudaError_t cudaFree(void* p) { if (p) { g_live_bytes -= (long)tracked_free(p); g_frees++; } return cudaSuccess; }
+cudaError_t cudaFree(void* p) { if (p) { __atomic_fetch_sub(&g_live_bytes, (long)tracked_free(p), __ATOMIC_RELAXED); __atomic_fetch_add(&g_frees, 1, __ATOMIC_RELAXED); } return cudaSuccess; }
 /* The host-buffer entry polls a mapped pinned counter that the backward kernel advances.  With
  * mock_set_auto_progress(limit) every cudaStreamQuery stands in for one frame of kernel progress: it bumps the
  * most recently allocated MAPPED pinned word and answers "not ready" until the counter has reached `limit`. */
@@ -161,7 +167,7 @@ cudaError_t cudaFreeHost(void* p) {
   return cudaSuccess;
 }
 cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned flags) { (void)flags; *d = h; return cudaSuccess; }
-cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int kind) { (void)kind; memmove(d, s, n); g_memcpys++; return cudaSuccess; }
+cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int kind) { (void)kind; memmove(d, s, n); __atomic_fetch_add(&g_memcpys, 1, __ATOMIC_RELAXED); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int kind, cudaStream_t st) { (void)st; return cudaMemcpy(d, s, n, kind); }
 cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, size_t sp, size_t w, size_t h, int kind, cudaStream_t st) {
   (void)kind; (void)st;
@@ -173,8 +179,8 @@ cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaS
 cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t st) { (void)st; memset(d, v, n); return cudaSuccess; }
 
 /* ---- streams and events: tokens; everything "completes" at once ---- */
-cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags) { (void)flags; *s = malloc(8); g_streams_live++; return cudaSuccess; }
-cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); g_streams_live--; return cudaSuccess; }
+cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned flags) { (void)flags; *s = malloc(8); __atomic_fetch_add(&g_streams_live, 1, __ATOMIC_RELAXED); return cudaSuccess; }
+cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); __atomic_fetch_sub(&g_streams_live, 1, __ATOMIC_RELAXED); return cudaSuccess; }
 cudaError_t cudaStreamQuery(cudaStream_t s) {
   (void)s;
   if (g_auto_progress && g_mapped_word && *g_mapped_word < g_auto_progress) {

@@ -258,3 +258,55 @@ def test_host_buffer_entry_redelivers_early_chunks_when_the_guard_tripped(mock):
     finally:
         mock.my_lib_supervision_free(s)
         mock.my_lib_denominator_graph_free(g)
+
+
+def test_no_device_memory_or_stream_outlives_the_handles(mock):
+    den = synth.make_den_fst(13, 150, 24, mean_deg=4.0)
+    B, T = 40, 7
+    sup = synth.make_supervision(14, den, B, T, num_paths=2, weight=1.0)
+    y = synth.make_nnet_output(15, B, T, den.num_pdfs).astype(np.float32)
+    live0, streams0, balance0 = mock.mock_stat(2), mock.mock_stat(5), mock.mock_stat(0) - mock.mock_stat(1)
+    g, s = _handles(mock, den, sup)
+    for k in range(3):
+        _compute(mock, g, s, y, ctypes.c_void_p(0x2000 * (1 + k % 2)))
+    assert mock.mock_stat(2) > live0
+    mock.my_lib_supervision_free(s)
+    mock.my_lib_denominator_graph_free(g)
+    assert mock.mock_stat(2) == live0 and mock.mock_stat(5) == streams0
+    assert mock.mock_stat(0) - mock.mock_stat(1) == balance0
+
+
+def test_host_threads_share_the_handles(mock):
+    """The reference drives several GPUs / streams from Python threads (parallel_train.py:55-75); ctypes drops
+    the GIL, so these calls really run concurrently: shared den graph, own stream, a new supervision per call."""
+    import threading
+    den = synth.make_den_fst(16, 200, 30, mean_deg=4.0)
+    B, T = 12, 6
+    sup = synth.make_supervision(17, den, B, T, num_paths=2, weight=1.0)
+    y = synth.make_nnet_output(18, B, T, den.num_pdfs).astype(np.float32)
+    live0, streams0 = mock.mock_stat(2), mock.mock_stat(5)
+    g, s0 = _handles(mock, den, sup)
+    n0 = mock.torchain_kernel_launch_count()
+    errors = []
+
+    def worker(tid):
+        try:
+            for it in range(40):
+                s = _handles(mock, den, sup)[1] if it % 2 else None
+                _compute(mock, g, s or s0, y, ctypes.c_void_p(0x3000 * (1 + tid)))
+                if s:
+                    mock.my_lib_supervision_free(s)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert mock.torchain_kernel_launch_count() - n0 == 6 * 40 * 5
+    assert mock.mock_stat(5) - streams0 <= 6      # 6 streams in use at once: never more workspaces than callers
+    mock.my_lib_supervision_free(s0)
+    mock.my_lib_denominator_graph_free(g)
+    assert mock.mock_stat(2) == live0 and mock.mock_stat(5) == streams0
