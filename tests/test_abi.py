@@ -417,6 +417,6 @@ int main(void) {
     exe = str(tmp_path / "host")
     libdir = os.path.dirname(_lib.LIB_PATH)
     subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.dirname(HEADER), str(src),
-                    "-o", exe, "-L", libdir, "-l:libtorchain_b200.so", "-Wl,-rpath," + libdir], check=True)
+                    "-o", exe, "-L", libdir, "-l:" + os.path.basename(_lib.LIB_PATH), "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
     assert out.startswith("ok ")

@@ -32,8 +32,11 @@ def mock():
     objs = os.path.join(os.path.dirname(_lib.LIB_PATH), "csrc", "chain_api.o")
     if not os.path.exists(objs):
         pytest.skip("library objects not built (run __graft_entry__.build())")
-    subprocess.run(["make", "-C", MOCK_DIR, "-s"], check=True)
-    lib = ctypes.CDLL(MOCK_LIB)
+    path = os.environ.get("TORCHAIN_MOCK_LIB")   # e.g. a sanitizer build of the host code
+    if not path:
+        subprocess.run(["make", "-C", MOCK_DIR, "-s"], check=True)
+        path = MOCK_LIB
+    lib = ctypes.CDLL(path)
     for name, (restype, argtypes) in _lib.SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = restype, argtypes
