@@ -34,7 +34,8 @@ static MockLaunch g_launches[MAX_LAUNCHES];
 static int g_nlaunches = 0, g_nlaunches_total = 0;
 static __thread int g_last_slot = 0;
 static long g_mallocs = 0, g_frees = 0, g_live_bytes = 0, g_memcpys = 0, g_host_allocs = 0;
-static int g_device = 0, g_device_count = 1;
+static __thread int g_device = 0; /* the current device is per host thread, as in CUDA */
+static int g_device_count = 1;
 static long g_streams_live = 0;
 
 /* every allocation carries its size in a 256-byte header so that live bytes can be tracked */
