@@ -39,10 +39,13 @@ static int g_device_count = 1;
 static long g_streams_live = 0;
 
 /* every allocation carries its size in a 256-byte header so that live bytes can be tracked */
+static int g_fill = 0; /* byte every new allocation is filled with (device memory is not zeroed in real life either) */
+void mock_set_fill(int byte) { g_fill = byte; }
 static void* tracked_alloc(size_t n) {
   unsigned char* p = (unsigned char*)calloc(1, n + 256);
   if (!p) return NULL;
   *(size_t*)p = n;
+  if (g_fill) memset(p + 256, g_fill, n);
   return p + 256;
 }
 static size_t tracked_free(void* q) {

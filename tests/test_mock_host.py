@@ -313,3 +313,66 @@ def test_host_threads_share_the_handles(mock):
     mock.my_lib_supervision_free(s0)
     mock.my_lib_denominator_graph_free(g)
     assert mock.mock_stat(2) == live0 and mock.mock_stat(5) == streams0
+
+
+def test_two_devices_in_one_process(mock):
+    """parallel_train.py drives several GPUs from one process: the den-graph handle keeps one partition upload
+    and one workspace per device, and a call leaves the caller's current device as it found it."""
+    den = synth.make_den_fst(19, 100, 16, mean_deg=3.0)
+    B, T = 8, 5
+    sup = synth.make_supervision(20, den, B, T, num_paths=2, weight=1.0)
+    y = synth.make_nnet_output(21, B, T, den.num_pdfs).astype(np.float32)
+    mock.mock_set_device_count(2)
+    g, s = _handles(mock, den, sup)
+    try:
+        d = np.empty_like(y)
+        res = np.zeros(3, dtype=np.float32)
+        grown = []
+        for dev in (0, 1, 1, 0):
+            m0 = mock.mock_stat(0)
+            ok = mock.my_lib_ComputeChainObjfAndDeriv(g, s, _p(y), y.shape[0], y.shape[1], y.shape[1], _p(res), _p(d),
+                                                      y.shape[1], None, 0, 0.0, 0.1, 0.0, dev, None)
+            assert ok == 1, mock.torchain_last_error()
+            grown.append(mock.mock_stat(0) - m0)
+            cur = ctypes.c_int(-1)
+            mock.cudaGetDevice(ctypes.byref(cur))
+            assert cur.value == 0
+        assert grown[0] > 0 and grown[1] > 0 and grown[2] == 0 and grown[3] == 0   # uploads once per device
+        assert mock.my_lib_ComputeChainObjfAndDeriv(g, s, _p(y), y.shape[0], y.shape[1], y.shape[1], _p(res), _p(d),
+                                                    y.shape[1], None, 0, 0.0, 0.1, 0.0, 2, None) == 0
+        assert b"device" in mock.torchain_last_error()
+    finally:
+        mock.mock_set_device_count(1)
+        mock.my_lib_supervision_free(s)
+        mock.my_lib_denominator_graph_free(g)
+
+
+def test_partition_autotuner_redeals_and_keeps_old_generations(mock):
+    """Synchronising full-width calls feed the partition autotuner (per-warp busy counters -> speeds -> LPT).
+    With the mock handing out pre-filled "device" memory the counters read as large equal numbers, so every one
+    of the three calibration rounds builds and uploads a new partition generation; after that the partition is
+    frozen (no further allocations), and every launch still gets a valid geometry."""
+    den = synth.make_den_fst(22, 3000, 64, mean_deg=6.0)
+    B, T = 128, 3
+    sup = synth.make_supervision(23, den, B, T, num_paths=2, weight=1.0)
+    y = synth.make_nnet_output(24, B, T, den.num_pdfs).astype(np.float32)
+    live0 = mock.mock_stat(2)
+    mock.mock_set_fill(1)
+    g, s = _handles(mock, den, sup)
+    try:
+        grown = []
+        for _ in range(6):
+            m0 = mock.mock_stat(0)
+            mock.mock_reset_launches()
+            _compute(mock, g, s, y)
+            grown.append(mock.mock_stat(0) - m0)
+            for name, grid, block, coop, smem in _launches(mock):
+                if "den_" in name:
+                    assert (grid, block, coop) == (148, 512, 1) and 0 < smem <= 227 * 1024
+        assert grown[0] > grown[1] > 0 and grown[1] == grown[2] == 12   # one generation = 2 directions x 6 arrays
+        assert grown[3:] == [0, 0, 0]
+    finally:
+        mock.mock_set_fill(0)
+        mock.my_lib_supervision_free(s)
+        mock.my_lib_denominator_graph_free(g)
+    assert mock.mock_stat(2) == live0
