@@ -852,6 +852,9 @@ __device__ __forceinline__ void den_chain_body(const DenBatch& batch) {
     for (int ci = 0; ci < NCTX; ci++) wait(ci);
     trace_frame_end(0);
     stamp();
+    // step 0 is complete everywhere: only frame 0 is still to be flushed (below), so the host may copy frame 1 out
+    if (p0.deriv_progress && blockIdx.x == 0 && threadIdx.x == 0)
+      *reinterpret_cast<volatile unsigned*>(p0.deriv_progress) = (unsigned)(T - 1);
 
     // ---- epilogue: frame 0's derivative rows, sanity sums
     if (is_aux) {
