@@ -258,6 +258,12 @@ def test_host_buffer_entry_redelivers_early_chunks_when_the_guard_tripped(mock):
         finally:
             mock.mock_set_auto_progress(0)
         assert early == 15 and piped - plain == early
+        # ... and T-1 after the kernel's last grid barrier: the single-frame chunk of frame 1 leaves early too
+        mock.mock_set_auto_progress(T - 1)
+        try:
+            assert call() - plain == early + 1 == n - 2
+        finally:
+            mock.mock_set_auto_progress(0)
     finally:
         mock.my_lib_supervision_free(s)
         mock.my_lib_denominator_graph_free(g)
