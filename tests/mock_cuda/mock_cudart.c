@@ -125,14 +125,29 @@ static cudaError_t record_launch(const void* func, dim3 grid, dim3 block, void**
  * test-side helper mock_capture_param (below) through a size the test supplies. */
 static size_t g_param_bytes = 0;
 void mock_set_param_capture(size_t nbytes) { g_param_bytes = nbytes > PARAM_BYTES ? PARAM_BYTES : nbytes; }
+/* per-kernel override: kernels whose name contains `pattern` capture `nbytes` (their parameter struct's size) */
+#define MAX_RULES 8
+static struct { char pattern[64]; size_t nbytes; } g_rules[MAX_RULES];
+static int g_nrules = 0;
+void mock_set_param_capture_for(const char* pattern, size_t nbytes) {
+  if (g_nrules >= MAX_RULES) return;
+  strncpy(g_rules[g_nrules].pattern, pattern, 63);
+  g_rules[g_nrules].nbytes = nbytes > PARAM_BYTES ? PARAM_BYTES : nbytes;
+  g_nrules++;
+}
+static size_t capture_bytes(const char* name) {
+  for (int i = 0; i < g_nrules; i++)
+    if (name && strstr(name, g_rules[i].pattern)) return g_rules[i].nbytes;
+  return g_param_bytes;
+}
 cudaError_t cudaLaunchKernel(const void* func, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t stream) {
   cudaError_t e = record_launch(func, grid, block, args, smem, stream, 0);
-  if (g_param_bytes && args && args[0]) memcpy(g_launches[g_last_slot].param0, args[0], g_param_bytes);
+  if (args && args[0] && capture_bytes(g_launches[g_last_slot].name)) memcpy(g_launches[g_last_slot].param0, args[0], capture_bytes(g_launches[g_last_slot].name));
   return e;
 }
 cudaError_t cudaLaunchCooperativeKernel(const void* func, dim3 grid, dim3 block, void** args, size_t smem, cudaStream_t stream) {
   cudaError_t e = record_launch(func, grid, block, args, smem, stream, 1);
-  if (g_param_bytes && args && args[0]) memcpy(g_launches[g_last_slot].param0, args[0], g_param_bytes);
+  if (args && args[0] && capture_bytes(g_launches[g_last_slot].name)) memcpy(g_launches[g_last_slot].param0, args[0], capture_bytes(g_launches[g_last_slot].name));
   return e;
 }
 cudaError_t cudaFuncSetAttribute(const void* f, int attr, int value) { (void)f; (void)attr; (void)value; return cudaSuccess; }

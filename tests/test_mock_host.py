@@ -27,6 +27,28 @@ class NumParams(ctypes.Structure):  # torchain_b200/csrc/chain_kernels.h, tb::Nu
                [(n, ctypes.c_void_p) for n in ("arc_val", "log_alpha", "log_beta", "arc_post", "chain_logprob")]
 
 
+class DenDir(ctypes.Structure):  # tb::DenDir
+    _fields_ = [(n, ctypes.c_void_p) for n in ("arcs", "tasks", "cta_arc_off", "cta_task_off", "warp_task_off",
+                                               "warp_arc_off")] + [("max_arcs_cta", ctypes.c_int), ("max_tasks_cta", ctypes.c_int)]
+
+
+class DenParams(ctypes.Structure):  # tb::DenParams
+    _fields_ = [("dir", DenDir * 2)] + \
+               [(n, ctypes.c_int) for n in ("N", "P", "B", "BP", "Btot", "seq0", "T")] + \
+               [("y", ctypes.c_void_p), ("yl", ctypes.c_int64 * 3), ("deriv", ctypes.c_void_p), ("dl", ctypes.c_int64 * 3)] + \
+               [(n, ctypes.c_void_p) for n in ("alpha", "beta", "etile", "gtile", "Ssum", "Bsum", "scalars", "barrier")] + \
+               [(n, ctypes.c_float) for n in ("leaky", "sum_pi", "scale_gamma", "scale_y")] + \
+               [(n, ctypes.c_int) for n in ("arcs_in_smem", "subs", "has_split")] + \
+               [(n, ctypes.c_void_p) for n in ("num_frame_off", "num_frame_arcs", "num_arc_pdf", "num_arc_seq",
+                                               "num_arc_post", "y_ready")] + \
+               [("y_chunk_frames", ctypes.c_int), ("deriv_progress", ctypes.c_void_p), ("debug_flags", ctypes.c_int)] + \
+               [(n, ctypes.c_void_p) for n in ("warp_busy", "cta_trace", "timeline")]
+
+
+class DenBatch(ctypes.Structure):  # tb::DenBatch
+    _fields_ = [("c", DenParams * 2), ("nctx", ctypes.c_int)]
+
+
 @pytest.fixture(scope="module")
 def mock():
     objs = os.path.join(os.path.dirname(_lib.LIB_PATH), "csrc", "chain_api.o")
@@ -44,7 +66,10 @@ def mock():
     lib.mock_launch_param0.restype = ctypes.c_void_p
     lib.mock_stat.restype = ctypes.c_long
     lib.mock_set_param_capture.argtypes = [ctypes.c_size_t]
-    lib.mock_set_param_capture(ctypes.sizeof(NumParams))
+    lib.mock_set_param_capture_for.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+    lib.mock_set_param_capture_for(b"num_fb_kernel", ctypes.sizeof(NumParams))
+    lib.mock_set_param_capture_for(b"den_forward_kernel", ctypes.sizeof(DenBatch))
+    lib.mock_set_param_capture_for(b"den_backward_kernel", ctypes.sizeof(DenBatch))
     return lib
 
 
@@ -382,3 +407,82 @@ def test_partition_autotuner_redeals_and_keeps_old_generations(mock):
         mock.my_lib_supervision_free(s)
         mock.my_lib_denominator_graph_free(g)
     assert mock.mock_stat(2) == live0
+
+
+def _den_batches(lib):
+    out = []
+    for i in range(lib.mock_launch_count()):
+        name = lib.mock_launch_name(i).decode()
+        if "den_forward_kernel" in name or "den_backward_kernel" in name:
+            out.append(("fwd" if "forward" in name else "bwd", DenBatch.from_buffer_copy(
+                ctypes.string_at(lib.mock_launch_param0(i), ctypes.sizeof(DenBatch)))))
+    return out
+
+
+def test_denominator_launch_parameters(mock):
+    """What the host hands the persistent kernels: geometry, sequence ranges of the contexts and passes,
+    per-context buffers, the scales that fold supervision.weight / l2 / the sign into the derivative."""
+    assert ctypes.sizeof(DenParams) == 400 and ctypes.sizeof(DenBatch) == 808   # mirrors of chain_kernels.h
+    den = synth.make_den_fst(25, 500, 48, mean_deg=5.0)
+    B, T, l2, leaky, w = 300, 4, 0.01, 0.2, 0.5
+    sup = synth.make_supervision(26, den, B, T, num_paths=2, weight=w)
+    y = synth.make_nnet_output(27, B, T, den.num_pdfs).astype(np.float32)
+    g, s = _handles(mock, den, sup)
+    try:
+        d = np.empty_like(y)
+        res = np.zeros(3, dtype=np.float32)
+        mock.mock_reset_launches()
+        ok = mock.torchain_ComputeChainObjfAndDeriv_ex(g, s, _p(y), y.shape[0], y.shape[1], y.shape[1], _p(res), None,
+                                                       _p(d), y.shape[1], None, 0, l2, leaky, 0.0, -1.0, 0, None)
+        assert ok == 1, mock.torchain_last_error()
+        batches = _den_batches(mock)
+        assert [k for k, _ in batches] == ["fwd", "bwd", "fwd", "bwd"]
+        (_, f1), (_, b1), (_, f2), (_, b2) = batches
+        assert bytes(f1) == bytes(b1) and bytes(f2) == bytes(b2)          # a launch pair shares its parameters
+        # pass 1: 256 sequences as two contexts of 128; pass 2: the remaining 44, one context padded to 64
+        assert f1.nctx == 2 and [(c.seq0, c.B, c.BP, c.subs) for c in f1.c] == [(0, 128, 128, 1), (128, 128, 128, 1)]
+        assert f2.nctx == 1 and (f2.c[0].seq0, f2.c[0].B, f2.c[0].BP, f2.c[0].subs) == (256, 44, 64, 2)
+        for bt in (f1, f2):
+            for c in bt.c[:bt.nctx]:
+                assert (c.N, c.P, c.Btot, c.T) == (den.num_states, den.num_pdfs, B, T)
+                assert c.y == y.ctypes.data and c.deriv == d.ctypes.data
+                assert list(c.yl) == [B * y.shape[1], y.shape[1], 1] and list(c.dl) == list(c.yl)
+                assert c.leaky == pytest.approx(leaky) and c.arcs_in_smem == 1 and c.has_split == 0
+                assert c.scale_gamma == pytest.approx(-1.0 * -w) and c.scale_y == pytest.approx(-1.0 * -w * l2)
+                assert c.y_ready is None and c.deriv_progress is None
+                for d_ in c.dir:
+                    assert d_.arcs and d_.tasks and d_.max_arcs_cta > 0 and d_.max_arcs_cta % 4 == 0
+        a, b = f1.c
+        for name in ("alpha", "beta", "etile", "gtile", "Ssum", "Bsum", "barrier"):
+            assert getattr(a, name) != getattr(b, name)                   # own buffers per context
+        assert a.scalars == b.scalars                                     # one set of sums per call
+        # alpha store of a context: (T + 1) x N x BP floats apart
+        assert b.alpha - a.alpha == 4 * (T + 1) * den.num_states * 128
+    finally:
+        mock.my_lib_supervision_free(s)
+        mock.my_lib_denominator_graph_free(g)
+
+
+def test_host_buffer_entry_launch_parameters(mock):
+    den = synth.make_den_fst(28, 80, 12, mean_deg=3.0)
+    B, T = 6, 20
+    sup = synth.make_supervision(29, den, B, T, num_paths=2, weight=1.0)
+    y = synth.make_nnet_output(30, B, T, den.num_pdfs).astype(np.float32)
+    d = np.empty_like(y)
+    res = np.zeros(3, dtype=np.float32)
+    g, s = _handles(mock, den, sup)
+    try:
+        mock.mock_reset_launches()
+        ok = mock.torchain_ComputeChainObjfAndDeriv_host(g, s, _p(y), y.shape[0], y.shape[1], y.shape[1], _p(res), _p(d),
+                                                         y.shape[1], None, 0, 0.0, 0.1, 0.0, 0)
+        assert ok == 1, mock.torchain_last_error()
+        (_, f), (_, b) = _den_batches(mock)
+        c = f.c[0]
+        assert c.y != y.ctypes.data and c.deriv != d.ctypes.data          # device copies, not the host buffers
+        assert c.y_ready and c.y_chunk_frames == 1 and c.deriv_progress   # one flag per frame, progress counter
+        flags = np.ctypeslib.as_array(ctypes.cast(c.y_ready, ctypes.POINTER(ctypes.c_uint)), shape=(T,))
+        assert (flags != 0).all()                                          # every frame was announced
+        assert c.scale_gamma == pytest.approx(-1.0) and c.scale_y == 0.0   # deriv_scale = +1 on this entry
+    finally:
+        mock.my_lib_supervision_free(s)
+        mock.my_lib_denominator_graph_free(g)
