@@ -486,3 +486,64 @@ def test_host_buffer_entry_launch_parameters(mock):
     finally:
         mock.my_lib_supervision_free(s)
         mock.my_lib_denominator_graph_free(g)
+
+
+def test_strided_xent_and_objective_only_entries(mock):
+    den = synth.make_den_fst(31, 90, 14, mean_deg=3.0)
+    B, T = 7, 9
+    P = den.num_pdfs
+    sup = synth.make_supervision(32, den, B, T, num_paths=2, weight=1.0)
+    g, s = _handles(mock, den, sup)
+    try:
+        # a network output left in (B, P, T): element strides over (frame, sequence, pdf) = (1, P*T, T)
+        x = np.zeros((B, P, T), dtype=np.float32)
+        dx = np.zeros_like(x)
+        xe = np.zeros_like(x)
+        st = (ctypes.c_int64 * 3)(1, P * T, T)
+        res = np.zeros(3, dtype=np.float32)
+        mock.mock_reset_launches()
+        ok = mock.torchain_ComputeChainObjfAndDeriv_strided(g, s, _p(x), T, B, P, st, _p(res), None, _p(dx), st, _p(xe), st,
+                                                            0.0, 0.1, 0.1, -1.0, 0, None)
+        assert ok == 1, mock.torchain_last_error()
+        kernels = [_kernel(lib_name) for lib_name, *_ in _launches(mock)]
+        assert kernels == ["num_fb_kernel", "den_forward_kernel", "den_backward_kernel", "zero_kernel",
+                           "final_scalars_kernel", "final_deriv_kernel"]    # the xent output is zeroed, then scattered
+        c = _den_batches(mock)[0][1].c[0]
+        assert list(c.yl) == [1, P * T, T] and list(c.dl) == [1, P * T, T] and c.y == x.ctypes.data
+        # frames / sequences that do not match the supervision, missing strides
+        assert mock.torchain_ComputeChainObjfAndDeriv_strided(g, s, _p(x), T + 1, B, P, st, _p(res), None, _p(dx), st, None,
+                                                              None, 0.0, 0.1, 0.0, -1.0, 0, None) == 0
+        assert mock.torchain_ComputeChainObjfAndDeriv_strided(g, s, _p(x), T, B, P, st, _p(res), None, _p(dx), None, None,
+                                                              None, 0.0, 0.1, 0.0, -1.0, 0, None) == 0
+        # objective only: no derivative buffer from the caller -> a scratch matrix in the workspace
+        y = np.zeros((T * B, P), dtype=np.float32)
+        mock.mock_reset_launches()
+        ok = mock.torchain_ComputeChainObjfAndDeriv_ex(g, s, _p(y), T * B, P, P, _p(res), None, None, 0, None, 0,
+                                                       0.0, 0.1, 0.0, 1.0, 0, None)
+        assert ok == 1, mock.torchain_last_error()
+        c = _den_batches(mock)[0][1].c[0]
+        assert c.deriv and c.deriv != y.ctypes.data and list(c.dl) == [B * P, P, 1]
+        # leaky-HMM coefficient outside (0, 1): Kaldi asserts, this returns an error
+        for bad in (0.0, 1.0, -0.1, float("nan")):
+            assert mock.torchain_ComputeChainObjfAndDeriv_ex(g, s, _p(y), T * B, P, P, _p(res), None, None, 0, None, 0,
+                                                             0.0, bad, 0.0, 1.0, 0, None) == 0
+            assert b"leaky" in mock.torchain_last_error()
+    finally:
+        mock.my_lib_supervision_free(s)
+        mock.my_lib_denominator_graph_free(g)
+
+
+def test_relayout_entries_launch_geometry(mock):
+    """torchain_to2d / torchain_from2d: one CTA per (sequence, 32 pdfs) block; sizes the tiled kernel cannot
+    take are refused so that the caller permutes some other way."""
+    B, P, T = 5, 70, 12
+    x = np.zeros((B, P, T), dtype=np.float32)
+    rows = np.zeros((T * B, P), dtype=np.float32)
+    mock.mock_reset_launches()
+    assert mock.torchain_to2d(_p(x), B, P, T, _p(rows), P, 0, None) == 1
+    assert mock.torchain_from2d(_p(rows), P, B, P, T, _p(x), -1.0, 0, None) == 1
+    ls = _launches(mock)
+    assert len(ls) == 2 and all("relayout" in l[0] or "2d" in l[0] for l in ls)
+    assert mock.torchain_to2d(_p(x), B, P, 1600, _p(rows), P, 0, None) == 0
+    assert mock.torchain_to2d(_p(x), B, P, T, _p(rows), P - 1, 0, None) == 0
+    assert mock.torchain_from2d(None, P, B, P, T, _p(x), 1.0, 0, None) == 0
