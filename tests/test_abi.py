@@ -420,3 +420,38 @@ int main(void) {
                     "-o", exe, "-L", libdir, "-l:" + os.path.basename(_lib.LIB_PATH), "-Wl,-rpath," + libdir], check=True)
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
     assert out.startswith("ok ")
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_text_fst_reader_rejects_corrupt_input_without_crashing(seed, tmp_path):
+    """Same for the AT&T text form of den.fst: tokens replaced by negative / huge / non-numeric ones, lines cut."""
+    import random
+    rng = random.Random(seed)
+    den = synth.make_den_fst(3, 40, 10, mean_deg=3.0)
+    lines = ["%d %d %d %d %.9g" % (den.src[a], den.dst[a], den.ilabel[a], den.ilabel[a], den.cost[a])
+             for a in range(den.num_arcs)] + ["%d %.9g" % (s, den.final_cost[s]) for s in range(den.num_states)]
+    junk = ["-1", "-2147483648", "2147483647", "99999999999999999999", "1e400", "nan", "inf", "-inf", "x", "", "0x10", "3.7"]
+    path = str(tmp_path / "den.txt")
+    accepted = 0
+    for _ in range(150):
+        ls = list(lines)
+        for _ in range(rng.randrange(1, 4)):
+            i = rng.randrange(len(ls))
+            tok = ls[i].split()
+            mode = rng.randrange(3)
+            if mode == 0 and tok:
+                tok[rng.randrange(len(tok))] = rng.choice(junk)
+            elif mode == 1 and tok:
+                tok = tok[:rng.randrange(len(tok))]
+            else:
+                tok = tok + [rng.choice(junk)]
+            ls[i] = " ".join(tok)
+        with open(path, "w") as f:
+            f.write("\n".join(ls) + "\n")
+        try:
+            g = io.DenominatorGraph(path, den.num_pdfs)
+            assert g.n_pdf == den.num_pdfs and np.isfinite(g.initial_probs).all()
+            accepted += 1
+        except (ValueError, RuntimeError, OSError):
+            pass
+    assert accepted < 150
