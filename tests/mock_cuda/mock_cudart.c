@@ -171,12 +171,12 @@ cudaError_t cudaFree(void* p) { if (p) { __atomic_fetch_sub(&g_live_bytes, (long
 /* The host-buffer entry polls a mapped pinned counter that the backward kernel advances.  With
  * mock_set_auto_progress(limit) every cudaStreamQuery stands in for one frame of kernel progress: it bumps the
  * most recently allocated MAPPED pinned word and answers "not ready" until the counter has reached `limit`. */
-static volatile unsigned* g_mapped_word = NULL;
+static __thread volatile unsigned* g_mapped_word = NULL; /* the calling thread's own counter */
 static unsigned g_auto_progress = 0;
 void mock_set_auto_progress(unsigned limit) { g_auto_progress = limit; }
 cudaError_t cudaHostAlloc(void** p, size_t n, unsigned flags) {
   *p = tracked_alloc(n ? n : 1);
-  g_host_allocs++;
+  __atomic_fetch_add(&g_host_allocs, 1, __ATOMIC_RELAXED);
   if (*p && (flags & 2u) && n == sizeof(unsigned)) g_mapped_word = (volatile unsigned*)*p;
   return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }

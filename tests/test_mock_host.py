@@ -547,3 +547,35 @@ def test_relayout_entries_launch_geometry(mock):
     assert mock.torchain_to2d(_p(x), B, P, 1600, _p(rows), P, 0, None) == 0
     assert mock.torchain_to2d(_p(x), B, P, T, _p(rows), P - 1, 0, None) == 0
     assert mock.torchain_from2d(None, P, B, P, T, _p(x), 1.0, 0, None) == 0
+
+
+def test_host_buffer_entry_from_several_threads(mock):
+    """Per-thread resources of the host-buffer entry (streams, device buffers, flags, progress counter):
+    three host threads call it concurrently on shared handles."""
+    import threading
+    den = synth.make_den_fst(33, 70, 10, mean_deg=3.0)
+    B, T = 4, 11
+    sup = synth.make_supervision(34, den, B, T, num_paths=2, weight=1.0)
+    y = synth.make_nnet_output(35, B, T, den.num_pdfs).astype(np.float32)
+    g, s = _handles(mock, den, sup)
+    errors = []
+
+    def worker():
+        try:
+            for _ in range(25):
+                d = np.full_like(y, np.nan)
+                res = np.full(3, np.nan, dtype=np.float32)
+                ok = mock.torchain_ComputeChainObjfAndDeriv_host(g, s, _p(y), y.shape[0], y.shape[1], y.shape[1], _p(res),
+                                                                 _p(d), y.shape[1], None, 0, 0.0, 0.1, 0.0, 0)
+                assert ok == 1 and np.all(d == 0.0) and np.all(res == 0.0)
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker) for _ in range(3)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    mock.my_lib_supervision_free(s)
+    mock.my_lib_denominator_graph_free(g)
+    assert not errors, errors
