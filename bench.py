@@ -162,6 +162,23 @@ def cpu_baseline(c, seconds_budget=20.0, threads=None):
     return fps, ncores, "B=%d of %d sequences x T=%d frames, same den graph/options, %.1f s" % (Bs, c["B"], T, dt)
 
 
+def parity_check(c, sup, y_np, res, neg_deriv_np, threads):
+    """The step's results against the fp64 oracle on the same inputs (outside every timed region).
+    Tolerances are BASELINE.json's: objf, l2_term 1e-5 relative; derivative 1e-4 of the largest magnitude."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    t0 = time.perf_counter()
+    r = ol.chain(ol.OracleDen(c["den"]), ol.OracleSup(sup), y_np, l2=c["l2"], leaky=c["leaky"], mode="fp64",
+                 threads=threads)
+    e_objf = abs(float(res[0]) - r["objf"]) / max(abs(r["objf"]), 1e-30)
+    e_l2 = abs(float(res[1]) - r["l2_term"]) / max(abs(r["l2_term"]), 1e-30)
+    e_w = abs(float(res[2]) - r["weight"]) / max(abs(r["weight"]), 1e-30)
+    e_d = float(np.abs(-neg_deriv_np.astype(np.float64) - r["deriv"]).max() / max(np.abs(r["deriv"]).max(), 1e-30))
+    return {"objf_rel_err": e_objf, "l2_rel_err": e_l2, "weight_rel_err": e_w, "deriv_rel_err": e_d,
+            "oracle_objf": r["objf"], "oracle_ok": bool(r["ok"]), "oracle_s": time.perf_counter() - t0,
+            "ok": bool(r["ok"] and e_objf < 1e-5 and e_l2 < 1e-5 and e_w < 1e-6 and e_d < 1e-4)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:

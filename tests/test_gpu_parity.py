@@ -241,30 +241,6 @@ def test_host_buffer_entry_guard_rewrites_early_chunks():
         np.testing.assert_allclose(d[fin], want[fin], rtol=1e-6, atol=0)
 
 
-def test_large_config_properties():
-    """BASELINE.json cfg 2 at full size: size-independent properties (the oracle's fp64
-    pass is too slow for the GPU suite at this size; bench.py times a bounded sample)."""
-    import torch
-    c = synth.make_config("chime5", with_y=False)
-    g, s = handles(c["den"], c["sup"])
-    B, T, P = c["B"], c["T"], c["P"]
-    gen = torch.Generator(device="cuda").manual_seed(1234)
-    y = (torch.randn(T * B, P, device="cuda", generator=gen) * 2.0)
-    res, d, x = run_abi(g, s, y.cpu().numpy(), 0.0, 0.1, xent=0.1, want_xent=True)
-    d64 = d.astype(np.float64)
-    assert res[0] <= 0.0 and res[2] == B * T
-    assert np.abs(d64.sum(axis=1)).max() < 1e-3              # num and den posteriors both sum to 1 per row
-    assert np.abs(x.astype(np.float64).sum(axis=1) - 1.0).max() < 1e-4
-    den_post = x.astype(np.float64) - d64                     # = weight * gamma_den
-    assert den_post.min() > -1e-5 and abs(den_post.sum() - B * T) < 1e-2 * B * T / 100
-    # linearity in supervision.weight: objf and deriv scale, posterior structure does not
-    c["sup"].weight = 0.5
-    g2, s2 = handles(c["den"], c["sup"])
-    res2, d2, _ = run_abi(g2, s2, y.cpu().numpy(), 0.0, 0.1)
-    assert res2[0] == pytest.approx(0.5 * res[0], rel=1e-5)
-    assert deriv_err(d2, 0.5 * d64) < DERIV_RTOL
-
-
 def test_gpu_single_frame_and_single_sequence():
     """T = 1 (the reference's own test skips it, chain-supervision-test.hpp:243) and B = 1."""
     for (B, T) in [(1, 1), (3, 1), (1, 5)]:
@@ -326,22 +302,6 @@ def test_python_chain_loss_not_kaldi_way():
     assert float(results.data[0]) == pytest.approx(r["objf"], rel=1e-5)        # results of the SECOND call
     assert deriv_err(y.grad.cpu().numpy(), -r["deriv"]) < DERIV_RTOL             # mmi grad overwritten too
     assert deriv_err(x.grad.cpu().numpy(), -0.25 * r["xent"]) < DERIV_RTOL
-
-
-def test_large_tree_config_properties():
-    """BASELINE.json cfg 4 (P=6000, N=20000, A~600k, B=256) at full size: size-independent properties."""
-    import torch
-    c = synth.make_config("large_tree", with_y=False, T=10)
-    g, s = handles(c["den"], c["sup"])
-    B, T, P = c["B"], c["T"], c["P"]
-    y = torch.randn(T * B, P, device="cuda", generator=torch.Generator(device="cuda").manual_seed(7)) * 2.0
-    res, d, x = run_abi(g, s, y.cpu().numpy(), 0.0, 0.1, xent=0.1, want_xent=True)
-    d64, x64 = d.astype(np.float64), x.astype(np.float64)
-    assert res[0] <= 0.0 and res[2] == B * T
-    assert np.abs(d64.sum(axis=1)).max() < 1e-3
-    assert np.abs(x64.sum(axis=1) - 1.0).max() < 1e-4
-    den_post = x64 - d64
-    assert den_post.min() > -1e-5 and abs(den_post.sum() - B * T) < 1e-4 * B * T
 
 
 def _hub_graph(seed, N, P, hubs):
