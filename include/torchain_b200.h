@@ -217,41 +217,6 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den_graph_ptr, void* supervisio
  * of boundaries (chunks + 1), 0 if num_frames < 1.  Host logic only; no device is touched. */
 int torchain_host_chunk_bounds(int num_frames, int* bounds, int max_entries);
 
-/* ---- measurement helpers (used by bench.py; not part of the reference API) -- */
-
-/* Per-kernel timing for the roofline line of bench.py: when enabled, every launch
- * of the persistent denominator kernel is bracketed by CUDA events on the
- * caller's stream; torchain_profile_read waits for them and returns the
- * accumulated device time (ms) and launch count since the last reset. */
-void torchain_profile_enable(int on);
-int torchain_profile_read(void* den_graph_ptr, double* den_kernel_ms, int64_t* den_kernel_launches, int reset);
-
-/* With profiling enabled the kernel also stamps %globaltimer (ns) at every phase
- * boundary of its last launch: [start, prologue, T forward frames, backward
- * prologue, T backward frames, end].  Copies up to max_entries; returns the count. */
-int torchain_profile_timeline(void* den_graph_ptr, int64_t* out_ns, int max_entries);
-
-/* torchain_profile_enable(2) additionally records, for every CTA and frame of the last
- * forward/backward launch pair, %globaltimer when main warp 0 finished its arcs, when aux
- * warp 0 finished, when the CTA passed its block reduction, and when it left the grid barrier.
- * Layout [2][frames][grid][4] int64 ns; returns the entry count (call with out_ns = NULL to size). */
-int64_t torchain_profile_cta_trace(void* den_graph_ptr, int64_t* out_ns, int64_t max_entries, int* frames, int* grid);
-
-/* L2-resident random 512-byte-row gather: the measured denominator of the
- * gather roofline.  Returns achieved GB/s, <0 on error. */
-double torchain_microbench_l2_gather(int device, int64_t table_bytes, int row_bytes, int iters);
-/* red.global.add.v4.f32 to random 512-byte rows of an L2-resident table; GB/s of operand bytes. */
-double torchain_microbench_l2_red(int device, int64_t table_bytes, int row_bytes, int iters);
-/* Mean latency in microseconds of the software grid barrier at one CTA per SM. */
-double torchain_microbench_grid_barrier(int device, int iters);
-/* Feasibility probe of a sequence-sliced recurrence: CTAs own 8 or 16 sequences with
- * exp(y) (mode 1: and the occupancies) in shared memory, 32 / 64-byte state gathers from L2, streamed arcs.
- * Returns microseconds per frame on a synthetic graph of config 2's shape; <0 on error. */
-double torchain_microbench_sliced(int device, int seqs_per_cta, int depth, int mode, int frames);
-/* The forward recurrence's gather pattern (5 MB + 1.5 MB tables, 512-byte rows) with `warps` warps per SM
- * and `depth` (8, 12, 16 or 24) gathers in flight per warp; GB/s. */
-double torchain_microbench_pattern(int device, int warps, int depth, int iters);
-
 #ifdef __cplusplus
 }
 #endif

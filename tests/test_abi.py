@@ -14,12 +14,16 @@ from torchain_b200 import _lib, io, synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "torchain_b200.h")
+HEADERS = [HEADER, os.path.join(ROOT, "include", "torchain_b200_profile.h")]
 
 
 def declared_symbols():
-    text = open(HEADER).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:my_lib|torchain)_\w+)\s*\(", text)))
+    names = set()
+    for h in HEADERS:
+        text = open(h).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names.update(re.findall(r"\b((?:my_lib|torchain)_\w+)\s*\(", text))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():

@@ -8,7 +8,7 @@ while [ $# -gt 1 ]; do
   name=$1; flags=$2; shift 2
   out=../../build/variants/$name
   mkdir -p $out
-  for f in chain_api den_kernel num_kernel layout_kernel microbench; do
+  for f in chain_api den_kernel num_kernel layout_kernel; do
     /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC $flags -c -o $out/$f.o $f.cu &
   done
   wait

@@ -10,12 +10,14 @@ python bench.py --impl reference --steps 3 --warmup 1 > $O/r01_bench_reference_a
 python tools/layout_probe.py > $O/r01_layout_probe.txt 2>&1
 python tools/den_timeline.py > $O/r01_den_timeline_final.txt 2>&1
 python - > $O/r01_microbench_final.txt 2>&1 <<'PY'
-from torchain_b200 import _lib
-lib = _lib.load()
+import sys
+sys.path.insert(0, 'tools/microbench')
+import mb as _mb
+mb = _mb.load()
 for rb in (512, 256, 128, 64, 32):
-    print("gather", rb, lib.torchain_microbench_l2_gather(0, 32 << 20, rb, 400))
-    print("red", rb, lib.torchain_microbench_l2_red(0, 32 << 20, rb, 400))
-print("barrier us", lib.torchain_microbench_grid_barrier(0, 2000))
+    print("gather", rb, mb.tb_microbench_l2_gather(0, 32 << 20, rb, 400))
+    print("red", rb, mb.tb_microbench_l2_red(0, 32 << 20, rb, 400))
+print("barrier us", mb.tb_microbench_grid_barrier(0, 2000))
 PY
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r01_ncu_launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $O/ncu_launches.log 2>&1

@@ -1,8 +1,19 @@
-// microbench.cu -- measured denominators for the gather roofline:
-// an L2-resident random-row gather, the matching vector RED scatter, and the
-// latency of the software grid barrier used by den_kernel.cu.
+// microbench.cu -- libtorchain_microbench.so: measured denominators for the gather roofline
+//  and feasibility probes.  BENCH-ONLY: bench.py and tools/ load it; nothing in
+// torchain_b200/ links or loads it, and none of its symbols is part of the drop-in boundary
+// (include/torchain_b200.h).
+//   * L2-resident random-row gather / vector RED scatter / software grid barrier latency
+//   * the forward recurrence's gather pattern (two tables, 512 B rows) with register loads,
+//     with an LDGSTS (cp.async) ring in shared memory, and with a TMA bulk-copy ring
+//   * the exp(y) tile held in distributed shared memory of a cluster
+//   * the sequence-sliced recurrence ruled out in round 1
 
-#include "chain_kernels.h"
+#include "microbench.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
 
 #include <algorithm>
 #include <cstring>
@@ -10,6 +21,9 @@
 
 namespace tb {
 namespace {
+
+std::atomic<long long> g_mb_launches{0};
+void count_launch(int n = 1) { g_mb_launches += n; }
 
 __device__ __forceinline__ unsigned hash32(unsigned x) {
   x ^= x >> 16;
@@ -510,4 +524,315 @@ double microbench_grid_barrier(int device, int iters) {
   return (double)best * 1e3 / iters;
 }
 
+
+namespace {
+// ---------------------------------------------------------------------------
+// The same two-table gather with the rows landing in SHARED memory instead of registers.
+// Register loads cap a warp at ~2 rows in flight whatever the unroll depth (pattern_kernel: the
+// throughput follows the warp count, not the depth); asynchronous copies are not tied to the
+// warp's scoreboards, so a few warps can keep many rows in flight.
+//   MODE 0: LDGSTS (cp.async.cg 16 B per lane, one 512 B row per warp instruction), groups
+//           committed per arc, cp.async.wait_group DEPTH-1 before an arc is consumed
+//   MODE 1: TMA bulk copies (cp.async.bulk, one elected lane per row, completion on an mbarrier
+//           per ring slot)
+// Each warp owns a ring of DEPTH slots x 2 rows (alpha row + exp row) = DEPTH KB.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int DEPTH, int MODE>
+__global__ void __launch_bounds__(1024) pattern_async_kernel(const float4* __restrict__ ta, unsigned na,
+                                                             const float4* __restrict__ te, unsigned ne, int iters,
+                                                             float* sink) {
+  extern __shared__ __align__(128) unsigned char smem_async[];
+  const unsigned warp_in_cta = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  float4* ring = reinterpret_cast<float4*>(smem_async) + (size_t)warp_in_cta * DEPTH * 64;  // [DEPTH][2][32] float4
+  unsigned long long* bars =
+      reinterpret_cast<unsigned long long*>(smem_async + (size_t)nwarps * DEPTH * 1024) + warp_in_cta * DEPTH;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const unsigned seed = warp * 9781u + 17u;
+  if (MODE == 1) {
+    if (lane == 0)
+      for (int u = 0; u < DEPTH; u++)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + u)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+  }
+  auto issue = [&](int k) {  // arc k -> slot k % DEPTH
+    const unsigned r = hash32(seed + (unsigned)k * 2654435761u);
+    const float4* ga = ta + (size_t)(r % na) * 32;
+    const float4* ge = te + (size_t)((r >> 7) % ne) * 32;
+    float4* slot = ring + (size_t)(k % DEPTH) * 64;
+    if (MODE == 0) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(slot + lane)), "l"(ga + lane) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(slot + 32 + lane)), "l"(ge + lane)
+                   : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    } else if (lane == 0) {
+      const unsigned bar = smem_u32(bars + k % DEPTH);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 1024;" ::"r"(bar) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 512, [%2];" ::"r"(
+                       smem_u32(slot)),
+                   "l"(ga), "r"(bar)
+                   : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 512, [%2];" ::"r"(
+                       smem_u32(slot + 32)),
+                   "l"(ge), "r"(bar)
+                   : "memory");
+    }
+  };
+#pragma unroll
+  for (int u = 0; u < DEPTH; u++) issue(u);
+  for (int k = 0; k < iters; k++) {
+    if (MODE == 0) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+    } else {
+      const unsigned bar = smem_u32(bars + k % DEPTH), parity = (unsigned)(k / DEPTH) & 1u;
+      unsigned done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+      }
+    }
+    const float4* slot = ring + (size_t)(k % DEPTH) * 64;
+    const float4 a = slot[lane], e = slot[32 + lane];
+    acc.x = fmaf(a.x, e.x, acc.x);
+    acc.y = fmaf(a.y, e.y, acc.y);
+    acc.z = fmaf(a.z, e.z, acc.z);
+    acc.w = fmaf(a.w, e.w, acc.w);
+    if (MODE == 1) __syncwarp();  // every lane has read the slot before lane 0 re-arms it
+    issue(k + DEPTH);             // (the tail issues DEPTH rows nobody consumes; drained below)
+  }
+  if (MODE == 0) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else {
+    for (int k = iters; k < iters + DEPTH; k++) {
+      const unsigned bar = smem_u32(bars + k % DEPTH), parity = (unsigned)(k / DEPTH) & 1u;
+      unsigned done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+      }
+    }
+  }
+  if (acc.x + acc.y + acc.z + acc.w == 123.456f) *sink = acc.x;
+}
+
+template <int DEPTH, int MODE>
+cudaError_t launch_pattern_async(int sms, int warps, const float4* ta, unsigned na, const float4* te, unsigned ne,
+                                 int iters, float* sink) {
+  auto kern = pattern_async_kernel<DEPTH, MODE>;
+  const size_t smem = (size_t)warps * DEPTH * 1024 + (size_t)warps * DEPTH * 8;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<sms, warps * 32, smem>>>(ta, na, te, ne, iters, sink);
+  count_launch();
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// exp(y) tile in DISTRIBUTED shared memory: a cluster of CS CTAs holds the
+// [P][128] fp32 tile (1.5 MB at config 2) across its shared memories, P/CS rows per CTA; every warp
+// alternates an L2 gather of an alpha row with a 512 B row read from the shared memory of the CTA
+// that owns the pdf (ld.shared::cluster.v4 through mapa).  MODE 0: both halves (the mixed pattern),
+// MODE 1: DSMEM reads only, MODE 2: L2 reads only on the same launch geometry.
+// ---------------------------------------------------------------------------
+template <int DEPTH>
+__global__ void __launch_bounds__(1024) dsmem_pattern_kernel(const float4* __restrict__ ta, unsigned na, unsigned ne,
+                                                             int cs, int mode, int iters, float* sink) {
+  extern __shared__ __align__(128) unsigned char smem_ds[];
+  float4* mine = reinterpret_cast<float4*>(smem_ds);
+  const unsigned rows_per_cta = (ne + cs - 1) / cs;
+  for (unsigned i = threadIdx.x; i < rows_per_cta * 32; i += blockDim.x) mine[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const unsigned base = smem_u32(mine);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const unsigned seed = warp * 9781u + 17u;
+  for (int it = 0; it < iters; it++) {
+    float4 v[DEPTH];
+#pragma unroll
+    for (int u = 0; u < DEPTH; u += 2) {
+      const unsigned r = hash32(seed + (unsigned)(it * DEPTH + u) * 2654435761u);
+      const unsigned pdf = (r >> 7) % ne, pdf2 = (r >> 3) % ne;
+      unsigned remote, remote2;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                   : "=r"(remote)
+                   : "r"(base + ((pdf / (unsigned)cs) * 32 + lane) * 16), "r"(pdf % (unsigned)cs));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;"
+                   : "=r"(remote2)
+                   : "r"(base + ((pdf2 / (unsigned)cs) * 32 + lane) * 16), "r"(pdf2 % (unsigned)cs));
+      if (mode != 1) v[u] = __ldcg(ta + (size_t)(r % na) * 32 + lane);
+      else
+        asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                     : "r"(remote2));
+      if (mode != 2)
+        asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v[u + 1].x), "=f"(v[u + 1].y), "=f"(v[u + 1].z), "=f"(v[u + 1].w)
+                     : "r"(remote));
+      else v[u + 1] = __ldcg(ta + (size_t)((r >> 3) % na) * 32 + lane);
+    }
+#pragma unroll
+    for (int u = 0; u < DEPTH; u++) {
+      acc.x += v[u].x;
+      acc.y += v[u].y;
+      acc.z += v[u].z;
+      acc.w += v[u].w;
+    }
+  }
+  if (acc.x + acc.y + acc.z + acc.w == 123.456f) *sink = acc.x;
+  // nobody may exit while a peer can still read its shared memory
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+}  // namespace
+
+// GB/s of row bytes delivered (both tables), scaled to nothing: the launch covers every SM.
+// mode 0 = LDGSTS ring, 1 = TMA bulk ring.
+double microbench_pattern_async(int device, int warps, int depth, int mode, int iters) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+  if (warps < 1 || warps > 32 || mode < 0 || mode > 1) return -1.0;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const unsigned na = 10000, ne = 2928;
+  float4 *ta = nullptr, *te = nullptr;
+  float* sink = nullptr;
+  cudaMalloc(&ta, (size_t)na * 512);
+  cudaMalloc(&te, (size_t)ne * 512);
+  cudaMalloc(&sink, 4);
+  cudaMemset(ta, 0, (size_t)na * 512);
+  cudaMemset(te, 0, (size_t)ne * 512);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  bool ok = true;
+  for (int rep = 0; rep < 4 && ok; rep++) {
+    cudaEventRecord(e0);
+    cudaError_t e = cudaErrorInvalidValue;
+#define TB_PA(D)                                                                                             \
+  if (depth == D)                                                                                            \
+    e = mode == 0 ? launch_pattern_async<D, 0>(sms, warps, ta, na, te, ne, iters, sink)                      \
+                  : launch_pattern_async<D, 1>(sms, warps, ta, na, te, ne, iters, sink);
+    TB_PA(2) TB_PA(4) TB_PA(6) TB_PA(8) TB_PA(12) TB_PA(16)
+#undef TB_PA
+    cudaEventRecord(e1);
+    ok = e == cudaSuccess && cudaEventSynchronize(e1) == cudaSuccess;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0) best = std::min(best, ms);
+  }
+  ok = ok && cudaGetLastError() == cudaSuccess;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(ta);
+  cudaFree(te);
+  cudaFree(sink);
+  if (!ok) return -1.0;
+  return (double)sms * warps * (double)iters * 1024.0 / (best * 1e-3) / 1e9;
+}
+
+// GB/s of row bytes delivered PER 148 SMs (the launch may cover fewer: clusters of 8 / 16 do not
+// tile every GPC; *ctas_out receives the CTAs that ran).  mode 0 = L2 + DSMEM, 1 = DSMEM only, 2 = L2 only.
+double microbench_dsmem_pattern(int device, int cluster_size, int warps, int depth, int mode, int iters,
+                                int* ctas_out) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+  if ((cluster_size != 2 && cluster_size != 4 && cluster_size != 8 && cluster_size != 16) || warps < 1 || warps > 32 ||
+      mode < 0 || mode > 2)
+    return -1.0;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const unsigned na = 10000, ne = 2928;
+  const size_t smem = (size_t)((ne + cluster_size - 1) / cluster_size) * 512;
+  if (smem > 227 * 1024) return -1.0;
+  void (*kern)(const float4*, unsigned, unsigned, int, int, int, float*) = nullptr;
+  if (depth == 2) kern = dsmem_pattern_kernel<2>;
+  else if (depth == 4) kern = dsmem_pattern_kernel<4>;
+  else if (depth == 8) kern = dsmem_pattern_kernel<8>;
+  else return -1.0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1.0;
+  if (cluster_size > 8 &&
+      cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+    return -1.0;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_size;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(warps * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cfg.gridDim = dim3(cluster_size);
+  int nclusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) {
+    (void)cudaGetLastError();
+    return -1.0;
+  }
+  nclusters = std::min(nclusters, sms / cluster_size);
+  const int ctas = nclusters * cluster_size;
+  cfg.gridDim = dim3(ctas);
+  if (ctas_out) *ctas_out = ctas;
+  float4* ta = nullptr;
+  float* sink = nullptr;
+  cudaMalloc(&ta, (size_t)na * 512);
+  cudaMalloc(&sink, 4);
+  cudaMemset(ta, 0, (size_t)na * 512);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  bool ok = true;
+  for (int rep = 0; rep < 4 && ok; rep++) {
+    cudaEventRecord(e0);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, (const float4*)ta, na, ne, cluster_size, mode, iters, sink);
+    count_launch();
+    cudaEventRecord(e1);
+    ok = e == cudaSuccess && cudaEventSynchronize(e1) == cudaSuccess;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0) best = std::min(best, ms);
+  }
+  ok = ok && cudaGetLastError() == cudaSuccess;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(ta);
+  cudaFree(sink);
+  if (!ok) return -1.0;
+  return (double)sms * warps * (double)iters * depth * 512.0 / (best * 1e-3) / 1e9;
+}
+
 }  // namespace tb
+
+extern "C" {
+double tb_microbench_l2_gather(int device, int64_t table_bytes, int row_bytes, int iters) {
+  return tb::microbench_l2_gather(device, table_bytes, row_bytes, iters);
+}
+double tb_microbench_l2_red(int device, int64_t table_bytes, int row_bytes, int iters) {
+  return tb::microbench_l2_red(device, table_bytes, row_bytes, iters);
+}
+double tb_microbench_grid_barrier(int device, int iters) { return tb::microbench_grid_barrier(device, iters); }
+double tb_microbench_pattern(int device, int warps, int depth, int iters) {
+  return tb::microbench_pattern(device, warps, depth, iters);
+}
+double tb_microbench_pattern_async(int device, int warps, int depth, int mode, int iters) {
+  return tb::microbench_pattern_async(device, warps, depth, mode, iters);
+}
+double tb_microbench_dsmem_pattern(int device, int cluster_size, int warps, int depth, int mode, int iters,
+                                   int* ctas_out) {
+  return tb::microbench_dsmem_pattern(device, cluster_size, warps, depth, mode, iters, ctas_out);
+}
+double tb_microbench_sliced(int device, int seqs_per_cta, int depth, int mode, int frames) {
+  return tb::microbench_sliced(device, seqs_per_cta, depth, mode, frames);
+}
+long long tb_microbench_launch_count(void) { return tb::g_mb_launches.load(); }
+}

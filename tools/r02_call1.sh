@@ -23,6 +23,8 @@ for k, v in rows.items():
     print("%-75s compute_done %6.0f  end %6.0f us (median of %d)" % (
         k, statistics.median(a for a, _ in v), statistics.median(b for _, b in v), len(v)))
 PY
-timeout 200 python bench.py --no-cpu-baseline > $O/r02_bench_start.json 2> $O/r02_bench_start.err
+timeout 200 python bench.py > $O/r02_bench_start.json 2> $O/r02_bench_start.err
 python -c "
 import json; d=json.load(open('$O/r02_bench_start.json')); print(d['ms_per_step'], d['value'], d['roofline']['frac'], d['roofline']['launch_ms'], d['e2e']['ms_per_step'], d['clocks'])"
+timeout 300 python tools/gather_probe.py > $O/r02_gather_probe.txt 2>&1
+cat $O/r02_gather_probe.txt

@@ -24,8 +24,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     args = ap.parse_args()
     lib = _lib.load()
+    sys.path.insert(0, os.path.join(ROOT, "tools", "microbench"))
+    import mb as _mb
+    mb = _mb.load()
     graphs = {}
-    l2_peak = lib.torchain_microbench_l2_gather(0, 32 << 20, 512, 400)
+    l2_peak = mb.tb_microbench_l2_gather(0, 32 << 20, 512, 400)
     for pt in args.points.split(","):
         name, B, T = pt.split(":")
         B, T = int(B), int(T)

@@ -63,11 +63,6 @@ SIGNATURES = {
     "torchain_profile_read": (_c_i, [_c_p, _c_p, _c_p, _c_i]),
     "torchain_profile_timeline": (_c_i, [_c_p, _c_p, _c_i]),
     "torchain_profile_cta_trace": (_c_i64, [_c_p, _c_p, _c_i64, _c_p, _c_p]),
-    "torchain_microbench_l2_gather": (_c_d, [_c_i, _c_i64, _c_i, _c_i]),
-    "torchain_microbench_l2_red": (_c_d, [_c_i, _c_i64, _c_i, _c_i]),
-    "torchain_microbench_grid_barrier": (_c_d, [_c_i, _c_i]),
-    "torchain_microbench_pattern": (_c_d, [_c_i, _c_i, _c_i, _c_i]),
-    "torchain_microbench_sliced": (_c_d, [_c_i, _c_i, _c_i, _c_i, _c_i]),
 }
 
 _lib = None

@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "../../include/torchain_b200.h"
+#include "../../include/torchain_b200_profile.h"
 #include "chain_kernels.h"
 
 namespace {
@@ -2007,21 +2008,6 @@ int64_t torchain_profile_cta_trace(void* den_graph_ptr, int64_t* out_ns, int64_t
     return n;
   }
   return 0;
-}
-
-double torchain_microbench_l2_gather(int device, int64_t table_bytes, int row_bytes, int iters) {
-  return tb::microbench_l2_gather(device, table_bytes, row_bytes, iters);
-}
-double torchain_microbench_l2_red(int device, int64_t table_bytes, int row_bytes, int iters) {
-  return tb::microbench_l2_red(device, table_bytes, row_bytes, iters);
-}
-double torchain_microbench_grid_barrier(int device, int iters) { return tb::microbench_grid_barrier(device, iters); }
-double torchain_microbench_pattern(int device, int warps, int depth, int iters) {
-  return tb::microbench_pattern(device, warps, depth, iters);
-}
-
-double torchain_microbench_sliced(int device, int seqs_per_cta, int depth, int mode, int frames) {
-  return tb::microbench_sliced(device, seqs_per_cta, depth, mode, frames);
 }
 
 }  // extern "C"

@@ -178,11 +178,4 @@ cudaError_t launch_from2d(const float* y_rows, float* x_bpt, int B, int P, int T
 void count_launch(int n = 1);
 int64_t launch_count();
 
-// micro-benchmarks
-double microbench_l2_gather(int device, int64_t table_bytes, int row_bytes, int iters);
-double microbench_l2_red(int device, int64_t table_bytes, int row_bytes, int iters);
-double microbench_grid_barrier(int device, int iters);
-double microbench_pattern(int device, int warps, int depth, int iters);
-double microbench_sliced(int device, int S, int depth, int mode, int frames);
-
 }  // namespace tb
