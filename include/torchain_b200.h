@@ -104,6 +104,14 @@ void* torchain_supervision_from_kaldi_bytes(const void* data, int64_t nbytes, in
  * inputs stay valid and owned by the caller. */
 void* torchain_supervision_merge(void* const* supervision_ptrs, int32_t n);
 
+/* Starts the (asynchronous) upload of the supervision's device image on `stream` of `device`, so that a
+ * data-loading thread can have minibatch k+1 resident while minibatch k is still being computed.  Optional:
+ * the first ComputeChainObjfAndDeriv on a device uploads on its own stream otherwise.  Later calls on other
+ * streams order themselves behind the upload.  Never synchronises the device: the image lives in pooled
+ * device + pinned memory that supervision handles hand back when they are freed (a training loop builds one
+ * Supervision per minibatch, /root/reference/example/chime5/train_faster.py:116-141). */
+int torchain_supervision_prefetch(void* supervision_ptr, int device, void* stream);
+
 /* The reference's reader-based constructors; egs reading is out of scope, so
  * these always return NULL and set the error string. */
 void* my_lib_supervision_new(void* reader_ptr);

@@ -37,6 +37,7 @@ SIGNATURES = {
         _c_p, [_c_f, _c_i32, _c_i32, _c_i32, _c_i32, _c_p, _c_p, _c_p, _c_p, _c_p]),
     "torchain_supervision_from_kaldi_bytes": (_c_p, [_c_p, _c_i64, _c_p]),
     "torchain_supervision_merge": (_c_p, [_c_p, _c_i32]),
+    "torchain_supervision_prefetch": (_c_i, [_c_p, _c_i, _c_p]),
     "my_lib_supervision_new": (_c_p, [_c_p]),
     "my_lib_supervision_rand_new": (_c_p, [_c_p]),
     "my_lib_supervision_free": (None, [_c_p]),

@@ -153,6 +153,12 @@ struct Workspace {
   char* timeline_dev = nullptr;
   int timeline_len = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof;  // around each denominator launch (profiling only)
+  // A workspace (alpha store, zeroed scalars and barrier counters, numerator scratch, the pinned result
+  // words, the fork / join events) serves ONE call at a time: two host threads that call on the same
+  // (device, stream) -- the legacy default stream, say -- must not interleave their memsets and launches.
+  // Held from a call's first enqueue to its last enqueue (or, for a call that delivers results to the
+  // host, its stream synchronisation); work already enqueued is ordered by the stream itself.
+  std::mutex call_mu;
   int in_use = 0;                // calls currently between get_workspace and their return (guarded by DenGraph::mu)
   unsigned long long last_use = 0;  // DenGraph::ws_clock at the last get_workspace
   ~Workspace() {
@@ -167,7 +173,24 @@ struct Workspace {
   }
 };
 
+// Test hooks, read from the environment ONCE per handle (when the graph is created), never per call:
+//   TORCHAIN_SPLIT_CAP=n        states with more than n arcs in a direction are split into sub-tasks (default 192)
+//   TORCHAIN_FORCE_UNSTAGED=1   arc slices stay in global memory even when they would fit shared memory
+//   TORCHAIN_NO_AUTOTUNE=1      the partition is not re-dealt from measured per-warp busy cycles
+struct GraphHooks {
+  int split_cap = 192;
+  bool force_unstaged = false, no_autotune = false;
+  static GraphHooks from_env() {
+    GraphHooks h;
+    if (const char* e = getenv("TORCHAIN_SPLIT_CAP")) h.split_cap = std::max(2, atoi(e));
+    h.force_unstaged = getenv("TORCHAIN_FORCE_UNSTAGED") != nullptr;
+    h.no_autotune = getenv("TORCHAIN_NO_AUTOTUNE") != nullptr;
+    return h;
+  }
+};
+
 struct DenGraph {
+  GraphHooks hooks;
   int N = 0, A = 0, P = 0, start = 0;
   std::vector<int> src, dst, pdf;
   std::vector<float> prob;
@@ -225,8 +248,7 @@ void build_dir(const DenGraph& g, int dir, int grid, int bins_per_cta, const std
   const int kTaskOverhead = 3;  // fixed per-state cost in arc units (prologue, store, partial sums)
   // States with very many arcs (real den graphs are heavy-tailed) would be one serial warp task;
   // they are split into sub-tasks of at most `cap` arcs that accumulate with REDs.
-  int cap = 192;
-  if (const char* e = getenv("TORCHAIN_SPLIT_CAP")) cap = std::max(2, atoi(e));
+  const int cap = g.hooks.split_cap;
   struct Item {
     int state, first, count, flag;  // arcs [first, first+count) of the state's CSR slice
   };
@@ -326,6 +348,7 @@ DenGraph* make_den_graph(int32_t N, int32_t A, const int32_t* src, const int32_t
     return nullptr;
   }
   auto g = std::make_unique<DenGraph>();
+  g->hooks = GraphHooks::from_env();
   g->N = N;
   g->A = A;
   g->P = num_pdfs;
@@ -527,10 +550,79 @@ bool read_fst_file(const char* path, std::vector<int32_t>* src, std::vector<int3
 // ---------------------------------------------------------------------------
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// The device copy of a supervision is ONE allocation filled by ONE copy: a training loop builds a new
-// Supervision for every minibatch, and 14 separate arrays cost 14 x (cudaMalloc + synchronous cudaMemcpy) on
-// first use and 14 x cudaFree (each an implicit device synchronisation) when the handle dies.
-struct DevView {  // a typed window into SupDevice::blob
+// The device copy of a supervision is ONE block filled by ONE asynchronous copy out of pinned staging
+// memory.  A training loop builds a new Supervision for every minibatch (the reference does,
+// /root/reference/example/chime5/train_faster.py:116-141), so nothing on this path may synchronise the
+// device: blocks (device memory + pinned staging of the same size) come from a process-wide pool and go back
+// to it when the handle dies -- no cudaMalloc / cudaFree per minibatch, no synchronous cudaMemcpy.  A block
+// remembers, per stream, an event behind the last work that read it; whoever gets the block next makes its
+// upload stream wait for those events first.
+struct SupBlock {
+  int device = -1;
+  char* dev = nullptr;
+  char* pinned = nullptr;
+  size_t cap = 0;
+  std::map<cudaStream_t, cudaEvent_t> last_use;  // behind the last kernels that read `dev`, per stream
+  ~SupBlock() {  // only when the pool sheds a block (the device is idle-synchronised by cudaFree itself)
+    for (auto& kv : last_use) cudaEventDestroy(kv.second);
+    if (dev) cudaFree(dev);
+    if (pinned) cudaFreeHost(pinned);
+  }
+};
+
+class SupBlockPool {
+ public:
+  // the longest-idle free block of `device` that holds `bytes` without being more than 4x too large (its
+  // last readers are the most likely to have finished), else a new one
+  cudaError_t acquire(int device, size_t bytes, std::unique_ptr<SupBlock>* out) {
+    {
+      std::lock_guard<std::mutex> lock(mu_);
+      int best = -1;
+      for (int i = 0; i < (int)free_.size() && best < 0; i++) {
+        const SupBlock& b = *free_[i];
+        if (b.device != device || b.cap < bytes || b.cap > 4 * std::max<size_t>(bytes, 1 << 16)) continue;
+        best = i;
+      }
+      if (best >= 0) {
+        *out = std::move(free_[best]);
+        free_.erase(free_.begin() + best);
+        return cudaSuccess;
+      }
+    }
+    auto b = std::make_unique<SupBlock>();
+    b->device = device;
+    b->cap = align_up(bytes + bytes / 4, 1 << 16);  // headroom: the next minibatch is about this size
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&b->dev), b->cap);
+    if (e != cudaSuccess) return e;
+    e = cudaMallocHost(reinterpret_cast<void**>(&b->pinned), b->cap);
+    if (e != cudaSuccess) return e;
+    *out = std::move(b);
+    return cudaSuccess;
+  }
+  void release(std::unique_ptr<SupBlock> b) {
+    std::unique_ptr<SupBlock> shed;  // destroyed outside the lock
+    std::lock_guard<std::mutex> lock(mu_);
+    free_.push_back(std::move(b));
+    if (free_.size() > kMaxFree) {  // oldest first
+      shed = std::move(free_.front());
+      free_.erase(free_.begin());
+    }
+  }
+
+ private:
+  static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+  static constexpr size_t kMaxFree = 8;
+  std::mutex mu_;
+  std::vector<std::unique_ptr<SupBlock>> free_;
+};
+// Leaked on purpose: handles may be freed by a host language's finalisers during process teardown, after
+// static destructors (and the CUDA runtime) are gone.
+SupBlockPool& sup_pool() {
+  static SupBlockPool* pool = new SupBlockPool();
+  return *pool;
+}
+
+struct DevView {  // a typed window into SupDevice::block
   void* ptr = nullptr;
   template <typename T>
   T* as() const {
@@ -538,9 +630,15 @@ struct DevView {  // a typed window into SupDevice::blob
   }
 };
 struct SupDevice {
-  DevBuf blob;
+  std::unique_ptr<SupBlock> block;
+  cudaEvent_t uploaded = nullptr;  // behind the upload copy, on the stream that performed it
+  cudaStream_t upload_stream = nullptr;
   DevView chain_level_off, level_state_off, chain_arc_off, in_off, in_arcs, out_off, out_arcs, final_cost, arc_row,
       arc_pdf, arc_cost, arc_seq, frame_off, frame_arcs;
+  ~SupDevice() {
+    if (uploaded) cudaEventDestroy(uploaded);
+    if (block) sup_pool().release(std::move(block));
+  }
 };
 
 struct Supervision {
@@ -852,7 +950,7 @@ int get_den_device(DenGraph* g, int device, DenDevice** out) {
   if (d->grid <= 0) return fail("cannot query SM count");
   for (int dir = 0; dir < 2; dir++) d->speed[dir].assign((size_t)d->grid * tb::kDenMainWarps, 1.0);
   CUDA_OK(d->warp_busy.reserve(sizeof(unsigned long long) * 2 * (size_t)d->grid * tb::kDenWarps));
-  if (getenv("TORCHAIN_NO_AUTOTUNE")) d->calib_rounds_done = kCalibRounds;
+  if (g->hooks.no_autotune) d->calib_rounds_done = kCalibRounds;
   if (!build_partition(g, d.get())) return 0;
   *out = d.get();
   g->dev[device] = std::move(d);
@@ -909,7 +1007,9 @@ int autotune_partition(DenGraph* g, DenDevice* d, cudaStream_t copy_stream = nul
   return build_partition(g, d);
 }
 
-int get_sup_device(Supervision* s, int device, SupDevice** out) {
+// The device image of a supervision on `device`, uploading it on `stream` (asynchronously) if this is its
+// first use there.  Every later user must order itself behind SupDevice::uploaded (wait_sup_uploaded).
+int get_sup_device(Supervision* s, int device, cudaStream_t stream, SupDevice** out) {
   std::lock_guard<std::mutex> lock(s->mu);
   auto it = s->dev.find(device);
   if (it != s->dev.end()) {
@@ -917,14 +1017,17 @@ int get_sup_device(Supervision* s, int device, SupDevice** out) {
     return 1;
   }
   auto d = std::make_unique<SupDevice>();
-  // lay the arrays out back to back (256-byte slots), stage them in one host buffer, upload once
-  std::vector<char> stage;
-  std::vector<std::pair<DevView*, size_t>> slots;
+  // lay the arrays out back to back (256-byte slots) in ONE pinned staging block, upload once
+  struct Slot {
+    DevView* view;
+    const void* src;
+    size_t nbytes, off;
+  };
+  std::vector<Slot> slots;
+  size_t total = 0;
   auto add = [&](DevView& view, const void* src, size_t nbytes) {
-    const size_t off = stage.size();
-    stage.resize(off + align_up(std::max<size_t>(nbytes, 16), 256));
-    if (nbytes) std::memcpy(stage.data() + off, src, nbytes);
-    slots.emplace_back(&view, off);
+    slots.push_back({&view, src, nbytes, total});
+    total += align_up(std::max<size_t>(nbytes, 16), 256);
   };
   auto add_vec = [&](DevView& view, const auto& v) { add(view, v.data(), sizeof(v[0]) * v.size()); };
   add_vec(d->chain_level_off, s->chain_level_off);
@@ -941,11 +1044,55 @@ int get_sup_device(Supervision* s, int device, SupDevice** out) {
   add_vec(d->arc_seq, s->arc_seq);
   add_vec(d->frame_off, s->frame_off);
   add_vec(d->frame_arcs, s->frame_arcs);
-  CUDA_OK(d->blob.reserve(stage.size()));
-  CUDA_OK(cudaMemcpy(d->blob.ptr, stage.data(), stage.size(), cudaMemcpyHostToDevice));
-  for (auto& sl : slots) sl.first->ptr = d->blob.as<char>() + sl.second;
+  CUDA_OK(sup_pool().acquire(device, total, &d->block));
+  SupBlock& b = *d->block;
+  // whoever read this block before (an earlier minibatch's kernels) must be done before it is overwritten;
+  // the staging half was last read by that minibatch's upload, which those kernels were ordered behind
+  for (auto& kv : b.last_use) {
+    if (kv.first == stream) continue;  // same stream: ordered anyway
+    CUDA_OK(cudaStreamWaitEvent(stream, kv.second, 0));
+  }
+  {
+    // the staging memory is reused too: the previous upload out of it must have completed.  It was ordered
+    // before kernels whose events we just made `stream` wait for -- but the HOST is about to write it now.
+    for (auto& kv : b.last_use) {
+      const cudaError_t q = cudaEventQuery(kv.second);
+      if (q == cudaErrorNotReady) CUDA_OK(cudaEventSynchronize(kv.second));
+      else if (q != cudaSuccess) CUDA_OK(q);
+    }
+  }
+  for (const Slot& sl : slots) {
+    if (sl.nbytes) std::memcpy(b.pinned + sl.off, sl.src, sl.nbytes);
+    sl.view->ptr = b.dev + sl.off;
+  }
+  CUDA_OK(cudaMemcpyAsync(b.dev, b.pinned, total, cudaMemcpyHostToDevice, stream));
+  CUDA_OK(cudaEventCreateWithFlags(&d->uploaded, cudaEventDisableTiming));
+  CUDA_OK(cudaEventRecord(d->uploaded, stream));
+  d->upload_stream = stream;
+  {  // the upload itself reads the staging half: a handle freed before any kernel used it is covered too
+    cudaEvent_t& ev = b.last_use[stream];
+    if (!ev) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CUDA_OK(cudaEventRecord(ev, stream));
+  }
   *out = d.get();
   s->dev[device] = std::move(d);
+  return 1;
+}
+
+// Orders `stream` behind the upload of `sd` (no-op on the stream that uploaded it).
+int wait_sup_uploaded(Supervision* s, SupDevice* sd, cudaStream_t stream) {
+  if (sd->upload_stream == stream) return 1;
+  std::lock_guard<std::mutex> lock(s->mu);
+  CUDA_OK(cudaStreamWaitEvent(stream, sd->uploaded, 0));
+  return 1;
+}
+
+// Marks `stream`'s work enqueued so far as a reader of the block (see SupBlock::last_use).
+int mark_sup_used(Supervision* s, SupDevice* sd, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(s->mu);
+  cudaEvent_t& ev = sd->block->last_use[stream];
+  if (!ev) CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  CUDA_OK(cudaEventRecord(ev, stream));
   return 1;
 }
 
@@ -1082,9 +1229,11 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   SupDevice* sd;
   Workspace* ws;
   if (!get_den_device(g, device, &dd)) return 0;
-  if (!get_sup_device(sup, device, &sd)) return 0;
+  if (!get_sup_device(sup, device, stream, &sd)) return 0;
+  if (!wait_sup_uploaded(sup, sd, stream)) return 0;
   if (!get_workspace(g, device, (void*)stream, &ws)) return 0;
   WorkspaceLease lease{g, ws};
+  std::lock_guard<std::mutex> one_call(ws->call_mu);  // released before `lease` (reverse declaration order)
   const bool want_xent = xent != nullptr && xent_regularize != 0.f;
 
   if (!deriv) {  // objective only: derivatives go to scratch
@@ -1218,10 +1367,6 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
     ws->trace_frames = T + 1;
     ws->trace_grid = dd->grid;
   }
-  {
-    const char* dbg = getenv("TORCHAIN_DEBUG_FLAGS");
-    dp.debug_flags = dbg ? atoi(dbg) : 0;
-  }
   dp.timeline = g_profile.load() ? reinterpret_cast<unsigned long long*>(zb + z_tl) : nullptr;
   ws->timeline_dev = zb + z_tl;
   ws->timeline_len = 2 * T + 6;
@@ -1236,9 +1381,8 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
     if (!partition_for(dp.subs, &part)) return 0;
     bind(part);
     // arc / task slices are staged in shared memory unless the graph is too large for it
-    // (TORCHAIN_FORCE_UNSTAGED=1 exercises the global-memory path on small graphs)
     dp.arcs_in_smem = 1;
-    if (tb::den_smem_bytes(dp) > 200 * 1024 || getenv("TORCHAIN_FORCE_UNSTAGED")) dp.arcs_in_smem = 0;
+    if (tb::den_smem_bytes(dp) > 200 * 1024 || g->hooks.force_unstaged) dp.arcs_in_smem = 0;
     for (int ci = 0; ci < 2; ci++) {
       tb::DenParams& c = batch.c[ci];
       c = dp;
@@ -1265,12 +1409,11 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
       // The numerator runs on a side stream, on the registers the forward launch leaves free.
       // It needs all of nnet_output: resident from the start in the device entry, after the
       // last chunk has landed in the host-buffer entry (event recorded on the copy stream).
+      CUDA_OK(cudaEventRecord(ws->ev_fork, stream));  // behind the supervision upload and the memsets
+      CUDA_OK(cudaStreamWaitEvent(ws->side, ws->ev_fork, 0));
       if (chunked.all_landed) {
         CUDA_OK(cudaStreamWaitEvent(ws->side, chunked.all_landed, 0));
         if (chunked.all_landed2) CUDA_OK(cudaStreamWaitEvent(ws->side, chunked.all_landed2, 0));
-      } else {
-        CUDA_OK(cudaEventRecord(ws->ev_fork, stream));
-        CUDA_OK(cudaStreamWaitEvent(ws->side, ws->ev_fork, 0));
       }
       CUDA_OK(tb::launch_numerator(np, ws->side));
       CUDA_OK(cudaEventRecord(ws->ev_join, ws->side));
@@ -1323,6 +1466,7 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   fp.arc_pdf = sd->arc_pdf.as<int>();
   fp.arc_post = np.arc_post;
   CUDA_OK(tb::launch_final(fp, stream));
+  if (!mark_sup_used(sup, sd, stream)) return 0;  // the numerator's side stream joined `stream` before the backward launch
   if (results_dev_user)
     CUDA_OK(cudaMemcpyAsync(results_dev_user, res_dev, 3 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   if (chunked.results4_dev)
@@ -1671,6 +1815,16 @@ void* torchain_supervision_merge(void* const* sups, int32_t n) try {
   return out.release();
 } catch (...) {
   return abi_exception_ptr();
+}
+
+int torchain_supervision_prefetch(void* sup, int device, void* stream) try {
+  if (!sup) return fail("null supervision handle");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail("cannot select CUDA device");
+  SupDevice* sd = nullptr;
+  return get_sup_device(static_cast<Supervision*>(sup), device, static_cast<cudaStream_t>(stream), &sd);
+} catch (...) {
+  return abi_exception_int();
 }
 
 void my_lib_supervision_free(void* p) { delete static_cast<Supervision*>(p); }

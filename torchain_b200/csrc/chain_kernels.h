@@ -88,11 +88,10 @@ struct DenParams {
   const unsigned* y_ready;
   int y_chunk_frames;
   // host-buffer entry only: mapped pinned counter; after the grid barrier of backward step t the
-  // derivative rows of frames > t are complete and the kernel publishes T-1-t here (at the start of
-  // step t-1, and once more after the last barrier), so the host can start copying finished frame
-  // chunks out while the recurrence is still running.  null = unused.
+  // derivative rows of frames > t are complete and the kernel publishes T-1-t here with a system-scope
+  // release (at the start of step t-1, and once more after the last barrier), so the host can start
+  // copying finished frame chunks out while the recurrence is still running.  null = unused.
   unsigned* deriv_progress;
-  int debug_flags;    // timing experiments only (TORCHAIN_DEBUG_FLAGS): 1 = skip the aux-warp work of the backward launch (wrong results)
   unsigned long long* warp_busy;  // [2][grid][kDenWarps] SM cycles each warp spent in its frame work (feeds the partition autotuner)
   unsigned long long* cta_trace;  // optional [phase][frame][cta][4]: main warp 0 done, aux warp 0 done, CTA done, barrier exit
   unsigned long long* timeline;  // optional: globaltimer at every phase boundary (2T+5 entries), or null

@@ -140,6 +140,19 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned* ptr) {
   return v;
 }
 
+// Flags written by the copy engine (host-buffer entry) are released at system scope.
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* ptr) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+// Publishes a progress word to the host (mapped pinned memory): everything this thread has observed --
+// including other CTAs' derivative rows, through the grid barrier it sits behind -- is visible to a host
+// thread (and to copies that thread enqueues afterwards) that reads the new value.
+__device__ __forceinline__ void st_release_sys(unsigned* ptr, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -190,6 +203,11 @@ __device__ __forceinline__ void cta_reduce_to(const float* red, int BP, int rows
 
 // Transpose frame t of nnet_output (rows frame*Btot+seq, pdf innermost) into
 // etile[pdf][seq] = exp(y) through padded shared memory.
+// nnet_output is read with ld.global.cg (L2 only), never ld.global.nc: in the host-buffer entry the
+// copy engine is still writing later frames of the same buffer while this launch runs, and a 32-byte
+// sector can straddle two frames (B*P not a multiple of 8), so the matrix is not read-only for the
+// lifetime of the kernel and a line cached in L1 could go stale.  Every element is read once per
+// launch, so nothing is lost by skipping L1.
 __device__ __forceinline__ void stage_exp_tile(const DenParams& p, int t, float* etile, float* tile, int i, int lane,
                                                bool want_sq, double& sumsq) {
   const int BP = p.BP;
@@ -231,7 +249,7 @@ __device__ __forceinline__ void flush_gamma_tile(const DenParams& p, int frame, 
   const bool want_y = p.scale_y != 0.f;
 #pragma unroll
   for (int j = 0; j < 32; j++)
-    yv[j] = (want_y && s0 + j < p.B && pdf < p.P) ? __ldg(ycol + (int64_t)j * p.yl.s) : 0.f;
+    yv[j] = (want_y && s0 + j < p.B && pdf < p.P) ? __ldcg(ycol + (int64_t)j * p.yl.s) : 0.f;
 #pragma unroll
   for (int k = 0; k < 32; k++) {
     if (p0 + k < p.P) gtile[(size_t)(p0 + k) * BP + s0 + lane] = 0.f;
@@ -265,7 +283,7 @@ __device__ __forceinline__ void aux_work(const DenParams& p, int flush_frame, in
   if (stage_frame >= 0 && p.y_ready != nullptr) {  // host-buffer entry: wait until this frame's chunk has landed
     if (lane == 0) {
       const unsigned* flag = p.y_ready + stage_frame / p.y_chunk_frames;
-      while (ld_acquire(flag) == 0u) {
+      while (ld_acquire_sys(flag) == 0u) {
       }
     }
     __syncwarp();
@@ -826,18 +844,18 @@ __device__ __forceinline__ void den_chain_body(const DenBatch& batch) {
           if (t < T - 1) trace_frame_end(t + 1);
           stamp();
         }
-        if (ci == NCTX - 1 && t < T - 1 && p0.deriv_progress && blockIdx.x == 0 && threadIdx.x == 0) {
-          // the derivative rows of frames > t+1 are complete in every context
-          // A plain posted store: the rows it announces were made visible by the grid barrier this
-          // thread has just acquired, and nothing after it depends on when it lands.  (A system-scope
-          // fence here kept thread 0 of CTA 0 -- and with it every frame -- waiting for the PCIe write:
-          // 65 us per call, profiles/r01_host_trace.txt.)
-          *reinterpret_cast<volatile unsigned*>(p0.deriv_progress) = (unsigned)(T - 2 - t);
-          if (p0.debug_flags & 2) __threadfence_system();
+        if (ci == NCTX - 1 && t < T - 1 && p0.deriv_progress && blockIdx.x == 0 && warp == kDenMainWarps && lane == 0) {
+          // The derivative rows of frames > t+1 are complete in every context: every CTA wrote them before
+          // it arrived at the barrier thread 0 of this CTA has just acquired, and the bar.sync inside wait()
+          // orders that acquire before this store.  The release is at SYSTEM scope because the reader is
+          // the host (which then enqueues copy-engine reads of those rows).  It is issued by an aux-warp
+          // lane: on thread 0 -- the barrier thread -- the fence in front of the store held every frame
+          // back by the PCIe round trip (65 us per call, profiles/r01_host_trace.txt); the aux warps have
+          // that much slack in every frame.
+          st_release_sys(p0.deriv_progress, (unsigned)(T - 2 - t));
         }
         if (is_aux) {
-          if (!(p.debug_flags & 1))
-            aux_work(p, t + 1 < T ? t + 1 : -1, t - 1, tile, auxw, lane, false, sumsq, false, gsum, t);
+          aux_work(p, t + 1 < T ? t + 1 : -1, t - 1, tile, auxw, lane, false, sumsq, false, gsum, t);
         } else {
           const long long c0 = clock64();
           beta_step<V, SUBS, SPLIT>(p, arcs, tasks, abeg, aend, tb, te, t, sm.red, warp, lane, ab);
@@ -853,8 +871,8 @@ __device__ __forceinline__ void den_chain_body(const DenBatch& batch) {
     trace_frame_end(0);
     stamp();
     // step 0 is complete everywhere: only frame 0 is still to be flushed (below), so the host may copy frame 1 out
-    if (p0.deriv_progress && blockIdx.x == 0 && threadIdx.x == 0)
-      *reinterpret_cast<volatile unsigned*>(p0.deriv_progress) = (unsigned)(T - 1);
+    if (p0.deriv_progress && blockIdx.x == 0 && warp == kDenMainWarps && lane == 0)
+      st_release_sys(p0.deriv_progress, (unsigned)(T - 1));
 
     // ---- epilogue: frame 0's derivative rows, sanity sums
     if (is_aux) {
