@@ -8,7 +8,12 @@ forward-backward + denominator alpha/beta + derivative, incl. the negation the
 reference's backward() does) over one synthetic minibatch of BASELINE.json
 config 2 ("chime5": P=2928, N=10000, A~300k, B=128 x T=50 per GPU, leaky 0.1,
 l2 5e-5).  N>1: one process per GPU (torchrun), each rank owns B sequences
-(weak scaling), the 3 result scalars are all-reduced over NCCL every step.
+(weak scaling), the 3 result scalars are all-reduced over NCCL every step by the
+package's distributed op (torchain_b200.distributed.sharded_step).  The line also
+carries: a parity block (the step's results against the fp64 oracle, every rank),
+the step with a NEW Supervision handle per minibatch (fresh_supervision_*), and
+the other BASELINE.json configurations on the same launch geometry as flat keys
+(cfg3_strong_*: 512 sequences split over the ranks; cfg4_*: large tree).
 
 Reference arm (--impl reference): the Kaldi-CPU-equivalent restatement
 (oracle/, kaldi_fp32 mode) on the host cores, bounded sample, rank 0 only.
@@ -216,10 +221,104 @@ def run_reference(args):
     emit(line)
 
 
+class Runner:
+    """One workload resident on this rank's GPU: handles, nnet_output, derivative, and the step the bench times.
+
+    A step is one ComputeChainObjfAndDeriv-equivalent call (derivative negated in-kernel, what the reference's
+    backward() returns).  N=1: `torchain_ComputeChainObjfAndDeriv_ex` with the three results delivered to the host
+    (the reference's call semantics: ChainResults.data is a CPU tensor).  N>1: the package's distributed op
+    (`torchain_b200.distributed.sharded_step`): results stay on the device, NCCL sums them in place, one
+    device-to-host read."""
+
+    def __init__(self, torch, lib, c, dev, local, world, rank):
+        from torchain_b200 import io
+        self.torch, self.lib, self.c, self.dev, self.local, self.world = torch, lib, c, dev, local, world
+        den, sup = c["den"], c["sup"]
+        self.B, self.T, self.P = c["B"], c["T"], c["P"]
+        self.g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
+                                                 den.final_cost, den.num_pdfs)
+        self.s = self.new_supervision(sup)
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        self.y = torch.randn(self.T * self.B, self.P, device=dev, generator=gen) * 2.0
+        self.deriv = torch.empty_like(self.y)
+        self.res_dev = torch.zeros(3, device=dev)
+        self.res_host = np.zeros(3, dtype=np.float32)
+        self.stream = torch.cuda.current_stream(dev)
+
+    def new_supervision(self, sup):
+        from torchain_b200 import io
+        return io.Supervision.from_arrays(sup.weight, sup.num_sequences, sup.frames_per_sequence, sup.label_dim,
+                                          sup.arc_begin, sup.arc_dst, sup.arc_label, sup.arc_cost, sup.final_cost)
+
+    def step(self, host_results=False, s=None):
+        # Multi-GPU steps take the results on the device (they are all-reduced first); the warm-up
+        # steps ask for host results on every rank too, because only a synchronising call lets the
+        # library read back its per-warp busy counters and calibrate the partition (DESIGN.md 4.1) --
+        # what the Python op (chain_loss) does on every call.
+        c, s = self.c, (s or self.s)
+        if self.world == 1 or host_results:
+            ok = self.lib.torchain_ComputeChainObjfAndDeriv_ex(
+                self.g.ptr, s.ptr, self.y.data_ptr(), self.T * self.B, self.P, self.y.stride(0),
+                self.res_host.ctypes.data_as(ctypes.c_void_p), self.res_dev.data_ptr(),
+                self.deriv.data_ptr(), self.deriv.stride(0), None, 0,
+                c["l2"], c["leaky"], 0.0, -1.0, self.local, ctypes.c_void_p(self.stream.cuda_stream))
+            if ok != 1:
+                from torchain_b200 import _lib
+                raise RuntimeError(_lib.last_error())
+        else:
+            from torchain_b200.distributed import sharded_step
+            sharded_step(self.g, s, self.y, self.deriv, self.res_dev, c["l2"], c["leaky"], None, -1.0)
+            self.res_host[:] = self.res_dev.cpu().numpy()   # the minibatch totals, one device-to-host read
+
+    def sync_all(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([v], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def time_steps(self, steps, warmup, step=None):
+        """ms per step: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks."""
+        torch = self.torch
+        step = step or self.step
+        for _ in range(warmup):
+            self.step(host_results=True)
+        self.sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for _ in range(steps):
+            step()
+        e1.record(self.stream)
+        self.sync_all()
+        return self.max_over_ranks(e0.elapsed_time(e1)) / steps
+
+
+def extra_config(torch, lib, name, B, T, dev, local, world, rank, steps=10):
+    """(ms per step, whole-job frames/s, gather frac of the 32 MB-table L2 peak is left to the caller) of another
+    BASELINE.json configuration on this launch geometry."""
+    c = make_workload(name, B, T, rank)
+    r = Runner(torch, lib, c, dev, local, world, rank)
+    ms = r.time_steps(steps, 4)
+    out = {"ms_per_step": ms, "frames_per_sec": world * c["B"] * c["T"] / (ms * 1e-3),
+           "gather_gbs": alg_bytes(c)[1] * c["B"] * c["T"] / (ms * 1e-3) / 1e9,
+           "objf": float(r.res_host[0]), "weight": float(r.res_host[2])}
+    del r
+    lib.torchain_supervision_pool_trim()
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from torchain_b200 import _lib, io
+    from concurrent.futures import ThreadPoolExecutor
+    from torchain_b200 import _lib, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -234,37 +333,9 @@ def run_b200(args):
     c = make_workload(args.config, args.batch, args.frames, rank)
     den, sup = c["den"], c["sup"]
     B, T, P = c["B"], c["T"], c["P"]
-    g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
-                                        den.final_cost, den.num_pdfs)
-    s = io.Supervision.from_arrays(sup.weight, B, T, sup.label_dim, sup.arc_begin, sup.arc_dst, sup.arc_label,
-                                   sup.arc_cost, sup.final_cost)
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    y = torch.randn(T * B, P, device=dev, generator=gen) * 2.0
-    deriv = torch.empty_like(y)
-    res_dev = torch.zeros(3, device=dev)
-    res_host = np.zeros(3, dtype=np.float32)
-    stream = torch.cuda.current_stream(dev)
-
-    def step(host_results=False):
-        # Multi-GPU steps take the results on the device (they are all-reduced first); the warm-up
-        # steps ask for host results on every rank too, because only a synchronising call lets the
-        # library read back its per-warp busy counters and calibrate the partition --
-        # what the Python op (chain_loss) does on every call.
-        ok = lib.torchain_ComputeChainObjfAndDeriv_ex(
-            g.ptr, s.ptr, y.data_ptr(), T * B, P, y.stride(0),
-            res_host.ctypes.data_as(ctypes.c_void_p) if (world == 1 or host_results) else None, res_dev.data_ptr(),
-            deriv.data_ptr(), deriv.stride(0), None, 0,
-            c["l2"], c["leaky"], 0.0, -1.0, local, ctypes.c_void_p(stream.cuda_stream))
-        if ok != 1:
-            raise RuntimeError(_lib.last_error())
-        if world > 1:  # the path's only exchange: objf / l2_term / weight summed over ranks
-            dist.all_reduce(res_dev)
-            res_host[:] = res_dev.cpu().numpy()
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+    R = Runner(torch, lib, c, dev, local, world, rank)
+    g, s, y, deriv, res_host, stream = R.g, R.s, R.y, R.deriv, R.res_host, R.stream
+    step, sync_all = R.step, R.sync_all
 
     for _ in range(max(args.warmup, 3)):
         step(host_results=True)
@@ -288,12 +359,49 @@ def run_b200(args):
     den_ms, den_n = ctypes.c_double(0), ctypes.c_int64(0)
     lib.torchain_profile_read(g.ptr, ctypes.byref(den_ms), ctypes.byref(den_n), 1)
     lib.torchain_profile_enable(0)
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    ms_per_step = ms / args.steps
+    ms_per_step = R.max_over_ranks(ms) / args.steps
     value = world * B * T / (ms_per_step * 1e-3)
+    step_results = res_host.copy()
+
+    # ---- the same step with the per-minibatch host work inside the timed region: a NEW Supervision handle every
+    # step (validation, state times, per-sequence split, CSR both ways, device upload), as a training loop has it
+    # (/root/reference/example/chime5/train_faster.py:116-141 takes a new supervision from its reader every step).
+    # A worker thread builds and prefetches handle k+1 (asynchronous upload on its own stream into a pooled block)
+    # while step k runs; `serial` builds it inline, for contrast.
+    fresh = None
+    if not args.no_fresh_supervision:
+        sups_np = [sup] + [synth.make_supervision(5000 + 1000 * rank + k, den, B, T, num_paths=4, weight=1.0)
+                           for k in range(3)]
+        side = torch.cuda.Stream(dev)
+        pool = ThreadPoolExecutor(max_workers=1)
+
+        def build(k):
+            torch.cuda.set_device(local)
+            return R.new_supervision(sups_np[k % len(sups_np)]).prefetch(local, side)
+
+        n_fresh = max(4, min(args.steps, 20))
+        for mode in ("overlapped", "serial"):
+            for timed in (False, True):
+                k, fut = 0, (pool.submit(build, 0) if mode == "overlapped" else None)
+                sync_all()
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record(stream)
+                for _ in range(n_fresh if timed else 2):
+                    if mode == "overlapped":
+                        h, fut = fut.result(), pool.submit(build, k + 1)
+                    else:
+                        h = R.new_supervision(sups_np[k % len(sups_np)])
+                    step(s=h)
+                    del h
+                    k += 1
+                ev1.record(stream)
+                sync_all()
+                if mode == "overlapped":
+                    fut.result()
+            t_ms = R.max_over_ranks(ev0.elapsed_time(ev1)) / n_fresh
+            fresh = dict(fresh or {}, **{mode + "_ms_per_step": t_ms})
+        pool.shutdown()
+        lib.torchain_supervision_pool_trim()
 
     # ---- e2e: the reference-facing C-ABI call with HOST (pinned) buffers, copies inside the timed region
     y_pin = torch.empty(T * B, P, pin_memory=True)
@@ -318,33 +426,31 @@ def run_b200(args):
     torch.cuda.synchronize(dev)
     e2e_s = (time.perf_counter() - t0) / n_e2e
     clocks = sampler.stop() if rank == 0 else None   # sampled over the device-timed AND the e2e-timed loops
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * T / float(te.item())
+    e2e_s = R.max_over_ranks(e2e_s)
+    e2e_value = world * B * T / e2e_s
 
     # ---- parity: this rank's shard against the fp64 oracle on the same inputs (outside the timed regions)
     parity = None
     if not args.no_parity:
-        step(host_results=True)            # un-reduced results of this rank's own shard
+        ok = lib.torchain_ComputeChainObjfAndDeriv_ex(
+            g.ptr, s.ptr, y.data_ptr(), T * B, P, y.stride(0), res_host.ctypes.data_as(ctypes.c_void_p), None,
+            deriv.data_ptr(), deriv.stride(0), None, 0, c["l2"], c["leaky"], 0.0, -1.0, local,
+            ctypes.c_void_p(stream.cuda_stream))          # un-reduced results of this rank's own shard
+        if ok != 1:
+            raise RuntimeError(_lib.last_error())
         torch.cuda.synchronize(dev)
-        local_res = res_host.copy() if world == 1 else None
-        if world > 1:                      # step() overwrote res_host with the all-reduced values
-            ok = lib.torchain_ComputeChainObjfAndDeriv_ex(
-                g.ptr, s.ptr, y.data_ptr(), T * B, P, y.stride(0), res_host.ctypes.data_as(ctypes.c_void_p), None,
-                deriv.data_ptr(), deriv.stride(0), None, 0, c["l2"], c["leaky"], 0.0, -1.0, local,
-                ctypes.c_void_p(stream.cuda_stream))
-            if ok != 1:
-                raise RuntimeError(_lib.last_error())
-            local_res = res_host.copy()
-        parity = parity_check(c, sup, y.cpu().numpy(), local_res, deriv.cpu().numpy(),
+        parity = parity_check(c, sup, y.cpu().numpy(), res_host.copy(), deriv.cpu().numpy(),
                               max(1, host_cores() // world))
         d_host = d_pin.numpy()             # the e2e entry's derivative (not negated) must be the same matrix
         parity["e2e_deriv_vs_device_rel"] = float(
             np.abs(d_host + deriv.cpu().numpy()).max() / max(np.abs(d_host).max(), 1e-30))
         parity["e2e_objf_rel_err"] = abs(float(r_e2e[0]) - parity["oracle_objf"]) / abs(parity["oracle_objf"])
         parity["ok"] = bool(parity["ok"] and parity["e2e_deriv_vs_device_rel"] < 1e-4 and parity["e2e_objf_rel_err"] < 1e-5)
-        if world > 1:                      # worst rank
+        if world > 1:                      # worst rank; and the all-reduced totals against the sum of the oracles
+            tot = torch.tensor([parity["oracle_objf"]], device=dev, dtype=torch.float64)
+            dist.all_reduce(tot)
+            parity["reduced_objf_rel_err"] = abs(float(step_results[0]) - float(tot.item())) / abs(float(tot.item()))
+            parity["ok"] = bool(parity["ok"] and parity["reduced_objf_rel_err"] < 1e-5)
             keys = ["objf_rel_err", "l2_rel_err", "weight_rel_err", "deriv_rel_err", "e2e_deriv_vs_device_rel",
                     "e2e_objf_rel_err", "oracle_s"]
             tmax = torch.tensor([parity[k] for k in keys] + [0.0 if parity["ok"] else 1.0], device=dev,
@@ -356,6 +462,24 @@ def run_b200(args):
             parity["ranks_checked"] = world
         parity["tolerances"] = "objf, l2_term 1e-5 relative; derivative 1e-4 of max |oracle derivative|"
         parity["oracle"] = "oracle/chain_oracle.cpp fp64 mode, every rank's own shard, max over ranks"
+
+    # ---- the other BASELINE.json configurations on this launch geometry (flat keys on the same line):
+    # cfg 3 = 512 sequences in total, strong-split over the ranks; cfg 4 = large tree, 256 sequences per GPU
+    extras = {}
+    if not args.no_extra_configs and args.config == "chime5" and not args.batch and not args.frames:
+        del R
+        torch.cuda.empty_cache()
+        if 512 % world == 0:
+            e3 = extra_config(torch, lib, "chime5", 512 // world, 50, dev, local, world, rank)
+            extras.update(cfg3_strong_total_seqs=512, cfg3_strong_seqs_per_gpu=512 // world,
+                          cfg3_strong_ms_per_step=e3["ms_per_step"], cfg3_strong_frames_per_sec=e3["frames_per_sec"],
+                          cfg3_strong_gather_gbs_per_gpu=e3["gather_gbs"])
+        e4 = extra_config(torch, lib, "large_tree", 0, 0, dev, local, world, rank)
+        extras.update(cfg4_seqs_per_gpu=256, cfg4_ms_per_step=e4["ms_per_step"],
+                      cfg4_frames_per_sec=e4["frames_per_sec"], cfg4_gather_gbs_per_gpu=e4["gather_gbs"])
+        if world == 8:   # cfg 5's small end: 64 sequences over 8 GPUs
+            e5 = extra_config(torch, lib, "chime5", 8, 50, dev, local, world, rank)
+            extras.update(cfg5_64seqs_ms_per_step=e5["ms_per_step"], cfg5_64seqs_frames_per_sec=e5["frames_per_sec"])
 
     if rank != 0:
         if world > 1:
@@ -410,19 +534,26 @@ def run_b200(args):
             "name": args.config, "parallelism": "seq-shard x%d" % world,
             "l2_policy": "working set per step (y+deriv+alpha store = %.2f GB) exceeds the 126 MB L2; no flush" % (
                 (2 * T * B * P * 4 + (T + 1) * c["N"] * B * 4) / 1e9)},
-        "results": {"objf": float(res_host[0]), "l2_term": float(res_host[1]), "weight": float(res_host[2])},
+        "objf": float(step_results[0]), "l2_term": float(step_results[1]), "weight": float(step_results[2]),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": T * B * P * 4,
-                "d2h_bytes_per_step": T * B * P * 4 + 12, "ms_per_step": float(te.item()) * 1e3,
+                "d2h_bytes_per_step": T * B * P * 4 + 12, "ms_per_step": e2e_s * 1e3,
                 "api": "torchain_ComputeChainObjfAndDeriv_host (pinned host nnet_output in, derivative + results out)"},
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
+    if fresh:
+        line["fresh_supervision_ms_per_step"] = fresh["overlapped_ms_per_step"]
+        line["fresh_supervision_serial_ms_per_step"] = fresh["serial_ms_per_step"]
+        line["fresh_supervision_vs_step"] = fresh["overlapped_ms_per_step"] / ms_per_step
+    line.update(extras)
     if cpu:
         line["cpu_baseline"] = cpu
     if parity:
         line["parity"] = parity
-        # flat copies inside `config`, which survives the driver's parser whole
+        # flat copies at top level and inside `config` (which survives the driver's parser whole)
+        line.update(parity_ok=parity["ok"], parity_objf_rel_err=parity["objf_rel_err"],
+                    parity_deriv_rel_err=parity["deriv_rel_err"])
         line["config"].update(parity_ok=parity["ok"], parity_objf_rel_err=parity["objf_rel_err"],
                               parity_deriv_rel_err=parity["deriv_rel_err"])
     emit(line)
@@ -464,6 +595,8 @@ def main():
     ap.add_argument("--frames", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the fp64-oracle check of the step's results")
+    ap.add_argument("--no-fresh-supervision", action="store_true", help="skip the new-Supervision-per-step loops")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip cfg 3 (strong split) / cfg 4 extras")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -112,6 +112,10 @@ void* torchain_supervision_merge(void* const* supervision_ptrs, int32_t n);
  * Supervision per minibatch, /root/reference/example/chime5/train_faster.py:116-141). */
 int torchain_supervision_prefetch(void* supervision_ptr, int device, void* stream);
 
+/* Frees the pooled supervision blocks no handle is using (at most 8 are kept; like
+ * torch.cuda.empty_cache() for this library's one pool).  Waits for the device. */
+void torchain_supervision_pool_trim(void);
+
 /* The reference's reader-based constructors; egs reading is out of scope, so
  * these always return NULL and set the error string. */
 void* my_lib_supervision_new(void* reader_ptr);

@@ -115,3 +115,75 @@ def test_gpu_shards_equal_full_batch():
     assert parts[0][0][2] + parts[1][0][2] == pytest.approx(full[2])
     d_all = synth.interleave_rows([parts[0][1], parts[1][1]], Bs)
     assert np.abs(d_all - dfull).max() < 1e-4 * np.abs(dfull).max()
+
+
+def _nccl_worker(rank, world, port, out):
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from torchain_b200 import io
+    from torchain_b200.distributed import chain_loss_distributed
+    den, sups, ys, Bs, T = _case()
+    sp = sups[rank]
+    g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
+                                        den.final_cost, den.num_pdfs)
+    s = io.Supervision.from_arrays(sp.weight, sp.num_sequences, sp.frames_per_sequence, sp.label_dim, sp.arc_begin,
+                                   sp.arc_dst, sp.arc_label, sp.arc_cost, sp.final_cost)
+    y = torch.from_numpy(ys[rank]).cuda().requires_grad_(True)
+    loss, results = chain_loss_distributed(y, g, s, l2_regularize=0.01, leaky_hmm_coefficient=0.1)
+    loss.backward()
+    torch.cuda.synchronize()
+    out[rank] = (results.data.numpy().copy(), float(loss), y.grad.cpu().numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_nccl_chain_loss_distributed_two_gpus():
+    """The distributed op itself under NCCL (run with `gpurun --gpus 2`): every rank's ChainResults describe the
+    merged minibatch (objf / l2_term / weight summed on the device), gradients stay rank-local."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    den, sups, ys, Bs, T = _case()
+    merged = synth.append_supervisions(sups)
+    y_all = synth.interleave_rows(ys, Bs)
+    full = ol.chain(ol.OracleDen(den), ol.OracleSup(merged), y_all, l2=0.01, leaky=0.1, mode="fp64")
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_nccl_worker, args=(2, port, out), nprocs=2, join=True)
+    for rank in range(2):
+        data, loss, _ = out[rank]
+        assert data[0] == pytest.approx(full["objf"], rel=1e-5)
+        assert data[1] == pytest.approx(full["l2_term"], rel=1e-5)
+        assert data[2] == pytest.approx(full["weight"])
+        assert loss == pytest.approx(-full["objf"] / full["weight"], rel=1e-5)
+    d_all = synth.interleave_rows([out[0][2], out[1][2]], Bs)
+    assert np.abs(d_all + full["deriv"]).max() < 1e-4 * np.abs(full["deriv"]).max()
+
+
+@pytest.mark.gpu
+def test_gpu_sharded_step_leaves_results_on_the_device():
+    """Single process: the sharded op is the plain op plus a no-op reduction; results arrive in device memory and
+    the call never synchronises."""
+    from torchain_b200 import io
+    from torchain_b200.distributed import chain_loss_distributed, sharded_step
+    den, sups, ys, Bs, T = _case()
+    sp, y_np = sups[0], ys[0]
+    ref = ol.chain(ol.OracleDen(den), ol.OracleSup(sp), y_np, l2=0.01, leaky=0.1, mode="fp64")
+    g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
+                                        den.final_cost, den.num_pdfs)
+    s = io.Supervision.from_arrays(sp.weight, sp.num_sequences, sp.frames_per_sequence, sp.label_dim, sp.arc_begin,
+                                   sp.arc_dst, sp.arc_label, sp.arc_cost, sp.final_cost)
+    y = torch.from_numpy(y_np).cuda()
+    d = torch.empty_like(y)
+    res = torch.zeros(3, device="cuda")
+    sharded_step(g, s, y, d, res, 0.01, 0.1)
+    assert res.cpu()[0].item() == pytest.approx(ref["objf"], rel=1e-5)
+    assert np.abs(d.cpu().numpy() + ref["deriv"]).max() < 1e-4 * np.abs(ref["deriv"]).max()
+    yg = y.clone().requires_grad_(True)
+    loss, results = chain_loss_distributed(yg, g, s, l2_regularize=0.01, leaky_hmm_coefficient=0.1)
+    (loss * 7.0).backward()
+    assert float(results.data[0]) == pytest.approx(ref["objf"], rel=1e-5)
+    assert np.abs(yg.grad.cpu().numpy() + ref["deriv"]).max() < 1e-4 * np.abs(ref["deriv"]).max()

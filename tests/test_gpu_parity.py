@@ -754,3 +754,122 @@ def test_reference_training_loop():
     g, s = handles(den, sup)
     hist = ts.run_sgd(chain_loss, g, s, x, den.num_pdfs, "cuda")
     ts.check_history(hist, sup.num_sequences, sup.frames_per_sequence)
+
+
+def test_host_buffer_entry_odd_row_bytes():
+    """B*P not a multiple of 8 floats (B=3, P=61: 732 bytes per frame): 32-byte sectors straddle frame -- and chunk --
+    boundaries, so while the forward launch reads frame t the copy engine may still be writing the other half of the
+    same sector.  nnet_output is therefore read with ld.global.cg, never through the non-coherent path."""
+    den = synth.make_den_fst(31, 300, 61, mean_deg=5.0)
+    B, T = 3, 40
+    sup = synth.make_supervision(32, den, B, T, num_paths=3, weight=1.0)
+    y = synth.make_nnet_output(33, B, T, den.num_pdfs, scale=1.5)
+    r = ol.chain(ol.OracleDen(den), ol.OracleSup(sup), y, l2=5e-5, leaky=0.1, mode="fp64")
+    g, s = handles(den, sup)
+    for _ in range(5):
+        res, d = _host_entry(g, s, y, 5e-5, 0.1)
+        assert rel(res[0], r["objf"]) < OBJF_RTOL
+        assert deriv_err(d, r["deriv"]) < DERIV_RTOL
+
+
+def test_gpu_two_threads_one_stream():
+    """Two host threads calling on the SAME (device, stream) -- the legacy default stream -- share one workspace
+    (alpha store, zeroed scalars, barrier counters, pinned result words); the calls must serialise, not interleave."""
+    import threading
+    import torch
+    lib = _lib.load()
+    cases = []
+    for k in range(2):
+        den = synth.make_den_fst(40 + k, 400, 50, mean_deg=5.0) if k == 0 else cases[0][0]
+        sup = synth.make_supervision(50 + k, den, 20 + 7 * k, 12, num_paths=3, weight=1.0)
+        y = synth.make_nnet_output(60 + k, sup.num_sequences, 12, den.num_pdfs, scale=1.5)
+        r = ol.chain(ol.OracleDen(den), ol.OracleSup(sup), y, l2=5e-5, leaky=0.1, mode="fp64")
+        cases.append((den, sup, y, r))
+    den = cases[0][0]
+    g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
+                                        den.final_cost, den.num_pdfs)
+    sups = [io.Supervision.from_arrays(c[1].weight, c[1].num_sequences, 12, c[1].label_dim, c[1].arc_begin,
+                                       c[1].arc_dst, c[1].arc_label, c[1].arc_cost, c[1].final_cost) for c in cases]
+    ys = [torch.from_numpy(c[2]).cuda() for c in cases]
+    ds = [torch.empty_like(y) for y in ys]
+    torch.cuda.synchronize()
+    errors = []
+
+    def work(k):
+        try:
+            res = np.zeros(3, dtype=np.float32)
+            for _ in range(30):
+                ds[k].fill_(float("nan"))
+                ok = lib.my_lib_ComputeChainObjfAndDeriv(
+                    g.ptr, sups[k].ptr, ys[k].data_ptr(), ys[k].shape[0], ys[k].shape[1], ys[k].stride(0),
+                    res.ctypes.data_as(ctypes.c_void_p), ds[k].data_ptr(), ds[k].stride(0), None, 0,
+                    5e-5, 0.1, 0.0, 0, None)     # stream 0: the legacy default stream, both threads
+                assert ok == 1, _lib.last_error()
+                assert rel(res[0], cases[k][3]["objf"]) < OBJF_RTOL, (k, res)
+                torch.cuda.synchronize()
+                assert deriv_err(ds[k].cpu().numpy(), cases[k][3]["deriv"]) < DERIV_RTOL
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
+def test_gpu_fresh_supervision_per_step_prefetched_from_a_worker_thread():
+    """A training loop builds a new Supervision for every minibatch
+    (/root/reference/example/chime5/train_faster.py:116-141).  Here a worker thread builds and prefetches
+    (asynchronous upload on its own stream) the next handle while the current step runs; handles die right after
+    their step, their pooled device blocks are reused by later minibatches while kernels of earlier ones may still
+    be running.  Every step must match the oracle."""
+    import threading
+    import torch
+    from torchain_b200.functions import chain_loss
+    den = synth.make_den_fst(71, 600, 80, mean_deg=6.0)
+    B, T, n_steps = 24, 16, 12
+    g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
+                                        den.final_cost, den.num_pdfs)
+    oden = ol.OracleDen(den)
+    sups = [synth.make_supervision(100 + k, den, B, T, num_paths=3, weight=1.0) for k in range(n_steps)]
+    y = synth.make_nnet_output(72, B, T, den.num_pdfs, scale=1.5)
+    refs = [ol.chain(oden, ol.OracleSup(sp), y, l2=5e-5, leaky=0.1, mode="fp64") for sp in sups]
+    yt = torch.from_numpy(y).cuda()
+    side = torch.cuda.Stream()
+    box = {}
+
+    def prepare(k):
+        sp = sups[k]
+        h = io.Supervision.from_arrays(sp.weight, B, T, sp.label_dim, sp.arc_begin, sp.arc_dst, sp.arc_label,
+                                       sp.arc_cost, sp.final_cost)
+        box[k] = h.prefetch(0, side)
+
+    prepare(0)
+    for k in range(n_steps):
+        worker = threading.Thread(target=prepare, args=(k + 1,)) if k + 1 < n_steps else None
+        if worker:
+            worker.start()
+        inp = yt.clone().requires_grad_(True)
+        loss, results = chain_loss(inp, g, box.pop(k), l2_regularize=5e-5, leaky_hmm_coefficient=0.1)
+        loss.backward()                      # the handle of step k is garbage from here on
+        assert rel(float(results.data[0]), refs[k]["objf"]) < OBJF_RTOL
+        assert deriv_err(inp.grad.cpu().numpy(), -refs[k]["deriv"]) < DERIV_RTOL
+        if worker:
+            worker.join()
+    _lib.load().torchain_supervision_pool_trim()
+
+
+def test_to2d_backward_accepts_any_gradient_layout():
+    """a row-broadcast gradient (strides (0, 1)) or a non-float one reaches _To2d.backward."""
+    import torch
+    from torchain_b200.functions import to2d
+    x = torch.randn(4, 33, 50, device="cuda", requires_grad=True)
+    to2d(x).sum(0).sum().backward()
+    assert torch.equal(x.grad, torch.ones_like(x))
+    x.grad = None
+    w = torch.randn(50 * 4, 33, device="cuda", dtype=torch.float64)
+    (to2d(x).double() * w).sum().backward()
+    ref = w.float().view(50, 4, 33).permute(1, 2, 0)
+    assert torch.allclose(x.grad, ref)

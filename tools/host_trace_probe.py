@@ -1,8 +1,6 @@
-"""Host-side timeline of the host-buffer entry (TORCHAIN_HOST_TRACE=1) on BASELINE.json config 2, for the
-default and for the experiment toggles of the entry: a system fence behind the progress counter
-(TORCHAIN_DEBUG_FLAGS=2), equal chunks (TORCHAIN_HOST_UNIFORM_CHUNKS=1), derivative copied out only after
-the backward launch (TORCHAIN_HOST_NO_PIPELINED_OUT=1), two copy streams (TORCHAIN_HOST_COPY_STREAMS=2),
-frame flags by memset / stream memory operation (TORCHAIN_HOST_FLAG_MODE=memset|write).  `end` of a trace line is the duration of the call."""
+"""Host-side timeline of the host-buffer entry (TORCHAIN_HOST_TRACE=1) on BASELINE.json config 2.  `end` of a trace
+line is the duration of the call.  (Round 2 measured the experiment variants of the entry with this tool --
+profiles/r02_host_trace_variants.txt -- kept two copy streams and deleted the rest.)"""
 import ctypes, os, sys
 import numpy as np
 os.environ["TORCHAIN_HOST_TRACE"] = "1"
@@ -43,14 +41,6 @@ def variant(name, env, n=6):
 
 
 variant("warm-up (partition calibration)", {}, 5)
-variant("default", {})
-variant("system fence behind the progress counter (the code before r01_host_trace)", {"TORCHAIN_DEBUG_FLAGS": "2"})
-variant("uniform chunks", {"TORCHAIN_HOST_UNIFORM_CHUNKS": "1"})
-variant("no pipelined output", {"TORCHAIN_HOST_NO_PIPELINED_OUT": "1"})
-variant("two copy streams", {"TORCHAIN_HOST_COPY_STREAMS": "2"})
-variant("frame flags by memset", {"TORCHAIN_HOST_FLAG_MODE": "memset"})
-variant("frame flags by cuStreamWriteValue32", {"TORCHAIN_HOST_FLAG_MODE": "write"})
-variant("two copy streams + cuStreamWriteValue32", {"TORCHAIN_HOST_COPY_STREAMS": "2", "TORCHAIN_HOST_FLAG_MODE": "write"})
-variant("default again", {})
+variant("default (chunks alternate between two copy streams, progress word released at system scope)", {}, 8)
 # results must not depend on the variant
 print("objf %.4f l2_term %.4f weight %.1f  deriv finite: %s" % (res[0], res[1], res[2], bool(torch.isfinite(d_pin).all())))

@@ -38,6 +38,7 @@ SIGNATURES = {
     "torchain_supervision_from_kaldi_bytes": (_c_p, [_c_p, _c_i64, _c_p]),
     "torchain_supervision_merge": (_c_p, [_c_p, _c_i32]),
     "torchain_supervision_prefetch": (_c_i, [_c_p, _c_i, _c_p]),
+    "torchain_supervision_pool_trim": (None, []),
     "my_lib_supervision_new": (_c_p, [_c_p]),
     "my_lib_supervision_rand_new": (_c_p, [_c_p]),
     "my_lib_supervision_free": (None, [_c_p]),

@@ -70,6 +70,10 @@ struct DevBuf {
     ptr = nullptr;
     bytes = 0;
   }
+  void abandon() {  // forget the allocation without touching the runtime (process / thread teardown)
+    ptr = nullptr;
+    bytes = 0;
+  }
   cudaError_t reserve(size_t n) {
     if (n <= bytes) return cudaSuccess;
     if (ptr) cudaFree(ptr);
@@ -594,7 +598,7 @@ class SupBlockPool {
     b->cap = align_up(bytes + bytes / 4, 1 << 16);  // headroom: the next minibatch is about this size
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&b->dev), b->cap);
     if (e != cudaSuccess) return e;
-    e = cudaMallocHost(reinterpret_cast<void**>(&b->pinned), b->cap);
+    e = cudaHostAlloc(reinterpret_cast<void**>(&b->pinned), b->cap, cudaHostAllocDefault);
     if (e != cudaSuccess) return e;
     *out = std::move(b);
     return cudaSuccess;
@@ -606,6 +610,13 @@ class SupBlockPool {
     if (free_.size() > kMaxFree) {  // oldest first
       shed = std::move(free_.front());
       free_.erase(free_.begin());
+    }
+  }
+  void trim() {  // frees every idle block (cudaFree waits for the device)
+    std::vector<std::unique_ptr<SupBlock>> all;
+    {
+      std::lock_guard<std::mutex> lock(mu_);
+      all.swap(free_);
     }
   }
 
@@ -1496,15 +1507,23 @@ struct HostPath {
   int device = -1;
   cudaStream_t compute = nullptr, copy = nullptr, copy2 = nullptr;
   cudaEvent_t ready = nullptr, landed = nullptr, landed2 = nullptr;
-  DevBuf y, deriv, xent, flags;
+  DevBuf y, deriv, xent, flags, results4;
   unsigned* ones = nullptr;      // pinned constant 1s, one per frame flag of a chunk
   int ones_cap = 0;
   unsigned* progress = nullptr;  // pinned, device-mapped: frames of the derivative already complete
   HostPath() = default;
   HostPath(const HostPath&) = delete;
   HostPath& operator=(const HostPath&) = delete;
-  // No destructor on purpose: a thread_local of the main thread dies during process teardown, when the
-  // CUDA runtime may already be gone; streams and events of an ending thread are left to the driver.
+  // A thread_local of the main thread dies during process teardown, when the CUDA runtime may already be
+  // gone: streams, events and pinned memory of an ending thread are left to the driver, and the device
+  // buffers are let go WITHOUT cudaFree (DevBuf::abandon) for the same reason.
+  ~HostPath() {
+    y.abandon();
+    deriv.abandon();
+    xent.abandon();
+    flags.abandon();
+    results4.abandon();
+  }
   void release() {  // everything belongs to `device`; called when the thread moves to another device
     if (compute) cudaStreamDestroy(compute);
     if (copy) cudaStreamDestroy(copy);
@@ -1523,6 +1542,7 @@ struct HostPath {
     deriv.release();
     xent.release();
     flags.release();
+    results4.release();
     device = -1;
   }
 };
@@ -1653,6 +1673,167 @@ Supervision* parse_kaldi_supervision(const void* data, int64_t nbytes, int64_t* 
   if (consumed) *consumed = (int64_t)(r.p - static_cast<const unsigned char*>(data));
   return make_supervision(weight, B, T, P, (int32_t)nstates, arc_begin.data(), arc_dst.data(), arc_label.data(),
                           arc_cost.data(), final_cost.data());
+}
+
+// Synchronises the three streams of the host-buffer entry when an error return leaves its scope, so that no copy
+// still reads or writes the caller's host buffers (and no kernel still waits for chunks) after the call returned.
+struct HostDrain {
+  HostPath& h;
+  bool armed = true;
+  ~HostDrain() {
+    if (!armed) return;
+    cudaStreamSynchronize(h.copy);
+    cudaStreamSynchronize(h.copy2);
+    cudaStreamSynchronize(h.compute);
+  }
+};
+
+int host_entry(DenGraph* g, Supervision* sp, const float* y_host, int64_t rows, int64_t cols, int64_t ystride,
+               float* results, float* deriv_host, int64_t dstride, float* xent_host, int64_t xstride, float l2,
+               float leaky, float xent_regularize, int device) {
+  HostPath& h = g_host;
+  if (h.device != device) {
+    h.release();
+    CUDA_OK(cudaStreamCreateWithFlags(&h.compute, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&h.copy, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&h.copy2, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&h.ready, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&h.landed, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&h.landed2, cudaEventDisableTiming));
+    CUDA_OK(cudaHostAlloc(&h.progress, sizeof(unsigned), cudaHostAllocMapped));
+    CUDA_OK(h.results4.reserve(4 * sizeof(float)));
+    h.device = device;
+  }
+  const size_t bytes = sizeof(float) * (size_t)rows * cols;
+  CUDA_OK(h.y.reserve(bytes));
+  const bool want_xent = xent_host != nullptr && xent_regularize != 0.f;
+  if (want_xent) CUDA_OK(h.xent.reserve(bytes));
+
+  // The derivative is produced in device memory and copied out chunk by chunk (whole frames)
+  // by the copy engine WHILE the backward recurrence is still running: the kernel publishes how
+  // many trailing frames are complete in a mapped pinned counter (system-scope release), this
+  // (blocked anyway) host thread polls it and enqueues the copies.  Only the chunk holding frame 0
+  // waits for the end.
+  float* deriv_dev = nullptr;
+  const int64_t deriv_dev_stride = cols;
+  if (deriv_host) {
+    CUDA_OK(h.deriv.reserve(bytes));
+    deriv_dev = h.deriv.as<float>();
+  }
+  // nnet_output goes up in chunks of whole frames (chunk_bounds), alternating between TWO copy streams
+  // (measured, profiles/r02_host_trace_variants.txt: 3.78 ms per call against 3.92 ms with one stream --
+  // the 4-byte flag copy behind every chunk no longer stalls the next chunk's transfer; setting the flags
+  // by memset or by stream memory operations instead made no difference and was dropped).  The forward
+  // launch starts as soon as the first chunk has landed and waits, per frame, on the flag of the frame it
+  // stages next.
+  const int T = sp->T, B = sp->B;
+  // TORCHAIN_HOST_TRACE=1: one line per call on stderr with the host-side times (us since entry) at which
+  // everything was enqueued, the first / last early chunk left, the compute stream and the copies ended
+  static const bool trace = getenv("TORCHAIN_HOST_TRACE") != nullptr;
+  auto now_us = [] {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  };
+  const double tr0 = trace ? now_us() : 0.0;
+  double tr_enq = 0.0, tr_first = -1.0, tr_last = -1.0, tr_sync = 0.0;
+  const std::vector<int> cb = chunk_bounds(T);
+  const int nchunks = (int)cb.size() - 1;
+  if (h.ones_cap < T) {  // no copy of an earlier call is in flight: every call ends with a sync of both copy streams
+    if (h.ones) cudaFreeHost(h.ones);
+    h.ones = nullptr;
+    h.ones_cap = 0;
+    const int cap = std::max(T, 64);
+    CUDA_OK(cudaMallocHost(&h.ones, sizeof(unsigned) * (size_t)cap));
+    for (int i = 0; i < cap; i++) h.ones[i] = 1u;
+    h.ones_cap = cap;
+  }
+  CUDA_OK(h.flags.reserve(sizeof(unsigned) * (size_t)T));
+  HostDrain drain{h};  // from here on, an error return waits for whatever has been enqueued
+  CUDA_OK(cudaMemsetAsync(h.flags.ptr, 0, sizeof(unsigned) * (size_t)T, h.compute));
+  CUDA_OK(cudaEventRecord(h.ready, h.compute));
+  CUDA_OK(cudaStreamWaitEvent(h.copy, h.ready, 0));
+  CUDA_OK(cudaStreamWaitEvent(h.copy2, h.ready, 0));
+  for (int k = 0; k < nchunks; k++) {
+    const int64_t r0 = (int64_t)cb[k] * B, nr = (int64_t)(cb[k + 1] - cb[k]) * B;
+    const cudaStream_t st = (k & 1) ? h.copy2 : h.copy;
+    CUDA_OK(copy_rows(h.y.as<float>() + r0 * cols, sizeof(float) * cols, y_host + r0 * ystride,
+                      sizeof(float) * ystride, sizeof(float) * cols, nr, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaMemcpyAsync(h.flags.as<unsigned>() + cb[k], h.ones, sizeof(unsigned) * (size_t)(cb[k + 1] - cb[k]),
+                            cudaMemcpyHostToDevice, st));
+  }
+  CUDA_OK(cudaEventRecord(h.landed, h.copy));
+  CUDA_OK(cudaEventRecord(h.landed2, h.copy2));
+  ChunkedInput ci;
+  ci.flags = h.flags.as<unsigned>();
+  ci.chunk_frames = 1;  // one flag per frame
+  ci.all_landed = h.landed;
+  ci.all_landed2 = h.landed2;
+  const bool pipelined_out = deriv_host != nullptr && B <= tb::kMaxBP;
+  if (pipelined_out) {
+    *reinterpret_cast<volatile unsigned*>(h.progress) = 0u;
+    unsigned* dptr = nullptr;
+    CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), h.progress, 0));
+    ci.deriv_progress = dptr;
+  }
+  ci.results4_dev = h.results4.as<float>();
+  // enqueue everything without synchronising (results are fetched below)
+  if (!compute(g, sp, h.y.as<float>(), rows, cols, row_layout(B, cols), nullptr, nullptr, deriv_dev,
+               row_layout(B, deriv_dev_stride), want_xent ? h.xent.as<float>() : nullptr, row_layout(B, cols), l2,
+               leaky, xent_regularize, 1.0f, device, h.compute, ci))
+    return 0;
+  auto copy_chunk = [&](int k, cudaStream_t st) -> cudaError_t {
+    const int64_t r0 = (int64_t)cb[k] * B, nr = (int64_t)(cb[k + 1] - cb[k]) * B;
+    return copy_rows(deriv_host + r0 * dstride, sizeof(float) * dstride, deriv_dev + r0 * cols,
+                     sizeof(float) * cols, sizeof(float) * cols, nr, cudaMemcpyDeviceToHost, st);
+  };
+  int next = nchunks - 1;
+  if (trace) tr_enq = now_us() - tr0;
+  if (pipelined_out) {
+    // frames >= T - progress are complete; chunk k covers frames [cb[k], cb[k+1])
+    while (next >= 1) {
+      const unsigned need = (unsigned)(T - cb[next]);
+      bool done = false;
+      // acquire: pairs with the kernel's st.release.sys, so the copy enqueued below is ordered behind the rows
+      while (__atomic_load_n(h.progress, __ATOMIC_ACQUIRE) < need) {
+        if (cudaStreamQuery(h.compute) != cudaErrorNotReady) {
+          done = true;
+          break;
+        }
+      }
+      if (done) break;
+      CUDA_OK(copy_chunk(next, h.copy));
+      if (trace) {
+        tr_last = now_us() - tr0;
+        if (tr_first < 0.0) tr_first = tr_last;
+      }
+      next--;
+    }
+  }
+  const int first_early = next + 1;  // chunks [first_early, nchunks) left before the final pass had run
+  CUDA_OK(cudaStreamSynchronize(h.compute));
+  CUDA_OK(cudaStreamSynchronize(h.copy2));  // long done: the forward launch consumed its chunks
+  if (trace) tr_sync = now_us() - tr0;
+  if (deriv_host)
+    for (; next >= 0; next--) CUDA_OK(copy_chunk(next, h.copy));
+  if (want_xent)
+    CUDA_OK(copy_rows(xent_host, sizeof(float) * xstride, h.xent.ptr, sizeof(float) * cols,
+                      sizeof(float) * cols, rows, cudaMemcpyDeviceToHost, h.copy));
+  float res_host[4];
+  CUDA_OK(cudaMemcpyAsync(res_host, ci.results4_dev, sizeof(res_host), cudaMemcpyDeviceToHost, h.copy));
+  CUDA_OK(cudaStreamSynchronize(h.copy));
+  if (trace)
+    fprintf(stderr, "host_trace T=%d chunks=%d early=%d enqueued=%.0f first_early=%.0f last_early=%.0f compute_done=%.0f end=%.0f us\n",
+            T, nchunks, nchunks - first_early, tr_enq, tr_first, tr_last, tr_sync, now_us() - tr0);
+  if (deriv_host && first_early < nchunks && res_host[3] == 0.f) {
+    // The numeric guard tripped (Kaldi: objf = -10 * weight, derivative reset to the l2 part): the final
+    // pass rewrote the derivative AFTER the early chunks had left, so they go out again.
+    for (int k = first_early; k < nchunks; k++) CUDA_OK(copy_chunk(k, h.copy));
+    CUDA_OK(cudaStreamSynchronize(h.copy));
+  }
+  drain.armed = false;  // everything has been waited for
+  results[0] = res_host[0];
+  results[1] = res_host[1];
+  results[2] = res_host[2];
+  return 1;
 }
 
 // Nothing may propagate through the C ABI: a std::bad_alloc / std::length_error from a corrupt size field
@@ -1827,6 +2008,8 @@ int torchain_supervision_prefetch(void* sup, int device, void* stream) try {
   return abi_exception_int();
 }
 
+void torchain_supervision_pool_trim(void) { sup_pool().trim(); }
+
 void my_lib_supervision_free(void* p) { delete static_cast<Supervision*>(p); }
 int my_lib_supervision_num_pdf(void* p) { return p ? static_cast<Supervision*>(p)->P : 0; }
 int my_lib_supervision_num_sequence(void* p) { return p ? static_cast<Supervision*>(p)->B : 0; }
@@ -1923,185 +2106,8 @@ int torchain_ComputeChainObjfAndDeriv_host(void* den, void* sup, const float* y_
   if (cols != g->P) return fail("nnet_output cols != den_graph.NumPdfs()");
   if (ystride < cols || (deriv_host && dstride < cols) || (xent_host && xstride < cols))
     return fail("row stride < cols");
-  HostPath& h = g_host;
-  if (h.device != device) {
-    h.release();
-    CUDA_OK(cudaStreamCreateWithFlags(&h.compute, cudaStreamNonBlocking));
-    CUDA_OK(cudaStreamCreateWithFlags(&h.copy, cudaStreamNonBlocking));
-    CUDA_OK(cudaStreamCreateWithFlags(&h.copy2, cudaStreamNonBlocking));
-    CUDA_OK(cudaEventCreateWithFlags(&h.ready, cudaEventDisableTiming));
-    CUDA_OK(cudaEventCreateWithFlags(&h.landed, cudaEventDisableTiming));
-    CUDA_OK(cudaEventCreateWithFlags(&h.landed2, cudaEventDisableTiming));
-    CUDA_OK(cudaHostAlloc(&h.progress, sizeof(unsigned), cudaHostAllocMapped));
-    h.device = device;
-  }
-  const size_t bytes = sizeof(float) * (size_t)rows * cols;
-  CUDA_OK(h.y.reserve(bytes));
-  const bool want_xent = xent_host != nullptr && xent_regularize != 0.f;
-  if (want_xent) CUDA_OK(h.xent.reserve(bytes));
-
-  // The derivative is produced in device memory and copied out chunk by chunk (whole frames)
-  // by the copy engine WHILE the backward recurrence is still running: the kernel publishes how
-  // many trailing frames are complete in a mapped pinned counter, this (blocked anyway) host
-  // thread polls it and enqueues the copies.  Only the chunk holding frame 0 waits for the end.
-  float* deriv_dev = nullptr;
-  const int64_t deriv_dev_stride = cols;
-  if (deriv_host) {
-    CUDA_OK(h.deriv.reserve(bytes));
-    deriv_dev = h.deriv.as<float>();
-  }
-  // nnet_output goes up in chunks of whole frames (chunk_bounds); the forward launch starts as soon
-  // as the first chunk has landed and waits, per frame, on the flag of the frame it stages next.
-  const int T = sp->T, B = sp->B;
-  // TORCHAIN_HOST_TRACE=1: one line per call on stderr with the host-side times (us since entry) at which
-  // everything was enqueued, the first / last early chunk left, the compute stream and the copies ended
-  static const bool trace = getenv("TORCHAIN_HOST_TRACE") != nullptr;
-  auto now_us = [] {
-    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
-  };
-  const double tr0 = trace ? now_us() : 0.0;
-  double tr_enq = 0.0, tr_first = -1.0, tr_last = -1.0, tr_sync = 0.0;
-  std::vector<int> cb = chunk_bounds(T);
-  if (getenv("TORCHAIN_HOST_UNIFORM_CHUNKS")) {  // experiment: equal chunks of ~T/16 frames
-    const int cf = std::max(1, (T + 15) / 16);
-    cb.clear();
-    for (int f = 0; f < T; f += cf) cb.push_back(f);
-    cb.push_back(T);
-  }
-  const int nchunks = (int)cb.size() - 1;
-  if (h.ones_cap < T) {  // no copy of an earlier call is in flight: every call ends with a sync of h.copy
-    if (h.ones) cudaFreeHost(h.ones);
-    h.ones = nullptr;
-    h.ones_cap = 0;
-    const int cap = std::max(T, 64);
-    CUDA_OK(cudaMallocHost(&h.ones, sizeof(unsigned) * (size_t)cap));
-    for (int i = 0; i < cap; i++) h.ones[i] = 1u;
-    h.ones_cap = cap;
-  }
-  CUDA_OK(h.flags.reserve(sizeof(unsigned) * (size_t)T));
-  CUDA_OK(cudaMemsetAsync(h.flags.ptr, 0, sizeof(unsigned) * (size_t)T, h.compute));
-  CUDA_OK(cudaEventRecord(h.ready, h.compute));
-  CUDA_OK(cudaStreamWaitEvent(h.copy, h.ready, 0));
-  // Experiments (profiles/r01_host_trace.txt: the input phase takes ~1.72 ms where the copy alone takes
-  // 1.35 ms; the suspect is the copy-engine pipeline break at every chunk's 4-byte flag copy):
-  //   TORCHAIN_HOST_COPY_STREAMS=2     chunks alternate between two copy streams
-  //   TORCHAIN_HOST_FLAG_MODE=memset   frame flags set by cudaMemsetAsync instead of a copy of pinned 1s
-  //   TORCHAIN_HOST_FLAG_MODE=write    frame flags set by stream memory operations (cuStreamWriteValue32)
-  int copy_streams = 1, flag_mode = 0;
-  if (const char* e = getenv("TORCHAIN_HOST_COPY_STREAMS")) copy_streams = atoi(e) == 2 ? 2 : 1;
-  if (const char* e = getenv("TORCHAIN_HOST_FLAG_MODE")) flag_mode = !strcmp(e, "memset") ? 1 : (!strcmp(e, "write") ? 2 : 0);
-  typedef int (*WriteValue32)(cudaStream_t, unsigned long long, unsigned, unsigned);
-  static std::atomic<WriteValue32> write_value_fn{nullptr};
-  WriteValue32 write_value = write_value_fn.load();
-  if (flag_mode == 2 && !write_value) {  // looked up only when the experiment asks for it
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult st;
-    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &st) != cudaSuccess ||
-        st != cudaDriverEntryPointSuccess)
-      fn = nullptr;
-    (void)cudaGetLastError();
-    write_value = reinterpret_cast<WriteValue32>(fn);
-    write_value_fn.store(write_value);
-  }
-  if (flag_mode == 2 && !write_value) flag_mode = 0;
-  if (copy_streams == 2) CUDA_OK(cudaStreamWaitEvent(h.copy2, h.ready, 0));
-  for (int k = 0; k < nchunks; k++) {
-    const int64_t r0 = (int64_t)cb[k] * B, nr = (int64_t)(cb[k + 1] - cb[k]) * B;
-    const cudaStream_t st = (copy_streams == 2 && (k & 1)) ? h.copy2 : h.copy;
-    CUDA_OK(copy_rows(h.y.as<float>() + r0 * cols, sizeof(float) * cols, y_host + r0 * ystride,
-                              sizeof(float) * ystride, sizeof(float) * cols, nr, cudaMemcpyHostToDevice, st));
-    unsigned* const fl = h.flags.as<unsigned>() + cb[k];
-    const int nf = cb[k + 1] - cb[k];
-    if (flag_mode == 1) {
-      CUDA_OK(cudaMemsetAsync(fl, 1, sizeof(unsigned) * (size_t)nf, st));  // 0x01010101: any non-zero value will do
-    } else if (flag_mode == 2 && nf <= 8) {
-      for (int f = 0; f < nf; f++)
-        if (write_value(st, (unsigned long long)(uintptr_t)(fl + f), 1u, 0u) != 0) return fail("cuStreamWriteValue32 failed");
-    } else {
-      CUDA_OK(cudaMemcpyAsync(fl, h.ones, sizeof(unsigned) * (size_t)nf, cudaMemcpyHostToDevice, st));
-    }
-  }
-  CUDA_OK(cudaEventRecord(h.landed, h.copy));
-  if (copy_streams == 2) CUDA_OK(cudaEventRecord(h.landed2, h.copy2));
-  ChunkedInput ci;
-  ci.flags = h.flags.as<unsigned>();
-  ci.chunk_frames = 1;  // one flag per frame
-  ci.all_landed = h.landed;
-  ci.all_landed2 = copy_streams == 2 ? h.landed2 : nullptr;
-  const bool pipelined_out = deriv_host != nullptr && B <= tb::kMaxBP && !getenv("TORCHAIN_HOST_NO_PIPELINED_OUT");
-  if (pipelined_out) {
-    *reinterpret_cast<volatile unsigned*>(h.progress) = 0u;
-    unsigned* dptr = nullptr;
-    CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), h.progress, 0));
-    ci.deriv_progress = dptr;
-  }
-  // enqueue everything without synchronising (results are fetched below)
-  {
-    static thread_local DevBuf res_buf;
-    CUDA_OK(res_buf.reserve(4 * sizeof(float)));
-    ci.results4_dev = res_buf.as<float>();
-  }
-  if (!compute(g, sp, h.y.as<float>(), rows, cols, row_layout(B, cols), nullptr, nullptr, deriv_dev,
-               row_layout(B, deriv_dev_stride), want_xent ? h.xent.as<float>() : nullptr, row_layout(B, cols), l2,
-               leaky, xent_regularize, 1.0f, device, h.compute, ci)) {
-    // nothing may still be reading the caller's buffer (or waiting for its chunks) once this returns
-    cudaStreamSynchronize(h.copy);
-    if (copy_streams == 2) cudaStreamSynchronize(h.copy2);
-    cudaStreamSynchronize(h.compute);
-    return 0;
-  }
-  auto copy_chunk = [&](int k, cudaStream_t st) -> cudaError_t {
-    const int64_t r0 = (int64_t)cb[k] * B, nr = (int64_t)(cb[k + 1] - cb[k]) * B;
-    return copy_rows(deriv_host + r0 * dstride, sizeof(float) * dstride, deriv_dev + r0 * cols,
-                             sizeof(float) * cols, sizeof(float) * cols, nr, cudaMemcpyDeviceToHost, st);
-  };
-  int next = nchunks - 1;
-  if (trace) tr_enq = now_us() - tr0;
-  if (pipelined_out) {
-    // frames >= T - progress are complete; chunk k covers frames [cb[k], cb[k+1])
-    while (next >= 1) {
-      const unsigned need = (unsigned)(T - cb[next]);
-      bool done = false;
-      while (*reinterpret_cast<volatile unsigned*>(h.progress) < need) {
-        if (cudaStreamQuery(h.compute) != cudaErrorNotReady) {
-          done = true;
-          break;
-        }
-      }
-      if (done) break;
-      CUDA_OK(copy_chunk(next, h.copy));
-      if (trace) {
-        tr_last = now_us() - tr0;
-        if (tr_first < 0.0) tr_first = tr_last;
-      }
-      next--;
-    }
-  }
-  const int first_early = next + 1;  // chunks [first_early, nchunks) left before the final pass had run
-  CUDA_OK(cudaStreamSynchronize(h.compute));
-  if (copy_streams == 2) CUDA_OK(cudaStreamSynchronize(h.copy2));  // long done: the forward launch consumed its chunks
-  if (trace) tr_sync = now_us() - tr0;
-  if (deriv_host)
-    for (; next >= 0; next--) CUDA_OK(copy_chunk(next, h.copy));
-  if (want_xent)
-    CUDA_OK(copy_rows(xent_host, sizeof(float) * xstride, h.xent.ptr, sizeof(float) * cols,
-                              sizeof(float) * cols, rows, cudaMemcpyDeviceToHost, h.copy));
-  float res_host[4];
-  CUDA_OK(cudaMemcpyAsync(res_host, ci.results4_dev, sizeof(res_host), cudaMemcpyDeviceToHost, h.copy));
-  CUDA_OK(cudaStreamSynchronize(h.copy));
-  if (trace)
-    fprintf(stderr, "host_trace T=%d chunks=%d early=%d enqueued=%.0f first_early=%.0f last_early=%.0f compute_done=%.0f end=%.0f us\n",
-            T, nchunks, nchunks - first_early, tr_enq, tr_first, tr_last, tr_sync, now_us() - tr0);
-  if (deriv_host && first_early < nchunks && res_host[3] == 0.f) {
-    // The numeric guard tripped (Kaldi: objf = -10 * weight, derivative reset to the l2 part): the final
-    // pass rewrote the derivative AFTER the early chunks had left, so they go out again.
-    for (int k = first_early; k < nchunks; k++) CUDA_OK(copy_chunk(k, h.copy));
-    CUDA_OK(cudaStreamSynchronize(h.copy));
-  }
-  results[0] = res_host[0];
-  results[1] = res_host[1];
-  results[2] = res_host[2];
-  return 1;
+  return host_entry(g, sp, y_host, rows, cols, ystride, results, deriv_host, dstride, xent_host, xstride, l2, leaky,
+                    xent_regularize, device);
 } catch (...) {
   return abi_exception_int();
 }

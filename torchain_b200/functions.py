@@ -79,15 +79,23 @@ def _compute(den_graph, supervision, nnet_output, results, deriv, xent_deriv,
     stream = torch.cuda.current_stream(dev).cuda_stream
     res = results.data
     assert res.dtype == torch.float32 and res.numel() >= 3 and not res.is_cuda and res.is_contiguous()
-    ok = lib.torchain_ComputeChainObjfAndDeriv_strided(
-        den_graph, supervision,
-        nnet_output.data_ptr(), n_frame, n_seq, n_pdf, _tsp_strides(nnet_output, n_seq),
-        res.data_ptr(), None,
-        deriv.data_ptr(), _tsp_strides(deriv, n_seq),
-        xent_deriv.data_ptr() if xent_deriv is not None else None,
-        _tsp_strides(xent_deriv, n_seq) if xent_deriv is not None else None,
-        float(l2_regularize), float(leaky_hmm_coefficient), float(xent_regularize), float(deriv_scale),
-        dev, ctypes.c_void_p(stream))
+    def call():
+        return lib.torchain_ComputeChainObjfAndDeriv_strided(
+            den_graph, supervision,
+            nnet_output.data_ptr(), n_frame, n_seq, n_pdf, _tsp_strides(nnet_output, n_seq),
+            res.data_ptr(), None,
+            deriv.data_ptr(), _tsp_strides(deriv, n_seq),
+            xent_deriv.data_ptr() if xent_deriv is not None else None,
+            _tsp_strides(xent_deriv, n_seq) if xent_deriv is not None else None,
+            float(l2_regularize), float(leaky_hmm_coefficient), float(xent_regularize), float(deriv_scale),
+            dev, ctypes.c_void_p(stream))
+
+    ok = call()
+    if ok != 1 and "out of memory" in _lib.last_error():
+        # the library's workspace (the alpha store) is allocated with cudaMalloc, which cannot see the blocks
+        # torch's caching allocator holds free: hand them back and try once more
+        torch.cuda.empty_cache()
+        ok = call()
     if ok != 1:
         raise RuntimeError("ComputeChainObjfAndDeriv failed: " + _lib.last_error())
 
@@ -212,13 +220,17 @@ class _To2d(Function):
     @staticmethod
     def forward(ctx, x):
         ctx.shape = x.shape
+        ctx.device = x.device
         return _rows_of(x)
 
     @staticmethod
     def backward(ctx, grad_rows):
-        if grad_rows.stride(1) != 1:
-            grad_rows = grad_rows.contiguous()
         B, P, T = ctx.shape
+        # any gradient layout is accepted, as by the backward of the reference's permute().contiguous().view():
+        # a row-broadcast gradient (to2d(x).sum(0)) arrives expanded with strides (0, 1), a double one from .double()
+        if (grad_rows.stride(1) != 1 or grad_rows.stride(0) < P or grad_rows.dtype != torch.float32
+                or not grad_rows.is_cuda):
+            grad_rows = grad_rows.to(device=ctx.device, dtype=torch.float32).contiguous()
         out = grad_rows.new_empty(B, P, T)
         dev, stream = _stream_args(grad_rows)
         if _lib.load().torchain_from2d(grad_rows.data_ptr(), grad_rows.stride(0), B, P, T, out.data_ptr(), 1.0,

@@ -92,6 +92,20 @@ class Supervision:
             raise ValueError("invalid supervision: " + _lib.last_error())
         return cls(ptr)
 
+    def prefetch(self, device=None, stream=None):
+        """Start the asynchronous upload of the device image on `stream` (default: the current stream) of
+        `device`, e.g. from a data-loading thread while the previous minibatch is still being computed.
+        Optional -- the first chain_loss on a device uploads it otherwise.  Never synchronises the device."""
+        import torch
+        if device is None:
+            device = torch.cuda.current_device()
+        device = torch.device("cuda", device).index if not isinstance(device, int) else device
+        if stream is None:
+            stream = torch.cuda.current_stream(device)
+        if _lib.load().torchain_supervision_prefetch(self.ptr, int(device), ctypes.c_void_p(stream.cuda_stream)) != 1:
+            raise RuntimeError("supervision prefetch failed: " + _lib.last_error())
+        return self
+
     @property
     def num_chains(self):
         return _lib.load().torchain_supervision_num_chains(self.ptr)
