@@ -159,9 +159,36 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// ---- asynchronous gather ring (LDGSTS) -------------------------------------------------------
+// Register loads cap a warp at about two 512-byte rows in flight whatever the unroll depth, so the
+// gather throughput of a CTA follows its WARP count (tools/gather_probe.py, profiles/r02_gather_probe.txt:
+// 14 warps 12.6 TB/s ... 32 warps 19.9 TB/s), and warps are what the 112 / 128 registers per thread of
+// these loops make scarce.  cp.async (LDGSTS) is not tied to the warp's scoreboards: rows land in a
+// per-warp ring in shared memory (kRing arcs x 2 rows x 512 B), every lane copies and later reads back
+// its OWN 16 bytes (no cross-lane dependency, no barrier), and the same probe reaches 17.1 TB/s with 12
+// warps and 18.9 TB/s with 16 at four arcs in flight per warp.
+#ifndef DEN_RING
+#define DEN_RING 4
+#endif
+constexpr int kRing = DEN_RING;  // arcs in flight per warp; divides kStreamPad, so a stream is whole ring turns
+static_assert(kStreamPad % kRing == 0 || kRing % kStreamPad == 0, "ring depth vs stream padding");
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void lds128(unsigned addr, float (&v)[4]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+}
+
 struct Smem {
   float* red;     // [kDenMainWarps][BP]
   float* tile;    // [kDenAuxWarps][32][33]
+  float4* ring;   // [kDenMainWarps][kRing][2][32]  gather ring of the main warps
   int4* tasks;    // [max_tasks_cta]   (only if staged)
   int4* arcs;     // [max_arcs_cta]    (only if staged)
 };
@@ -172,7 +199,9 @@ __device__ __forceinline__ Smem carve(unsigned char* base, const DenParams& p) {
   size_t off = sizeof(float) * kDenMainWarps * p.subs * p.BP;
   s.tile = reinterpret_cast<float*>(base + off);
   off += sizeof(float) * kDenAuxWarps * 32 * 33;
-  off = (off + 15) & ~size_t(15);
+  off = (off + 127) & ~size_t(127);
+  s.ring = reinterpret_cast<float4*>(base + off);
+  off += sizeof(float4) * 64 * kRing * kDenMainWarps;
   int max_tasks = max(p.dir[0].max_tasks_cta, p.dir[1].max_tasks_cta);
   s.tasks = reinterpret_cast<int4*>(base + off);
   off += sizeof(int4) * max_tasks;
@@ -585,6 +614,200 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
   }
 }
 
+
+// ---- the same recurrence with the gathers going through the shared-memory ring
+#ifndef DEN_ASYNC_F
+#define DEN_ASYNC_F 1
+#endif
+#ifndef DEN_ASYNC_B
+#define DEN_ASYNC_B 1
+#endif
+template <int SUBS, bool SPLIT>
+__device__ __forceinline__ void alpha_step_async(const DenParams& p, const int4* __restrict__ arcs,
+                                                 const int4* __restrict__ tasks, int abeg, int aend, int tb, int t,
+                                                 float* red, float4* ring, int warp, int lane) {
+  constexpr int V = 4;
+  const int BP = p.BP;  // = (32 / SUBS) * V: a lane group covers the whole (padded) batch
+  const int col = (lane % (32 / SUBS)) * V;
+  const float* __restrict__ alpha_prev = p.alpha + (size_t)(t - 1) * p.N * BP;
+  float* __restrict__ alpha_cur = p.alpha + (size_t)t * p.N * BP;
+  const float* __restrict__ et = p.etile + (size_t)((t - 1) & 1) * p.P * BP;
+  const double* Sprev = p.Ssum + (size_t)(t - 1) * BP;
+  const int4* __restrict__ a = arcs + abeg;
+  const int n = aend - abeg;  // a multiple of kStreamPad
+  const unsigned rowbytes = (unsigned)BP * 4u;
+  const char* const ua = reinterpret_cast<const char*>(alpha_prev + col);
+  const char* const ue = reinterpret_cast<const char*>(et + col);
+  const unsigned slot0 = smem_u32(ring + lane);  // this lane's 16 bytes of slot 0's first row
+  // arc k -> slot k % kRing: state row at +0, exp row at +512; exactly ONE group is committed per arc
+  // (an empty one past the end of the stream), so "at most kRing-1 groups pending" == "arc k has landed"
+  auto issue = [&](int k, int u) {
+    if (k < n) {
+      const uint2 ar = *reinterpret_cast<const uint2*>(a + k);  // {source state, pdf} as row byte offsets
+      cp_async16(slot0 + u * 1024, ua + ar.x);
+      cp_async16(slot0 + u * 1024 + 512, ue + ar.y);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int u = 0; u < kRing; u++) issue(u, u);
+  float lamS[V], invS[V], part[V], acc[V];
+#pragma unroll
+  for (int v = 0; v < V; v++) {
+    const float S = (float)__ldcg(Sprev + col + v);
+    lamS[v] = p.leaky * S;
+    invS[v] = 1.0f / S;
+    part[v] = 0.f;
+    acc[v] = 0.f;
+  }
+  int task = tb;
+  for (int k = 0; k < n; k += kRing) {
+#pragma unroll
+    for (int u = 0; u < kRing; u++) {
+      cp_async_wait<kRing - 1>();
+      float av[V], ev[V];
+      lds128(slot0 + u * 1024, av);
+      lds128(slot0 + u * 1024 + 512, ev);
+      const int2 ar = *(reinterpret_cast<const int2*>(a + k + u) + 1);  // {prob | end flag, pi[source]}
+      issue(k + u + kRing, u);  // the slot is free again: this lane has read its 16 bytes of both rows
+      const float pr = fabsf(__int_as_float(ar.x)), pi = __int_as_float(ar.y);
+      const u64 pr2 = pk2(pr, pr), pi2 = pk2(pi, pi);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const u64 ad = fma2(pi2, pk2(lamS[2 * h], lamS[2 * h + 1]), pk2(av[2 * h], av[2 * h + 1]));
+        const u64 r = fma2(mul2(ad, pr2), pk2(ev[2 * h], ev[2 * h + 1]), pk2(acc[2 * h], acc[2 * h + 1]));
+        upk2(r, acc[2 * h], acc[2 * h + 1]);
+      }
+      if (ar.x < 0) {  // sign bit of the probability = last arc of this state (uniform within the lane group)
+        const int4 tk = tasks[task++];
+        float out[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          out[v] = acc[v] * invS[v];
+          part[v] += out[v];
+          acc[v] = 0.f;
+        }
+        float* const dst = row_ptr(alpha_cur + col, tk.x, rowbytes);
+        if (SPLIT && tk.z != 0) red_add<V>(dst, out);
+        else st_vec<V>(dst, out);
+      }
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int v = 0; v < V; v++) red[(warp * SUBS + lane / (32 / SUBS)) * BP + col + v] = part[v];
+}
+
+template <int SUBS, bool SPLIT>
+__device__ __forceinline__ void beta_step_async(const DenParams& p, const int4* __restrict__ arcs,
+                                                const int4* __restrict__ tasks, int abeg, int aend, int tb, int te,
+                                                int t, float* red, float4* ring, int warp, int lane, double& ab) {
+  constexpr int V = 4;
+  const int BP = p.BP;
+  const int col = (lane % (32 / SUBS)) * V;
+  const float* __restrict__ alpha_t = p.alpha + (size_t)t * p.N * BP;
+  const float* __restrict__ beta_next = p.beta + (size_t)((t + 1) % 3) * p.N * BP;
+  float* __restrict__ beta_cur = p.beta + (size_t)(t % 3) * p.N * BP;
+  float* __restrict__ beta_zero = p.beta + (size_t)((t + 2) % 3) * p.N * BP;
+  const float* __restrict__ et = p.etile + (size_t)(t & 1) * p.P * BP;
+  float* __restrict__ gt = p.gtile + (size_t)(t & 1) * p.P * BP;
+  const double* St = p.Ssum + (size_t)t * BP;
+  const double* Bn = p.Bsum + (size_t)(t + 1) * BP;
+  const int4* __restrict__ a = arcs + abeg;
+  const int n = aend - abeg;
+  const unsigned rowbytes = (unsigned)BP * 4u;
+  const char* const ub = reinterpret_cast<const char*>(beta_next + col);
+  const char* const ue = reinterpret_cast<const char*>(et + col);
+  char* const ug = reinterpret_cast<char*>(gt + col);
+  const unsigned slot0 = smem_u32(ring + lane);
+  auto issue = [&](int k, int u) {
+    if (k < n) {
+      const uint2 ar = *reinterpret_cast<const uint2*>(a + k);  // {destination state, pdf} as row byte offsets
+      cp_async16(slot0 + u * 1024, ub + ar.x);
+      cp_async16(slot0 + u * 1024 + 512, ue + ar.y);
+    }
+    cp_async_commit();
+  };
+  float al0[V], aln[V];
+#pragma unroll
+  for (int v = 0; v < V; v++) al0[v] = aln[v] = 0.f;
+  int task = tb;
+  float pi_h = 0.f;
+  if (tb < te) {
+    const int4 tk0 = tasks[tb];
+    pi_h = __int_as_float(tk0.w);
+    ld_cs<V>(row_ptr(alpha_t + col, tk0.x, rowbytes), al0);
+  }
+#pragma unroll
+  for (int u = 0; u < kRing; u++) issue(u, u);
+  if (tb + 1 < te) ld_cs<V>(row_ptr(alpha_t + col, tasks[tb + 1].x, rowbytes), aln);
+  float lamS[V], invS[V], bv[V], part[V], X[V], occ[V];
+#pragma unroll
+  for (int v = 0; v < V; v++) {
+    const float S = (float)__ldcg(St + col + v);
+    lamS[v] = p.leaky * S;
+    invS[v] = 1.0f / S;
+    bv[v] = p.leaky * (float)__ldcg(Bn + col + v);
+    part[v] = 0.f;
+    X[v] = 0.f;
+    occ[v] = fmaf(pi_h, lamS[v], al0[v]) * invS[v];
+  }
+  for (int k = 0; k < n; k += kRing) {
+#pragma unroll
+    for (int u = 0; u < kRing; u++) {
+      cp_async_wait<kRing - 1>();
+      float bn[V], ev[V], g[V];
+      lds128(slot0 + u * 1024, bn);
+      lds128(slot0 + u * 1024 + 512, ev);
+      const int4 ar = a[k + u];
+      issue(k + u + kRing, u);
+      const float pr = fabsf(__int_as_float(ar.z));
+      const u64 pr2 = pk2(pr, pr);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const u64 sum = add2(pk2(bn[2 * h], bn[2 * h + 1]), pk2(bv[2 * h], bv[2 * h + 1]));
+        const u64 vf = mul2(mul2(pr2, sum), pk2(ev[2 * h], ev[2 * h + 1]));
+        upk2(add2(pk2(X[2 * h], X[2 * h + 1]), vf), X[2 * h], X[2 * h + 1]);
+        upk2(mul2(vf, pk2(occ[2 * h], occ[2 * h + 1])), g[2 * h], g[2 * h + 1]);
+      }
+      red_add<V>(reinterpret_cast<float*>(ug + (unsigned)ar.y), g);
+      if (ar.z < 0) {  // sign bit of the probability = last arc of this state
+        const int4 tk = tasks[task];
+        float bd[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          bd[v] = X[v] * invS[v];
+          part[v] = fmaf(pi_h, bd[v], part[v]);
+          if (t == 0 && col + v < p.B) ab += (double)(occ[v] * (lamS[v] / p.leaky)) * (double)bd[v];
+          X[v] = 0.f;
+        }
+        float* const dst = row_ptr(beta_cur + col, tk.x, rowbytes);
+        if (SPLIT && tk.z != 0) {
+          red_add<V>(dst, bd);
+          if (tk.z == 2) {  // the state's first sub-task also clears the row used at step t-1
+            float zero[V];
+#pragma unroll
+            for (int v = 0; v < V; v++) zero[v] = 0.f;
+            st_vec<V>(row_ptr(beta_zero + col, tk.x, rowbytes), zero);
+          }
+        } else {
+          st_vec<V>(dst, bd);
+        }
+        task++;
+        if (task < te) {
+          pi_h = __int_as_float(tasks[task].w);
+#pragma unroll
+          for (int v = 0; v < V; v++) occ[v] = fmaf(pi_h, lamS[v], aln[v]) * invS[v];
+          if (task + 1 < te) ld_cs<V>(row_ptr(alpha_t + col, tasks[task + 1].x, rowbytes), aln);
+        }
+      }
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int v = 0; v < V; v++) red[(warp * SUBS + lane / (32 / SUBS)) * BP + col + v] = part[v];
+}
+
 template <bool STAGED, int SUBS>
 __device__ __forceinline__ void load_dir(const DenParams& p, int d, const Smem& sm, const int4*& arcs,
                                          const int4*& tasks, int& tb, int& te, int& abeg, int& aend, int warp,
@@ -761,7 +984,11 @@ __device__ __forceinline__ void den_chain_body(const DenBatch& batch) {
           if (t < T) aux_work(p, -1, t, tile, auxw, lane, true, sumsq, false, gsum);
         } else {
           const long long c0 = clock64();
-          alpha_step<V, SUBS, SPLIT>(p, arcs, tasks, abeg, aend, tb, t, sm.red, warp, lane);
+          if constexpr (DEN_ASYNC_F)
+            alpha_step_async<SUBS, SPLIT>(p, arcs, tasks, abeg, aend, tb, t, sm.red, sm.ring + (size_t)warp * kRing * 64,
+                                          warp, lane);
+          else
+            alpha_step<V, SUBS, SPLIT>(p, arcs, tasks, abeg, aend, tb, t, sm.red, warp, lane);
           busy += clock64() - c0;
         }
         trace_warp_done(t);
@@ -858,7 +1085,11 @@ __device__ __forceinline__ void den_chain_body(const DenBatch& batch) {
           aux_work(p, t + 1 < T ? t + 1 : -1, t - 1, tile, auxw, lane, false, sumsq, false, gsum, t);
         } else {
           const long long c0 = clock64();
-          beta_step<V, SUBS, SPLIT>(p, arcs, tasks, abeg, aend, tb, te, t, sm.red, warp, lane, ab);
+          if constexpr (DEN_ASYNC_B)
+            beta_step_async<SUBS, SPLIT>(p, arcs, tasks, abeg, aend, tb, te, t, sm.red,
+                                         sm.ring + (size_t)warp * kRing * 64, warp, lane, ab);
+          else
+            beta_step<V, SUBS, SPLIT>(p, arcs, tasks, abeg, aend, tb, te, t, sm.red, warp, lane, ab);
           busy += clock64() - c0;
         }
         trace_warp_done(t);
@@ -943,7 +1174,8 @@ int den_subs(int BP) { return BP >= 128 ? 1 : (BP >= 64 ? 2 : 4); }
 size_t den_smem_bytes(const DenParams& p) {
   size_t off = sizeof(float) * kDenMainWarps * p.subs * p.BP;
   off += sizeof(float) * kDenAuxWarps * 32 * 33;
-  off = (off + 15) & ~size_t(15);
+  off = (off + 127) & ~size_t(127);
+  off += sizeof(float4) * 64 * kRing * kDenMainWarps;
   if (p.arcs_in_smem) {
     off += sizeof(int4) * (size_t)std::max(p.dir[0].max_tasks_cta, p.dir[1].max_tasks_cta);
     off += sizeof(int4) * (size_t)std::max(p.dir[0].max_arcs_cta, p.dir[1].max_arcs_cta);
