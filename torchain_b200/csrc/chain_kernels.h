@@ -29,7 +29,10 @@ constexpr int kDenAuxWarps = DEN_AUX_WARPS;                // staging (transpose
 constexpr int kDenMainWarps = kDenWarps - kDenAuxWarps;
 // every lane group's arc stream is padded (zero-probability arcs) to a multiple of this many arcs,
 // a common multiple of the stage widths of the two gather loops
-constexpr int kStreamPad = 4;
+#ifndef DEN_STREAM_PAD
+#define DEN_STREAM_PAD 4
+#endif
+constexpr int kStreamPad = DEN_STREAM_PAD;
 #define DEN_F_SA_DEFAULT 2
 #define DEN_B_SA_DEFAULT 4
 constexpr int kCtxBP = 128;                    // sequences per context (lane width of the full-size kernels)

@@ -171,7 +171,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 #define DEN_RING 4
 #endif
 constexpr int kRing = DEN_RING;  // arcs in flight per warp; divides kStreamPad, so a stream is whole ring turns
-static_assert(kStreamPad % kRing == 0 || kRing % kStreamPad == 0, "ring depth vs stream padding");
+static_assert(kStreamPad % kRing == 0, "a stream is a whole number of ring turns");
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
