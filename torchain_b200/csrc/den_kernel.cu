@@ -167,10 +167,22 @@ __device__ __forceinline__ double warp_sum(double v) {
 // per-warp ring in shared memory (kRing arcs x 2 rows x 512 B), every lane copies and later reads back
 // its OWN 16 bytes (no cross-lane dependency, no barrier), and the same probe reaches 17.1 TB/s with 12
 // warps and 18.9 TB/s with 16 at four arcs in flight per warp.
+// Measured on config 2 (profiles/r02_variants_async_gather.txt): SLOWER than the register gathers in the real
+// kernels -- forward 27.6 vs 25.5 us per frame, backward 49.6 vs 41.4 -- although the bare gather pattern is
+// faster (17 vs 12.6 TB/s at 14 warps): every row crosses the shared-memory pipe twice (LDGSTS write + LDS
+// read, 18 wavefronts per arc against 2 for the register path), next to the arc records the same pipe
+// serves.  Kept as a compile-time option for the record; off in the product.
+#ifndef DEN_ASYNC_F
+#define DEN_ASYNC_F 0
+#endif
+#ifndef DEN_ASYNC_B
+#define DEN_ASYNC_B 0
+#endif
 #ifndef DEN_RING
 #define DEN_RING 4
 #endif
 constexpr int kRing = DEN_RING;  // arcs in flight per warp; divides kStreamPad, so a stream is whole ring turns
+constexpr size_t kRingBytes = (DEN_ASYNC_F || DEN_ASYNC_B) ? sizeof(float4) * 64 * kRing * kDenMainWarps : 0;
 static_assert(kStreamPad % kRing == 0, "a stream is a whole number of ring turns");
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
@@ -201,7 +213,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, const DenParams& p) {
   off += sizeof(float) * kDenAuxWarps * 32 * 33;
   off = (off + 127) & ~size_t(127);
   s.ring = reinterpret_cast<float4*>(base + off);
-  off += sizeof(float4) * 64 * kRing * kDenMainWarps;
+  off += kRingBytes;
   int max_tasks = max(p.dir[0].max_tasks_cta, p.dir[1].max_tasks_cta);
   s.tasks = reinterpret_cast<int4*>(base + off);
   off += sizeof(int4) * max_tasks;
@@ -616,12 +628,7 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
 
 
 // ---- the same recurrence with the gathers going through the shared-memory ring
-#ifndef DEN_ASYNC_F
-#define DEN_ASYNC_F 1
-#endif
-#ifndef DEN_ASYNC_B
-#define DEN_ASYNC_B 1
-#endif
+
 template <int SUBS, bool SPLIT>
 __device__ __forceinline__ void alpha_step_async(const DenParams& p, const int4* __restrict__ arcs,
                                                  const int4* __restrict__ tasks, int abeg, int aend, int tb, int t,
@@ -1175,7 +1182,7 @@ size_t den_smem_bytes(const DenParams& p) {
   size_t off = sizeof(float) * kDenMainWarps * p.subs * p.BP;
   off += sizeof(float) * kDenAuxWarps * 32 * 33;
   off = (off + 127) & ~size_t(127);
-  off += sizeof(float4) * 64 * kRing * kDenMainWarps;
+  off += kRingBytes;
   if (p.arcs_in_smem) {
     off += sizeof(int4) * (size_t)std::max(p.dir[0].max_tasks_cta, p.dir[1].max_tasks_cta);
     off += sizeof(int4) * (size_t)std::max(p.dir[0].max_arcs_cta, p.dir[1].max_arcs_cta);
