@@ -97,6 +97,15 @@ void* torchain_supervision_from_arrays(float weight, int32_t num_sequences,
  * a Kaldi-written file (none is available in the build environment). */
 void* torchain_supervision_from_kaldi_bytes(const void* data, int64_t nbytes, int64_t* consumed);
 
+/* The Supervision of the next binary nnet3 chain example in `data` (an ark or a piece of one: "[key \0B]
+ * <Nnet3ChainEg> ... <NnetChainSup> ... <Supervision> ... </Supervision> ... </Nnet3ChainEg>"), i.e. what the
+ * reference obtains as `new Supervision(eg.outputs[0].supervision)` (src/my_lib_example.cpp:71-76,
+ * src/my_lib_example_rand.cpp:244-249).  Examples are located by scanning for the <Nnet3ChainEg> token, as the
+ * reference's own indexer does (example/chime5/ark2scp.py:24-40); features, i-vectors and derivative weights
+ * are skipped.  *consumed (optional) = offset just past the example, so a caller can walk an ark.  Text-mode
+ * egs are refused.  Combine the examples of a minibatch with torchain_supervision_merge. */
+void* torchain_supervision_from_chain_egs(const void* data, int64_t nbytes, int64_t* consumed);
+
 /* Minibatch assembly: the hot-path part of Kaldi's MergeChainExamples / AppendSupervision, which the
  * reference runs inside its egs reader (src/my_lib_example_rand.cpp:160).  Appends `n` supervisions
  * (each with one or more sequences) sequence-major into a new handle whose num_sequences is the sum;

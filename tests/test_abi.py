@@ -459,3 +459,48 @@ def test_text_fst_reader_rejects_corrupt_input_without_crashing(seed, tmp_path):
         except (ValueError, RuntimeError, OSError):
             pass
     assert accepted < 150
+
+
+def chain_egs_bytes(sups, rng, keys=None):
+    """A binary egs ark as nnet3-chain-get-egs writes it, reduced to what the scanner looks at: per example
+    ``key \\0B<Nnet3ChainEg> ...inputs... <NnetChainSup> output ...indexes... <Supervision>...</Supervision> <DW2>
+    ...weights... </NnetChainSup> </Nnet3ChainEg>`` with opaque bytes where features / indexes / weights would be."""
+    out = b""
+    for k, sup in enumerate(sups):
+        junk = lambda n: bytes(rng.integers(0, 256, size=n, dtype=np.uint8)).replace(b"<", b"(")
+        out += (keys[k] if keys else b"utt%d-0" % k) + b" \x00B<Nnet3ChainEg> <NumInputs> " + struct.pack("<Bi", 4, 2)
+        out += b"<NnetIo> input " + junk(400) + b"</NnetIo> <NnetIo> ivector " + junk(60) + b"</NnetIo> "
+        out += b"<NumOutputs> " + struct.pack("<Bi", 4, 1) + b"<NnetChainSup> output <I1V> " + junk(90)
+        out += kaldi_supervision_bytes(sup) + b"<DW2> " + junk(70) + b"</NnetChainSup> </Nnet3ChainEg> "
+    return out
+
+
+def test_supervision_from_chain_egs_scans_an_ark():
+    den = synth.make_den_fst(3, 40, 9, mean_deg=3.0)
+    rng = np.random.default_rng(5)
+    sups = [synth.make_supervision(10 + k, den, 1 + k % 2, 6, num_paths=2, weight=1.0) for k in range(4)]
+    ark = chain_egs_bytes(sups, rng)
+    hs = io.Supervision.from_chain_egs(ark)
+    assert [h.shape for h in hs] == [(sp.num_sequences, 6, 9) for sp in sups]
+    assert len(io.Supervision.from_chain_egs(ark, max_examples=2)) == 2
+    mb = io.Supervision.merge(hs)
+    assert mb.shape == (sum(sp.num_sequences for sp in sups), 6, 9) and mb.num_chains == mb.n_batch
+    # a bare Supervision object announced by Kaldi's binary marker parses too
+    h, used = io.Supervision.from_kaldi_bytes(b"\x00B" + kaldi_supervision_bytes(sups[0]))
+    assert h.shape == hs[0].shape
+    with pytest.raises(ValueError, match="text-mode"):
+        io.Supervision.from_chain_egs(b"utt1 <Nnet3ChainEg> <NumInputs> 2 ...")
+    with pytest.raises(ValueError, match="without a <Supervision>"):
+        io.Supervision.from_chain_egs(b"utt1 \x00B<Nnet3ChainEg> <NumInputs> </Nnet3ChainEg> ")
+    with pytest.raises(ValueError):
+        io.Supervision.from_chain_egs(b"no examples here")
+    with pytest.raises(ValueError):   # truncated inside the supervision
+        io.Supervision.from_chain_egs(ark[:ark.index(b"<Supervision>") + 60])
+
+
+def test_vectorised_openfst_writer_equals_the_per_arc_writer(tmp_path):
+    den = synth.make_den_fst(12, 200, 30, mean_deg=5.0)
+    a, b = str(tmp_path / "a.fst"), str(tmp_path / "b.fst")
+    write_openfst_binary(a, den)
+    synth.write_openfst_binary(b, den)
+    assert open(a, "rb").read() == open(b, "rb").read()

@@ -156,3 +156,53 @@ def test_graph_whose_arc_slices_do_not_fit_shared_memory():
     g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
                                         den.final_cost, den.num_pdfs)
     _compare(den, oden, g, 128, 6, 5e-5, 0.1, seed=3101)
+
+
+def test_cfg2_den_graph_read_from_an_openfst_file(tmp_path):
+    """io.DenominatorGraph(path, n_pdf) -- the reference's constructor (torchain/io.py:51-54 ->
+    src/my_lib_example.cpp:129-134: ReadFstKaldi + DenominatorGraph) -- on a cfg-2-sized binary den.fst
+    (10 000 states, 300 k arcs, 4.9 MB): same graph, same initial probabilities, same loss as the handle built
+    from arrays, and the loss matches the oracle."""
+    import time
+    den, oden, g_arrays = _den("chime5")
+    path = str(tmp_path / "den.fst")
+    synth.write_openfst_binary(path, den)
+    t0 = time.perf_counter()
+    g_file = io.DenominatorGraph(path, den.num_pdfs)
+    print("read + prepared den.fst (%d bytes) in %.0f ms" % (os.path.getsize(path), 1e3 * (time.perf_counter() - t0)))
+    assert (g_file.n_state, g_file.n_arc, g_file.n_pdf) == (den.num_states, den.num_arcs, den.num_pdfs)
+    assert np.array_equal(g_file.initial_probs, g_arrays.initial_probs)
+    res_f, d_f, _, r = _compare(den, oden, g_file, 128, 50, 5e-5, 0.1, seed=4001)
+    sup = synth.make_supervision(4001, den, 128, 50, num_paths=4, weight=1.0)
+    y = synth.make_nnet_output(4002, 128, 50, den.num_pdfs, scale=2.0)
+    s = io.Supervision.from_arrays(sup.weight, 128, 50, sup.label_dim, sup.arc_begin, sup.arc_dst, sup.arc_label,
+                                   sup.arc_cost, sup.final_cost)
+    res_a, d_a, _ = run_abi(g_arrays, s, y, 5e-5, 0.1)
+    assert rel(res_f[0], res_a[0]) < 1e-6 and deriv_err(d_f, d_a.astype(np.float64)) < 1e-5
+
+
+def test_minibatch_from_chain_egs_bytes():
+    """Supervisions pulled out of a binary egs ark (token scan, as /root/reference/example/chime5/ark2scp.py:24-40),
+    merged into a minibatch (Kaldi's MergeChainExamples inside the reference's reader,
+    src/my_lib_example_rand.cpp:160) and run through chain_loss: equal to the oracle on the appended FST."""
+    import torch
+    from test_abi import chain_egs_bytes
+    from torchain.functions import chain_loss
+    den = synth.make_den_fst(5, 800, 120, mean_deg=6.0)
+    T = 30
+    Bs = [1, 2, 1, 1, 3, 1, 2, 1]
+    sups = [synth.make_supervision(600 + k, den, b, T, num_paths=3, weight=1.0) for k, b in enumerate(Bs)]
+    ys = [synth.make_nnet_output(700 + k, b, T, den.num_pdfs, scale=1.5) for k, b in enumerate(Bs)]
+    ark = chain_egs_bytes(sups, np.random.default_rng(9))
+    minibatch = io.Supervision.merge(io.Supervision.from_chain_egs(ark))
+    assert minibatch.shape == (sum(Bs), T, den.num_pdfs)
+    y_all = synth.interleave_rows(ys, Bs)
+    r = ol.chain(ol.OracleDen(den), ol.OracleSup(synth.append_supervisions(sups)), y_all, l2=5e-5, leaky=0.1,
+                 mode="fp64", threads=_cores())
+    g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
+                                        den.final_cost, den.num_pdfs)
+    inp = torch.from_numpy(y_all).cuda().requires_grad_(True)
+    loss, results = chain_loss(inp, g, minibatch, l2_regularize=5e-5, leaky_hmm_coefficient=0.1)
+    loss.backward()
+    assert rel(float(results.data[0]), r["objf"]) < OBJF_RTOL
+    assert deriv_err(inp.grad.cpu().numpy(), -r["deriv"]) < DERIV_RTOL

@@ -36,6 +36,7 @@ SIGNATURES = {
     "torchain_supervision_from_arrays": (
         _c_p, [_c_f, _c_i32, _c_i32, _c_i32, _c_i32, _c_p, _c_p, _c_p, _c_p, _c_p]),
     "torchain_supervision_from_kaldi_bytes": (_c_p, [_c_p, _c_i64, _c_p]),
+    "torchain_supervision_from_chain_egs": (_c_p, [_c_p, _c_i64, _c_p]),
     "torchain_supervision_merge": (_c_p, [_c_p, _c_i32]),
     "torchain_supervision_prefetch": (_c_i, [_c_p, _c_i, _c_p]),
     "torchain_supervision_pool_trim": (None, []),

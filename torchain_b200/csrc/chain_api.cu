@@ -1600,6 +1600,9 @@ struct ByteReader {
 
 Supervision* parse_kaldi_supervision(const void* data, int64_t nbytes, int64_t* consumed) {
   ByteReader r{static_cast<const unsigned char*>(data), static_cast<const unsigned char*>(data) + nbytes};
+  // A Kaldi binary stream announces itself with "\0B" (e.g. right after the key of an ark entry): skip it.  A text-mode
+  // object ("<Supervision> <Weight> 1 ...") fails the size-byte checks below and is reported as such.
+  if (nbytes >= 2 && r.p[0] == 0 && r.p[1] == 'B') r.p += 2;
   float weight = 0.f;
   int32_t B = 0, T = 0, P = 0;
   if (!r.token("<Supervision>") || !r.token("<Weight>") || !r.basic(&weight) || !r.token("<NumSequences>") ||
@@ -1836,6 +1839,56 @@ int host_entry(DenGraph* g, Supervision* sp, const float* y_host, int64_t rows, 
   return 1;
 }
 
+// nnet3 chain examples (kaldi@22fbdd:src/nnet3/nnet-chain-example.cc, NnetChainExample::Write, binary):
+//   [key ' ' '\0' 'B'] <Nnet3ChainEg> <NumInputs> ... NnetIo ... <NumOutputs> n
+//   <NnetChainSup> name <I1V> indexes <Supervision> ... </Supervision> <DW>|<DW2> deriv weights </NnetChainSup> ...
+//   </Nnet3ChainEg>
+// The reference pulls the Supervision out of such an example with Kaldi itself
+// (/root/reference/src/my_lib_example.cpp:71-76: eg.outputs[0].supervision) and finds the examples in an
+// ark by scanning for the <Nnet3ChainEg> token (/root/reference/example/chime5/ark2scp.py:24-40).  Same
+// scan here: the first <Supervision> object after the next <Nnet3ChainEg> token is parsed, everything
+// else in the example (features, i-vectors, derivative weights) is skipped.
+const unsigned char* find_bytes(const unsigned char* p, const unsigned char* end, const char* token) {
+  const size_t n = std::strlen(token);
+  if ((size_t)(end - p) < n) return nullptr;
+  const unsigned char* last = end - n;
+  for (; p <= last; p++) {
+    p = static_cast<const unsigned char*>(std::memchr(p, token[0], (size_t)(last - p) + 1));
+    if (!p) return nullptr;
+    if (std::memcmp(p, token, n) == 0) return p;
+  }
+  return nullptr;
+}
+
+Supervision* parse_chain_eg(const void* data, int64_t nbytes, int64_t* consumed) {
+  const unsigned char* base = static_cast<const unsigned char*>(data);
+  const unsigned char* end = base + nbytes;
+  const unsigned char* eg = find_bytes(base, end, "<Nnet3ChainEg>");
+  if (!eg) {
+    g_error = "no <Nnet3ChainEg> token in the buffer";
+    return nullptr;
+  }
+  // binary examples are announced by "\0B" right before the token; text-mode egs cannot be parsed here
+  if (eg - base >= 2 && !(eg[-2] == 0 && eg[-1] == 'B')) {
+    g_error = "text-mode nnet3 chain examples are not supported (expected the binary marker before <Nnet3ChainEg>)";
+    return nullptr;
+  }
+  const unsigned char* next_eg = find_bytes(eg + 14, end, "<Nnet3ChainEg>");
+  const unsigned char* sup = find_bytes(eg, next_eg ? next_eg : end, "<Supervision> ");
+  if (!sup) {
+    g_error = "<Nnet3ChainEg> without a <Supervision> object";
+    return nullptr;
+  }
+  int64_t used = 0;
+  Supervision* out = parse_kaldi_supervision(sup, (int64_t)((next_eg ? next_eg : end) - sup), &used);
+  if (!out) return nullptr;
+  const unsigned char* tail = find_bytes(sup + used, next_eg ? next_eg : end, "</Nnet3ChainEg>");
+  const unsigned char* stop = tail ? tail + 15 : sup + used;
+  if (tail && stop < end && *stop == ' ') stop++;
+  if (consumed) *consumed = (int64_t)(stop - base);
+  return out;
+}
+
 // Nothing may propagate through the C ABI: a std::bad_alloc / std::length_error from a corrupt size field
 // or an exhausted host ends as an error return with torchain_last_error() set.
 int abi_exception_int() {
@@ -1922,6 +1975,13 @@ void* torchain_supervision_from_arrays(float weight, int32_t num_sequences, int3
 void* torchain_supervision_from_kaldi_bytes(const void* data, int64_t nbytes, int64_t* consumed) try {
   if (!data || nbytes <= 0) return fail_ptr("supervision: null / empty buffer");
   return parse_kaldi_supervision(data, nbytes, consumed);
+} catch (...) {
+  return abi_exception_ptr();
+}
+
+void* torchain_supervision_from_chain_egs(const void* data, int64_t nbytes, int64_t* consumed) try {
+  if (!data || nbytes <= 0) return fail_ptr("supervision: null / empty buffer");
+  return parse_chain_eg(data, nbytes, consumed);
 } catch (...) {
   return abi_exception_ptr();
 }

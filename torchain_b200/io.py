@@ -78,6 +78,31 @@ class Supervision:
         return cls(ptr), int(consumed.value)
 
     @classmethod
+    def from_chain_egs(cls, data, max_examples=None):
+        """The supervisions of the binary nnet3 chain examples in `data` (bytes of an egs ark, e.g. what
+        ``nnet3-chain-copy-egs ... ark:-`` writes), one handle per example, found by scanning for the
+        ``<Nnet3ChainEg>`` token like the reference's indexer (/root/reference/example/chime5/ark2scp.py:24-40).
+        What the reference's readers hand out per example (``Example.supervision``, io.py:74-76) -- without the
+        features.  ``Supervision.merge(handles)`` makes the minibatch."""
+        lib = _lib.load()
+        buf = (ctypes.c_char * len(data)).from_buffer_copy(data)
+        base = ctypes.addressof(buf)
+        out, pos = [], 0
+        while pos < len(data) and (max_examples is None or len(out) < max_examples):
+            if data.find(b"<Nnet3ChainEg>", pos) < 0:
+                break
+            consumed = ctypes.c_int64(0)
+            ptr = lib.torchain_supervision_from_chain_egs(ctypes.c_void_p(base + pos), len(data) - pos,
+                                                          ctypes.byref(consumed))
+            if not ptr:
+                raise ValueError("invalid chain example: " + _lib.last_error())
+            out.append(cls(ptr))
+            pos += int(consumed.value)
+        if not out:
+            raise ValueError("invalid chain example: no <Nnet3ChainEg> token in the buffer")
+        return out
+
+    @classmethod
     def merge(cls, supervisions):
         """One minibatch supervision from a list of examples, appended sequence-major: what the
         reference's egs reader obtains from Kaldi's MergeChainExamples

@@ -251,6 +251,34 @@ def make_nnet_output(seed, num_sequences, frames_per_sequence, num_pdfs, scale=1
     return (rng.standard_normal((rows, int(num_pdfs))) * scale).astype(np.float32)
 
 
+def write_openfst_binary(path, den):
+    """den.fst as OpenFst writes a VectorFst<StdArc> (what ``fst::ReadFstKaldi`` reads at
+    /root/reference/src/my_lib_example.cpp:131; layout in SURVEY.md section 8f-1), vectorised: int32 magic,
+    "vector" / "standard", version 2, flags 0, properties, start, #states, #arcs, then per state
+    {float final, int64 narcs, narcs x {int32 ilabel, int32 olabel, float weight, int32 nextstate}}."""
+    import struct
+    N, A = den.num_states, den.num_arcs
+    order = np.argsort(den.src, kind="stable")
+    counts = np.bincount(den.src, minlength=N).astype(np.int64)
+    begin = np.zeros(N + 1, dtype=np.int64)
+    np.cumsum(counts, out=begin[1:])
+    body = np.zeros(3 * N + 4 * A, dtype=np.uint32)          # everything is a multiple of 4 bytes
+    s_off = 3 * np.arange(N, dtype=np.int64) + 4 * begin[:-1]
+    body[s_off] = den.final_cost.astype(np.float32).view(np.uint32)
+    body[s_off + 1] = (counts & 0xFFFFFFFF).astype(np.uint32)   # int64 narcs, little endian (high word stays 0)
+    a_off = np.repeat(s_off + 3, counts) + 4 * (np.arange(A, dtype=np.int64) - np.repeat(begin[:-1], counts))
+    body[a_off] = den.ilabel[order].astype(np.int32).view(np.uint32)
+    body[a_off + 1] = den.ilabel[order].astype(np.int32).view(np.uint32)
+    body[a_off + 2] = den.cost[order].astype(np.float32).view(np.uint32)
+    body[a_off + 3] = den.dst[order].astype(np.int32).view(np.uint32)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<i", 2125659606))
+        for t in (b"vector", b"standard"):
+            f.write(struct.pack("<i", len(t)) + t)
+        f.write(struct.pack("<iiQqqq", 2, 0, 0, den.start, N, A))
+        f.write(body.tobytes())
+
+
 # --- BASELINE.json configurations -------------------------------------------
 def small_case(seed):
     """cfg 1: mirrors the ranges of the reference's native test
