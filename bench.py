@@ -125,7 +125,8 @@ def make_workload(name, B, T, rank):
         c["B"] = B
     if T:
         c["T"] = T
-    den = synth.make_den_fst(1234, c["N"], c["P"], mean_deg=c["mean_deg"])
+    den = (synth.make_den_fst_tied if c.get("tied") else synth.make_den_fst)(1234, c["N"], c["P"],
+                                                                              mean_deg=c["mean_deg"])
     if c.get("hubs"):
         den = synth.add_hubs(den, c["hubs"])
     sup = synth.make_supervision(1235 + 1000 * rank, den, c["B"], c["T"], num_paths=4, weight=1.0)

@@ -38,7 +38,8 @@ def _den(name):
     """The config's den graph with its oracle and library handles (built once per session)."""
     if name not in _den_cache:
         c = synth.CONFIGS[name]
-        den = synth.make_den_fst(1234, c["N"], c["P"], mean_deg=c["mean_deg"])
+        den = (synth.make_den_fst_tied if c.get("tied") else synth.make_den_fst)(1234, c["N"], c["P"],
+                                                                                  mean_deg=c["mean_deg"])
         g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
                                             den.final_cost, den.num_pdfs)
         _den_cache[name] = (den, ol.OracleDen(den), g)
@@ -206,3 +207,81 @@ def test_minibatch_from_chain_egs_bytes():
     loss.backward()
     assert rel(float(results.data[0]), r["objf"]) < OBJF_RTOL
     assert deriv_err(inp.grad.cpu().numpy(), -r["deriv"]) < DERIV_RTOL
+
+
+# ---- run-based ("tied") kernels: graphs whose pdfs belong to the state being entered -----------------------
+@pytest.mark.parametrize("B,T", [(128, 50), (65, 20), (130, 12), (300, 8)])
+def test_tied_cfg2_graph_matches_oracle(B, T):
+    """config 2's shape with tied pdfs (10 000 states, 300 k arcs, ~20 k runs): den_tied_forward / backward kernels.
+    B = 130 / 300 mix run-based passes of 128 with a per-arc pass for the remainder (2 / 44 sequences)."""
+    den, oden, g = _den("chime5_tied")
+    runs, _ = synth.in_pdf_runs(den)
+    assert runs * 3 <= den.num_arcs
+    _compare(den, oden, g, B, T, 5e-5, 0.1, seed=5000 + B, want_xent=(B == 128))
+
+
+def test_tied_and_per_arc_kernels_agree(monkeypatch):
+    """The same tied graph through both kernel families (TORCHAIN_TIED=0 forces the per-arc kernels)."""
+    den = synth.make_den_fst_tied(9, 3000, 400, mean_deg=20.0)
+    oden = ol.OracleDen(den)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("TORCHAIN_TIED", mode)       # read once, when the graph handle is created
+        g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
+                                            den.final_cost, den.num_pdfs)
+        out[mode] = _compare(den, oden, g, 100, 25, 5e-5, 1e-5, seed=5101, weight=0.5)
+    assert deriv_err(out["1"][1], out["0"][1].astype(np.float64)) < 1e-5
+
+
+def test_tied_kernels_on_degenerate_graph(monkeypatch):
+    """States without in-arcs (alpha = 0 through the scratch run) and without out-arcs (beta' = 0), forced onto the
+    run-based kernels."""
+    monkeypatch.setenv("TORCHAIN_TIED", "1")
+    src = np.array([0, 0, 1, 1, 2, 2, 3, 0], dtype=np.int32)
+    dst = np.array([0, 1, 2, 0, 0, 4, 1, 2], dtype=np.int32)
+    ilabel = np.array([1, 2, 3, 1, 1, 4, 2, 3], dtype=np.int32)    # tied: label = f(destination)
+    prob = np.array([0.3, 0.3, 0.5, 0.4, 0.6, 0.3, 0.9, 0.3])
+    den = synth.DenFst(5, 4, 0, src, dst, ilabel, (-np.log(prob)).astype(np.float32),
+                       np.array([np.inf, 2.3, 2.3, 2.3, 0.1], dtype=np.float32))
+    oden = ol.OracleDen(den)
+    g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
+                                        den.final_cost, den.num_pdfs)
+    B, T = 70, 6
+    labels = [2, 3, 1]
+    arc_begin, arc_dst, arc_label, arc_cost = [0], [], [], []
+    for i in range(B * T):
+        arc_dst.append(i + 1)
+        arc_label.append(labels[(i % T) % 3])
+        arc_cost.append(0.25)
+        arc_begin.append(i + 1)
+    arc_begin.append(B * T)
+    final = np.full(B * T + 1, np.inf, dtype=np.float32)
+    final[-1] = 0.0
+    sup = synth.SupFst(1.0, B, T, 4, np.array(arc_begin, dtype=np.int32), np.array(arc_dst, dtype=np.int32),
+                       np.array(arc_label, dtype=np.int32), np.array(arc_cost, dtype=np.float32), final)
+    y = synth.make_nnet_output(5, B, T, 4)
+    r = ol.chain(oden, ol.OracleSup(sup), y, l2=0.0, leaky=0.05, mode="fp64")
+    s = io.Supervision.from_arrays(sup.weight, B, T, 4, sup.arc_begin, sup.arc_dst, sup.arc_label, sup.arc_cost,
+                                   sup.final_cost)
+    res, d, _ = run_abi(g, s, y, 0.0, 0.05)
+    assert rel(res[0], r["objf"]) < OBJF_RTOL
+    assert deriv_err(d, r["deriv"]) < DERIV_RTOL
+
+
+def test_tied_host_buffer_entry():
+    import torch
+    den, oden, g = _den("chime5_tied")
+
+    def entry(g, s, y, l2, leaky, xent=0.0, want_xent=False):
+        lib = _lib.load()
+        rows, cols = y.shape
+        yh = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32)).pin_memory()
+        dh = torch.full((rows, cols), float("nan")).pin_memory()
+        res = np.zeros(3, dtype=np.float32)
+        ok = lib.torchain_ComputeChainObjfAndDeriv_host(g.ptr, s.ptr, yh.data_ptr(), rows, cols, cols,
+                                                        res.ctypes.data_as(ctypes.c_void_p), dh.data_ptr(), cols,
+                                                        None, 0, l2, leaky, 0.0, 0)
+        assert ok == 1, _lib.last_error()
+        return res, dh.numpy().copy(), None
+
+    _compare(den, oden, g, 128, 30, 5e-5, 0.1, seed=5201, entry=entry)

@@ -42,6 +42,7 @@ class DenParams(ctypes.Structure):  # tb::DenParams
                [(n, ctypes.c_void_p) for n in ("num_frame_off", "num_frame_arcs", "num_arc_pdf", "num_arc_seq",
                                                "num_arc_post", "y_ready")] + \
                [("y_chunk_frames", ctypes.c_int), ("deriv_progress", ctypes.c_void_p)] + \
+               [("rdir", DenDir), ("R", ctypes.c_int), ("arun", ctypes.c_void_p), ("wbuf", ctypes.c_void_p)] + \
                [(n, ctypes.c_void_p) for n in ("warp_busy", "cta_trace", "timeline")]
 
 
@@ -108,7 +109,8 @@ def _launches(lib):
 
 
 def _kernel(name):
-    for k in ("num_fb_kernel", "den_forward_kernel", "den_backward_kernel", "final_scalars_kernel", "final_deriv_kernel",
+    for k in ("num_fb_kernel", "den_tied_forward_kernel", "den_tied_backward_kernel", "den_forward_kernel",
+              "den_backward_kernel", "final_scalars_kernel", "final_deriv_kernel",
               "zero_kernel"):
         if k in name:
             return k
@@ -436,7 +438,7 @@ def _den_batches(lib):
 def test_denominator_launch_parameters(mock):
     """What the host hands the persistent kernels: geometry, sequence ranges of the contexts and passes,
     per-context buffers, the scales that fold supervision.weight / l2 / the sign into the derivative."""
-    assert ctypes.sizeof(DenParams) == 392 and ctypes.sizeof(DenBatch) == 792   # mirrors of chain_kernels.h
+    assert ctypes.sizeof(DenParams) == 472 and ctypes.sizeof(DenBatch) == 952   # mirrors of chain_kernels.h
     den = synth.make_den_fst(25, 500, 48, mean_deg=5.0)
     B, T, l2, leaky, w = 300, 4, 0.01, 0.2, 0.5
     sup = synth.make_supervision(26, den, B, T, num_paths=2, weight=w)
@@ -593,3 +595,151 @@ def test_host_buffer_entry_from_several_threads(mock):
     mock.my_lib_supervision_free(s)
     mock.my_lib_denominator_graph_free(g)
     assert not errors, errors
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Run-based ("tied") kernels: the streams the host builds, executed in numpy.
+# ---------------------------------------------------------------------------------------------------------
+def _arr(ptr, ct, n):
+    return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ct)), shape=(n,)).copy()
+
+
+def _dir_arrays(d, nbins, grid):
+    warp_arc_off = _arr(d.warp_arc_off, ctypes.c_int, nbins + 1)
+    out = dict(warp_arc_off=warp_arc_off, recs=_arr(d.arcs, ctypes.c_int32, 4 * int(warp_arc_off[-1])).reshape(-1, 4))
+    if d.tasks:
+        out["warp_task_off"] = _arr(d.warp_task_off, ctypes.c_int, nbins + 1)
+        out["tasks"] = _arr(d.tasks, ctypes.c_int32, 4 * int(out["warp_task_off"][-1])).reshape(-1, 4)
+        out["cta_arc_off"] = _arr(d.cta_arc_off, ctypes.c_int, grid + 1)
+    return out
+
+
+def _f32(i):
+    return np.array([i], dtype=np.int32).view(np.float32)[0].astype(np.float64)
+
+
+def test_tied_streams_executed_in_numpy_match_the_oracle(mock):
+    """A graph with tied pdfs takes the run-based kernels (den_tied_*).  The mock records their launch parameters;
+    this test walks the uploaded record streams exactly as the kernels do (forward: arc / run records with one row
+    per record; backward phase A: runs; phase B: arcs pointing at their run's W row) in float64 for one sequence
+    and compares log-likelihood and occupancies with the oracle's per-arc formulation."""
+    mock.mock_set_param_capture_for(b"den_tied_forward_kernel", ctypes.sizeof(DenBatch))
+    mock.mock_set_param_capture_for(b"den_tied_backward_kernel", ctypes.sizeof(DenBatch))
+    P, N, T, leaky = 30, 150, 7, 0.1
+    den = synth.make_den_fst_tied(5, N, P, mean_deg=8.0)
+    runs_expected, _ = synth.in_pdf_runs(den)
+    assert runs_expected * 3 <= den.num_arcs
+    B = 65                                              # the tied path needs a pass of more than 64 sequences
+    sup = synth.make_supervision(6, den, B, T, num_paths=2)
+    y = synth.make_nnet_output(7, B, T, P, scale=1.5).astype(np.float32)
+    g, s = _handles(mock, den, sup)
+    try:
+        mock.mock_reset_launches()
+        _compute(mock, g, s, y)
+        names = [mock.mock_launch_name(i).decode() for i in range(mock.mock_launch_count())]
+        assert [_kernel(n) for n in names if "den_" in n] == ["den_tied_forward_kernel", "den_tied_backward_kernel"]
+        i_f = [i for i, n in enumerate(names) if "den_tied_forward_kernel" in n][0]
+        c = DenBatch.from_buffer_copy(ctypes.string_at(mock.mock_launch_param0(i_f), ctypes.sizeof(DenBatch))).c[0]
+        grid, bins, rowbytes = 148, 14, 4 * 128
+        assert (c.BP, c.subs, c.N, c.P, c.R) == (128, 1, N, P, runs_expected)
+        fwd, bwd = _dir_arrays(c.dir[0], grid * bins, grid), _dir_arrays(c.dir[1], grid * bins, grid)
+        run_off = _arr(c.rdir.warp_arc_off, ctypes.c_int, grid * bins + 1)
+        runs = _arr(c.rdir.arcs, ctypes.c_int32, 4 * c.R).reshape(-1, 4)
+        assert run_off[0] == 0 and run_off[-1] == c.R and (np.diff(run_off) >= 0).all()
+        pi = np.zeros(N)
+        for tk in fwd["tasks"]:
+            pi[tk[0]] = _f32(tk[3])
+        assert sorted(fwd["tasks"][:, 0].tolist()) == list(range(N)) == sorted(bwd["tasks"][:, 0].tolist())
+        arc_recs = fwd["recs"][(fwd["recs"][:, 1] >= 0) & (fwd["recs"][:, 1] != 0)]
+        assert len(arc_recs) == den.num_arcs                       # every arc exactly once ...
+        assert (fwd["recs"][:, 1] < 0).sum() == c.R                # ... every run closed exactly once (no empty states here)
+        sq = 3                                                     # one sequence of the minibatch
+        e = np.exp(y[sq::B].astype(np.float64))                    # [T, P]
+        alpha = np.zeros((2, N))
+        alpha[0] = pi
+        S = np.zeros(T + 1)
+        S[0] = pi.sum()
+        arun = np.zeros((T, c.R + 1))
+
+        def walk(d, fn):
+            for b in range(grid * bins):
+                task = d["warp_task_off"][b]
+                for k in range(d["warp_arc_off"][b], d["warp_arc_off"][b + 1]):
+                    task = fn(d["recs"][k], task)
+
+        for t in range(1, T + 1):
+            prev, cur = alpha[(t - 1) & 1], alpha[t & 1]
+            st = dict(racc=0.0, sacc=0.0)
+
+            def frec(r, task):
+                if r[1] >= 0:
+                    st["racc"] += (prev[r[0] // rowbytes] + leaky * _f32(r[2]) * S[t - 1]) * _f32(r[1])
+                else:
+                    out = st["racc"] * e[t - 1, r[0] // rowbytes] / S[t - 1]
+                    arun[t - 1, r[2] // rowbytes] = out
+                    st["sacc"] += out
+                    st["racc"] = 0.0
+                    if r[1] & 1:
+                        cur[fwd["tasks"][task][0]] = st["sacc"]
+                        st["sacc"] = 0.0
+                        return task + 1
+                return task
+            walk(fwd, frec)
+            S[t] = cur.sum()
+        tot = S[T] * (1.0 + leaky * pi.sum())
+        logp = np.log(tot) + np.log(S[:T]).sum()
+        beta = np.zeros((2, N))
+        beta[T & 1] = 1.0 / tot
+        gamma = np.zeros((T, P))
+        for t in range(T - 1, -1, -1):
+            nxt, cur = beta[(t + 1) & 1], beta[t & 1]
+            bsum = leaky * (pi * nxt).sum()
+            W = np.zeros(c.R + 1)
+            for r in runs:                                          # phase A
+                full = nxt[r[0] // rowbytes] + bsum
+                gamma[t, r[1] // rowbytes] += arun[t, r[2] // rowbytes] * full
+                W[r[2] // rowbytes] = full * e[t, r[1] // rowbytes]
+            st = dict(X=0.0)
+
+            def brec(r, task):                                      # phase B
+                st["X"] += abs(_f32(r[2])) * W[r[0] // rowbytes]
+                if r[2] < 0:
+                    cur[bwd["tasks"][task][0]] = st["X"] / S[t]
+                    st["X"] = 0.0
+                    return task + 1
+                return task
+            walk(bwd, brec)
+        import oracle_lib as ol
+        oden = ol.OracleDen(den)
+        lp_ref, d_ref, ok = ol.den_only(oden, B, T, y.astype(np.float64), leaky=leaky)
+        gamma_ref = d_ref.reshape(T, B, P)[:, sq, :]
+        assert np.abs(gamma.sum(axis=1) - 1.0).max() < 1e-6
+        assert np.abs(gamma - gamma_ref).max() < 1e-6
+        # the oracle's log-likelihood is the sum over all B sequences: check this sequence's share through its own run
+        lp1, _, _ = ol.den_only(oden, 1, T, y[sq::B].astype(np.float64), leaky=leaky)
+        assert lp1 == pytest.approx(logp, rel=1e-6)
+    finally:
+        mock.my_lib_supervision_free(s)
+        mock.my_lib_denominator_graph_free(g)
+
+
+def test_untied_graphs_and_small_batches_keep_the_per_arc_kernels(mock):
+    den_u = synth.make_den_fst(5, 150, 30, mean_deg=8.0)            # a pdf per arc: as many runs as arcs
+    den_t = synth.make_den_fst_tied(5, 150, 30, mean_deg=8.0)
+    for den, B, tied in ((den_u, 65, False), (den_t, 64, False), (den_t, 130, True)):
+        sup = synth.make_supervision(6, den, B, 4, num_paths=2)
+        y = synth.make_nnet_output(7, B, 4, 30).astype(np.float32)
+        g, s = _handles(mock, den, sup)
+        try:
+            mock.mock_reset_launches()
+            _compute(mock, g, s, y)
+            names = [_kernel(mock.mock_launch_name(i).decode()) for i in range(mock.mock_launch_count())]
+            den_names = [n for n in names if "den_" in n]
+            if tied:   # 128 sequences run-based, the remaining 2 (padded to 32) per-arc
+                assert den_names == ["den_tied_forward_kernel", "den_tied_backward_kernel", "den_forward_kernel",
+                                     "den_backward_kernel"]
+            else:
+                assert den_names == ["den_forward_kernel", "den_backward_kernel"]
+        finally:
+            mock.my_lib_supervision_free(s)
+            mock.my_lib_denominator_graph_free(g)

@@ -126,8 +126,16 @@ struct DenPartition {  // one uploaded partition of both directions
   std::vector<double> work[2];  // [grid*kDenMainWarps] cost units assigned to each warp
 };
 
+struct TiedPartition {  // the run-based kernels' streams (uploaded once per device; not autotuned)
+  DevBuf arcs[2], tasks[2], cta_arc_off[2], cta_task_off[2], warp_task_off[2], warp_arc_off[2];
+  int max_arcs_cta[2] = {0, 0}, max_tasks_cta[2] = {0, 0};
+  DevBuf runs, cta_run_off, warp_run_off;
+  int max_runs_cta = 0;
+};
+
 struct DenDevice {  // per (device) state
   int grid = 0;
+  std::unique_ptr<TiedPartition> tied;  // built on first use if the graph qualifies
   // Partitions are never freed or overwritten while the handle lives: launches already
   // enqueued on other streams keep reading the generation they were given.
   std::vector<std::unique_ptr<DenPartition>> generations;
@@ -149,7 +157,7 @@ struct DenDevice {  // per (device) state
 constexpr int kCalibRounds = 3;
 
 struct Workspace {
-  DevBuf alpha, beta, tiles, zeroed, num_scratch, scratch_deriv, cta_trace;
+  DevBuf alpha, beta, tiles, zeroed, num_scratch, scratch_deriv, cta_trace, arun, wbuf;
   int trace_frames = 0, trace_grid = 0;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -181,14 +189,17 @@ struct Workspace {
 //   TORCHAIN_SPLIT_CAP=n        states with more than n arcs in a direction are split into sub-tasks (default 192)
 //   TORCHAIN_FORCE_UNSTAGED=1   arc slices stay in global memory even when they would fit shared memory
 //   TORCHAIN_NO_AUTOTUNE=1      the partition is not re-dealt from measured per-warp busy cycles
+//   TORCHAIN_TIED=0|1           never / always use the run-based kernels (default: when the graph has few runs per arc)
 struct GraphHooks {
   int split_cap = 192;
+  int tied = -1;
   bool force_unstaged = false, no_autotune = false;
   static GraphHooks from_env() {
     GraphHooks h;
     if (const char* e = getenv("TORCHAIN_SPLIT_CAP")) h.split_cap = std::max(2, atoi(e));
     h.force_unstaged = getenv("TORCHAIN_FORCE_UNSTAGED") != nullptr;
     h.no_autotune = getenv("TORCHAIN_NO_AUTOTUNE") != nullptr;
+    if (const char* e = getenv("TORCHAIN_TIED")) h.tied = atoi(e) != 0;
     return h;
   }
 };
@@ -200,6 +211,12 @@ struct DenGraph {
   std::vector<float> prob;
   std::vector<float> pi;
   double sum_pi = 0.0;
+  // runs = distinct (destination state, pdf) pairs, numbered in (state, pdf) order; run_of[a] = run of arc a.
+  // A graph whose pdfs are tied to the state being entered (a real den.fst) has ~2 runs per state; the
+  // run-based kernels (den_kernel.cu, "tied") are used when runs are few against arcs.
+  int R = 0;
+  std::vector<int> run_of, run_dst, run_pdf;
+  bool tied = false;
   std::mutex mu;
   std::map<int, std::unique_ptr<DenDevice>> dev;
   std::map<std::pair<int, void*>, std::unique_ptr<Workspace>> ws;
@@ -239,7 +256,8 @@ void lpt(const std::vector<int>& items, const std::vector<int>& cost, const std:
 //   dir 1: tasks = source states with their out-arcs     (other = destination)
 void build_dir(const DenGraph& g, int dir, int grid, int bins_per_cta, const std::vector<double>& speed /* [grid*bins_per_cta] */,
                unsigned rowbytes /* bytes of one [state|pdf] row of this geometry: 4 * BP */, DirHost* out,
-               std::vector<double>* work) {
+               std::vector<double>* work, const std::vector<int>* x_index = nullptr /* per arc: row index stored in
+               the record's first field instead of the other state (tied phase B: the arc's run); never split */) {
   const int N = g.N, A = g.A;
   std::vector<int> deg(N, 0), begin(N + 1, 0);
   const std::vector<int>& key = dir == 0 ? g.dst : g.src;
@@ -252,7 +270,7 @@ void build_dir(const DenGraph& g, int dir, int grid, int bins_per_cta, const std
   const int kTaskOverhead = 3;  // fixed per-state cost in arc units (prologue, store, partial sums)
   // States with very many arcs (real den graphs are heavy-tailed) would be one serial warp task;
   // they are split into sub-tasks of at most `cap` arcs that accumulate with REDs.
-  const int cap = g.hooks.split_cap;
+  const int cap = x_index ? std::numeric_limits<int>::max() : g.hooks.split_cap;
   struct Item {
     int state, first, count, flag;  // arcs [first, first+count) of the state's CSR slice
   };
@@ -308,7 +326,7 @@ void build_dir(const DenGraph& g, int dir, int grid, int bins_per_cta, const std
         for (int k = begin[s] + item.first; k < begin[s] + item.first + item.count; k++) {
           const int a = arc_of[k];
           int4 ar;  // state / pdf stored as row BYTE offsets: the gather address is base + offset
-          ar.x = (int)((unsigned)other[a] * rowbytes);
+          ar.x = (int)((unsigned)(x_index ? (*x_index)[a] : other[a]) * rowbytes);
           ar.y = (int)((unsigned)g.pdf[a] * rowbytes);
           float pr = g.prob[a], pio = g.pi[other[a]];
           std::memcpy(&ar.z, &pr, 4);
@@ -317,7 +335,7 @@ void build_dir(const DenGraph& g, int dir, int grid, int bins_per_cta, const std
         }
         if (item.count == 0) {  // a state without arcs still needs its end-of-state marker
           int4 ar;
-          ar.x = (int)((unsigned)s * rowbytes);
+          ar.x = x_index ? 0 : (int)((unsigned)s * rowbytes);
           ar.y = 0;
           ar.z = 0;  // probability 0.0f
           ar.w = 0;
@@ -415,6 +433,38 @@ DenGraph* make_den_graph(int32_t N, int32_t A, const int32_t* src, const int32_t
   for (int s = 0; s < N; s++) {
     g->pi[s] = (float)avg[s];
     g->sum_pi += (double)g->pi[s];
+  }
+  // runs: arcs sorted by (destination, pdf)
+  {
+    std::vector<int> order(A);
+    for (int a = 0; a < A; a++) order[a] = a;
+    std::sort(order.begin(), order.end(), [&](int x, int y) {
+      if (g->dst[x] != g->dst[y]) return g->dst[x] < g->dst[y];
+      if (g->pdf[x] != g->pdf[y]) return g->pdf[x] < g->pdf[y];
+      return x < y;
+    });
+    g->run_of.assign(A, 0);
+    for (int k = 0; k < A; k++) {
+      const int a = order[k];
+      if (k == 0 || g->dst[a] != g->dst[order[k - 1]] || g->pdf[a] != g->pdf[order[k - 1]]) {
+        g->run_dst.push_back(g->dst[a]);
+        g->run_pdf.push_back(g->pdf[a]);
+      }
+      g->run_of[a] = (int)g->run_dst.size() - 1;
+    }
+    g->R = (int)g->run_dst.size();
+    // worth it when an arc's exp(y) gather and occupancy RED are shared by >= 3 arcs on average; split states
+    // (more than split_cap arcs in a direction) are only handled by the per-arc kernels
+    std::vector<int> din(N, 0), dout(N, 0);
+    for (int a = 0; a < A; a++) {
+      din[g->dst[a]]++;
+      dout[g->src[a]]++;
+    }
+    int maxdeg = 0;
+    for (int s = 0; s < N; s++) maxdeg = std::max(maxdeg, std::max(din[s], dout[s]));
+    g->tied = A > 0 && (int64_t)g->R * 3 <= (int64_t)A && maxdeg <= g->hooks.split_cap;
+    if (g->hooks.tied == 0) g->tied = false;
+    if (g->hooks.tied == 1 && A > 0 && maxdeg <= 4 * g->hooks.split_cap) g->tied = true;
   }
   return g.release();
 }
@@ -949,6 +999,113 @@ int build_partition(DenGraph* g, DenDevice* d, int subs = 1) {
   return 1;
 }
 
+
+// Streams of the run-based kernels (den_kernel.cu "tied"): forward = destination states with their in-arcs
+// grouped by run, every run closed by a run record; phase A = the runs dealt evenly; phase B = source states
+// with their out-arcs, each pointing at the W row of its run.
+int build_tied_partition(DenGraph* g, DenDevice* d) {
+  const int N = g->N, A = g->A, R = g->R, grid = d->grid, bins = tb::kDenMainWarps;
+  const unsigned rowbytes = 4u * (unsigned)tb::kCtxBP;
+  auto part = std::make_unique<TiedPartition>();
+  // ---- forward
+  {
+    std::vector<int> deg(N, 0), begin(N + 1, 0);
+    for (int a = 0; a < A; a++) deg[g->dst[a]]++;
+    for (int s = 0; s < N; s++) begin[s + 1] = begin[s] + deg[s];
+    std::vector<int> arc_of(A), pos(begin.begin(), begin.end() - 1);
+    for (int a = 0; a < A; a++) arc_of[pos[g->dst[a]]++] = a;
+    for (int s = 0; s < N; s++)  // runs are numbered in (state, pdf) order: sorting by run groups a state's arcs
+      std::stable_sort(arc_of.begin() + begin[s], arc_of.begin() + begin[s + 1],
+                       [&](int x, int y) { return g->run_of[x] < g->run_of[y]; });
+    std::vector<int> cost(N), all(N);
+    for (int s = 0; s < N; s++) {
+      int runs = 0;
+      for (int k = begin[s]; k < begin[s + 1]; k++)
+        if (k == begin[s] || g->run_of[arc_of[k]] != g->run_of[arc_of[k - 1]]) runs++;
+      cost[s] = deg[s] + std::max(runs, 1) + 2;
+      all[s] = s;
+    }
+    std::vector<std::vector<int>> by_cta;
+    lpt(all, cost, std::vector<double>(grid, 1.0), &by_cta);
+    std::vector<int4> recs, tasks;
+    std::vector<int> cta_arc_off(1, 0), cta_task_off(1, 0), warp_task_off(1, 0), warp_arc_off(1, 0);
+    for (int c = 0; c < grid; c++) {
+      std::vector<std::vector<int>> by_warp;
+      lpt(by_cta[c], cost, std::vector<double>(bins, 1.0), &by_warp);
+      const int arc0 = (int)recs.size(), task0 = (int)tasks.size();
+      for (int w = 0; w < bins; w++) {
+        for (int s : by_warp[w]) {
+          int4 tk = make_int4(s, (int)recs.size() - arc0, 0, 0);
+          float pis = g->pi[s];
+          std::memcpy(&tk.w, &pis, 4);
+          tasks.push_back(tk);
+          auto run_record = [&](int pdf, int run, bool last) {
+            recs.push_back(make_int4((int)((unsigned)pdf * rowbytes), (int)(0x80000000u | (last ? 1u : 0u)),
+                                     (int)((unsigned)run * rowbytes), 0));
+          };
+          for (int k = begin[s]; k < begin[s + 1]; k++) {
+            const int a = arc_of[k];
+            int4 ar = make_int4((int)((unsigned)g->src[a] * rowbytes), 0, 0, 0);
+            float pr = g->prob[a], pio = g->pi[g->src[a]];
+            std::memcpy(&ar.y, &pr, 4);
+            std::memcpy(&ar.z, &pio, 4);
+            recs.push_back(ar);
+            const bool run_ends = k + 1 == begin[s + 1] || g->run_of[arc_of[k + 1]] != g->run_of[a];
+            if (run_ends) run_record(g->pdf[a], g->run_of[a], k + 1 == begin[s + 1]);
+          }
+          if (deg[s] == 0) run_record(0, R, true);  // no in-arcs: alpha = 0, written through the scratch run row R
+        }
+        const int stream_begin = warp_arc_off.back();
+        while (((int)recs.size() - stream_begin) % tb::kStreamPad != 0)
+          recs.push_back(make_int4(0, 0, 0, 0));  // zero-probability arc behind the last run record: feeds nothing
+        warp_task_off.push_back((int)tasks.size());
+        warp_arc_off.push_back((int)recs.size());
+      }
+      cta_arc_off.push_back((int)recs.size());
+      cta_task_off.push_back((int)tasks.size());
+      part->max_arcs_cta[0] = std::max(part->max_arcs_cta[0], (int)recs.size() - arc0);
+      part->max_tasks_cta[0] = std::max(part->max_tasks_cta[0], (int)tasks.size() - task0);
+    }
+    CUDA_OK(upload(part->arcs[0], recs));
+    CUDA_OK(upload(part->tasks[0], tasks));
+    CUDA_OK(upload(part->cta_arc_off[0], cta_arc_off));
+    CUDA_OK(upload(part->cta_task_off[0], cta_task_off));
+    CUDA_OK(upload(part->warp_task_off[0], warp_task_off));
+    CUDA_OK(upload(part->warp_arc_off[0], warp_arc_off));
+  }
+  // ---- phase B: the per-arc builder with the arc's run as the gathered row, never split
+  {
+    DirHost h;
+    std::vector<double> work;
+    build_dir(*g, 1, grid, bins, std::vector<double>((size_t)grid * bins, 1.0), rowbytes, &h, &work, &g->run_of);
+    CUDA_OK(upload(part->arcs[1], h.arcs));
+    CUDA_OK(upload(part->tasks[1], h.tasks));
+    CUDA_OK(upload(part->cta_arc_off[1], h.cta_arc_off));
+    CUDA_OK(upload(part->cta_task_off[1], h.cta_task_off));
+    CUDA_OK(upload(part->warp_task_off[1], h.warp_task_off));
+    CUDA_OK(upload(part->warp_arc_off[1], h.warp_arc_off));
+    part->max_arcs_cta[1] = h.max_arcs_cta;
+    part->max_tasks_cta[1] = h.max_tasks_cta;
+  }
+  // ---- phase A: runs, contiguous equal shares (run order = destination-state order)
+  {
+    std::vector<int4> runs(R);
+    for (int r = 0; r < R; r++)
+      runs[r] = make_int4((int)((unsigned)g->run_dst[r] * rowbytes), (int)((unsigned)g->run_pdf[r] * rowbytes),
+                          (int)((unsigned)r * rowbytes), 0);
+    const int nb = grid * bins;
+    std::vector<int> cta_run_off(grid + 1), warp_run_off(nb + 1);
+    for (int b = 0; b <= nb; b++) warp_run_off[b] = (int)((int64_t)R * b / nb);
+    for (int c = 0; c <= grid; c++) cta_run_off[c] = warp_run_off[c * bins];
+    for (int c = 0; c < grid; c++) part->max_runs_cta = std::max(part->max_runs_cta, cta_run_off[c + 1] - cta_run_off[c]);
+    CUDA_OK(upload(part->runs, runs));
+    CUDA_OK(upload(part->cta_run_off, cta_run_off));
+    CUDA_OK(upload(part->warp_run_off, warp_run_off));
+  }
+  d->tied = std::move(part);
+  return 1;
+}
+
 int get_den_device(DenGraph* g, int device, DenDevice** out) {
   std::lock_guard<std::mutex> lock(g->mu);
   auto it = g->dev.find(device);
@@ -1282,14 +1439,32 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   np.arc_post = reinterpret_cast<float*>(nb + off_post);
   np.chain_logprob = reinterpret_cast<double*>(nb + off_clp);
 
-  tb::DenParams dp;
-  // ---- denominator workspace.  A launch pair covers up to kMaxBP = 256 sequences as one or two
+  tb::DenParams dp = {};
+  // ---- run-based ("tied") kernels: graphs with few runs per arc, passes of one context of 128 sequences
+  TiedPartition* tp = nullptr;
+  if (g->tied && B > tb::kCtxBP / 2) {
+    std::lock_guard<std::mutex> lock(g->mu);
+    if (!dd->tied && !build_tied_partition(g, dd)) return 0;
+    tp = dd->tied.get();
+  }
+  const int pass_cap = tp ? tb::kCtxBP : tb::kMaxBP;  // sequences per launch pair
+  const int rem = B % tb::kCtxBP;
+  const bool tied_rest_general = tp && rem != 0 && pad_batch(rem) != tb::kCtxBP;  // a short last pass runs per-arc
+
+  // ---- denominator workspace.  A per-arc launch pair covers up to kMaxBP = 256 sequences as one or two
   // contexts of kCtxBP = 128 (own buffers each); larger minibatches run as consecutive passes.
-  const int nctx_max = B > tb::kCtxBP ? 2 : 1;
+  const int nctx_max = (!tp && B > tb::kCtxBP) ? 2 : 1;
   const int BPmax = B > tb::kCtxBP ? tb::kCtxBP : pad_batch(B);
   const size_t alpha_ctx = (size_t)(T + 1) * N * BPmax, beta_ctx = (size_t)3 * N * BPmax,
                tile_ctx = (size_t)2 * P * BPmax;
-  CUDA_OK(ws->alpha.reserve(sizeof(float) * alpha_ctx * nctx_max));
+  if (tp) {  // alpha is a two-row ping-pong; the forward contributions of the runs take the alpha store's place
+    const size_t general = tied_rest_general ? (size_t)(T + 1) * N * pad_batch(rem) : 0;
+    CUDA_OK(ws->alpha.reserve(sizeof(float) * std::max((size_t)2 * N * tb::kCtxBP, general)));
+    CUDA_OK(ws->arun.reserve(sizeof(float) * (size_t)T * (g->R + 1) * tb::kCtxBP));
+    CUDA_OK(ws->wbuf.reserve(sizeof(float) * (size_t)(g->R + 1) * tb::kCtxBP));
+  } else {
+    CUDA_OK(ws->alpha.reserve(sizeof(float) * alpha_ctx * nctx_max));
+  }
   CUDA_OK(ws->beta.reserve(sizeof(float) * beta_ctx * nctx_max));
   CUDA_OK(ws->tiles.reserve(sizeof(float) * tile_ctx * nctx_max));  // etile
   // zeroed block: per context {gtile | Ssum | Bsum | barriers}, then the timeline; scalars + results after it
@@ -1343,7 +1518,7 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   bool calibrating;
   {
     std::lock_guard<std::mutex> lock(g->mu);
-    calibrating = B <= tb::kMaxBP && tb::den_subs(BPmax) == 1 && dd->calib_rounds_done < kCalibRounds &&
+    calibrating = !tp && B <= tb::kMaxBP && tb::den_subs(BPmax) == 1 && dd->calib_rounds_done < kCalibRounds &&
                   !dd->calib_pending;
   }
   const bool calib_async = calibrating && results_host == nullptr;
@@ -1368,7 +1543,7 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   dp.num_arc_post = np.arc_post;
   dp.y_ready = chunked.flags;
   dp.y_chunk_frames = chunked.chunk_frames;
-  dp.deriv_progress = (B <= tb::kMaxBP) ? chunked.deriv_progress : nullptr;
+  dp.deriv_progress = (B <= pass_cap) ? chunked.deriv_progress : nullptr;  // single-pass calls only
   dp.cta_trace = nullptr;
   if (g_profile.load() >= 2) {
     const size_t tb_bytes = sizeof(unsigned long long) * 2 * (size_t)(T + 1) * dd->grid * (4 + tb::kDenWarps);
@@ -1382,18 +1557,46 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   ws->timeline_dev = zb + z_tl;
   ws->timeline_len = 2 * T + 6;
   bool numerator_done = false;
-  for (int seq0 = 0; seq0 < B; seq0 += tb::kMaxBP) {
-    const int pass_B = std::min(B - seq0, tb::kMaxBP);
+  for (int seq0 = 0; seq0 < B; seq0 += pass_cap) {
+    const int pass_B = std::min(B - seq0, pass_cap);
     tb::DenBatch batch;
     batch.nctx = pass_B > tb::kCtxBP ? 2 : 1;
     dp.BP = batch.nctx == 2 ? tb::kCtxBP : pad_batch(pass_B);
     dp.subs = tb::den_subs(dp.BP);
+    const bool tied_pass = tp && dp.BP == tb::kCtxBP;
     DenPartition* part = nullptr;
-    if (!partition_for(dp.subs, &part)) return 0;
-    bind(part);
-    // arc / task slices are staged in shared memory unless the graph is too large for it
-    dp.arcs_in_smem = 1;
-    if (tb::den_smem_bytes(dp) > 200 * 1024 || g->hooks.force_unstaged) dp.arcs_in_smem = 0;
+    if (tied_pass) {
+      for (int dir = 0; dir < 2; dir++) {
+        dp.dir[dir].arcs = tp->arcs[dir].as<int4>();
+        dp.dir[dir].tasks = tp->tasks[dir].as<int4>();
+        dp.dir[dir].cta_arc_off = tp->cta_arc_off[dir].as<int>();
+        dp.dir[dir].cta_task_off = tp->cta_task_off[dir].as<int>();
+        dp.dir[dir].warp_task_off = tp->warp_task_off[dir].as<int>();
+        dp.dir[dir].warp_arc_off = tp->warp_arc_off[dir].as<int>();
+        dp.dir[dir].max_arcs_cta = tp->max_arcs_cta[dir];
+        dp.dir[dir].max_tasks_cta = tp->max_tasks_cta[dir];
+      }
+      dp.rdir.arcs = tp->runs.as<int4>();
+      dp.rdir.tasks = nullptr;
+      dp.rdir.cta_arc_off = tp->cta_run_off.as<int>();
+      dp.rdir.cta_task_off = nullptr;
+      dp.rdir.warp_task_off = nullptr;
+      dp.rdir.warp_arc_off = tp->warp_run_off.as<int>();
+      dp.rdir.max_arcs_cta = tp->max_runs_cta;
+      dp.rdir.max_tasks_cta = 0;
+      dp.R = g->R;
+      dp.arun = ws->arun.as<float>();
+      dp.wbuf = ws->wbuf.as<float>();
+      dp.has_split = 0;
+      dp.arcs_in_smem = 1;
+      if (tb::den_tied_smem_bytes(dp) > 220 * 1024) return fail("tied denominator graph: a CTA's streams do not fit shared memory");
+    } else {
+      if (!partition_for(dp.subs, &part)) return 0;
+      bind(part);
+      // arc / task slices are staged in shared memory unless the graph is too large for it
+      dp.arcs_in_smem = 1;
+      if (tb::den_smem_bytes(dp) > 200 * 1024 || g->hooks.force_unstaged) dp.arcs_in_smem = 0;
+    }
     for (int ci = 0; ci < 2; ci++) {
       tb::DenParams& c = batch.c[ci];
       c = dp;
@@ -1429,12 +1632,12 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
       CUDA_OK(tb::launch_numerator(np, ws->side));
       CUDA_OK(cudaEventRecord(ws->ev_join, ws->side));
     }
-    CUDA_OK(tb::launch_den(batch, 0, dd->grid, stream));
+    CUDA_OK(tied_pass ? tb::launch_den_tied(batch, 0, dd->grid, stream) : tb::launch_den(batch, 0, dd->grid, stream));
     if (!numerator_done) {
       CUDA_OK(cudaStreamWaitEvent(stream, ws->ev_join, 0));
       numerator_done = true;
     }
-    CUDA_OK(tb::launch_den(batch, 1, dd->grid, stream));
+    CUDA_OK(tied_pass ? tb::launch_den_tied(batch, 1, dd->grid, stream) : tb::launch_den(batch, 1, dd->grid, stream));
     if (calib_async) {
       std::lock_guard<std::mutex> lock(g->mu);
       if (!dd->calib_pending) {

@@ -95,6 +95,13 @@ struct DenParams {
   // release (at the start of step t-1, and once more after the last barrier), so the host can start
   // copying finished frame chunks out while the recurrence is still running.  null = unused.
   unsigned* deriv_progress;
+  // ---- tied-pdf ("run-based") kernels only (den_tied_*): a run is a (destination state, pdf) pair
+  // dir[0] then holds the forward stream of arc + run records, dir[1] the backward stream of arcs that
+  // point at their run's W row, and rdir the runs dealt evenly over the bins (arcs = run records, no tasks).
+  DenDir rdir;
+  int R;             // number of runs
+  float* arun;       // T x R x BP   forward contribution of every run, a_{t+1}(run), written forward / read backward
+  float* wbuf;       // R x BP       W_t(run) = (beta'_{t+1}(dst) + b_{t+1}) * e_t(pdf) of the current backward step
   unsigned long long* warp_busy;  // [2][grid][kDenWarps] SM cycles each warp spent in its frame work (feeds the partition autotuner)
   unsigned long long* cta_trace;  // optional [phase][frame][cta][4]: main warp 0 done, aux warp 0 done, CTA done, barrier exit
   unsigned long long* timeline;  // optional: globaltimer at every phase boundary (2T+5 entries), or null
@@ -111,6 +118,10 @@ size_t den_smem_bytes(const DenParams& p);
 // Enqueues one persistent launch (cooperative, `grid` CTAs): phase 0 = forward (alpha)
 // recurrence over all frames, phase 1 = backward (beta + derivative) recurrence.
 cudaError_t launch_den(const DenBatch& b, int phase, int grid, cudaStream_t stream);
+// The same two launches for a graph with tied pdfs (few runs per state): one context of kCtxBP sequences,
+// arc / run slices in shared memory, no split states.  den_tied_smem_bytes(p) must fit the device.
+size_t den_tied_smem_bytes(const DenParams& p);
+cudaError_t launch_den_tied(const DenBatch& b, int phase, int grid, cudaStream_t stream);
 int den_max_grid(int device);  // co-resident CTAs (one per SM)
 int den_subs(int BP);          // lane groups per warp for a padded batch size
 

@@ -1129,6 +1129,437 @@ __device__ __forceinline__ void den_chain_body(const DenBatch& batch) {
   stamp();
 }
 
+#ifndef DEN_F_MAXNREG_TIED
+#define DEN_F_MAXNREG_TIED 112
+#endif
+
+// =====================================================================================================
+// Tied-pdf ("run-based") recurrences.
+//
+// In a real den.fst the pdf on an arc belongs to the HMM state being entered, so the in-arcs of a state
+// carry very few distinct pdfs: ~2 RUNS = (destination state, pdf) pairs per state for ~30 in-arcs.
+// Grouping by run takes exp(y) and the occupancy RED out of the per-arc work:
+//   forward   a_{t+1}(r) = e_t(pdf_r) / S_t * sum_{arcs i->j in r} alpha'_t(i) p     (one exp row per RUN)
+//             alpha_{t+1}(j) = sum_{runs of j} a_{t+1}(r);  a_{t+1}(r) is kept (T x R x BP, instead of the
+//             alpha store: the backward pass needs nothing else from the forward pass)
+//   backward  phase A, per run:   full = beta'_{t+1}(j_r) + b_{t+1};  gamma_t(pdf_r) += a_{t+1}(r) * full  (one RED per RUN)
+//                                 W_t(r) = full * e_t(pdf_r)
+//             phase B, per arc:   beta'_t(i) = (1 / S_t) * sum_{arcs i->j} p * W_t(run of the arc)          (ONE gather per arc)
+// L2 bytes per sequence-frame: 8 A + ~20 R against 20 A for the per-arc kernels (A arcs, R runs): 2.1x fewer at
+// R = A / 15.  Same results: it is the same sum in a different order (tools/tied_pdf_study.py holds the algebra
+// in numpy against the oracle).  The host picks these kernels when the graph has few runs per arc; phase A and
+// phase B are separated by a second grid barrier per frame.
+//
+// Streams (16-byte records, staged in shared memory):
+//   forward   arc record {alpha row offset of the source, prob bits (>= 0), pi[source] bits, -}
+//             run record {exp row offset of the pdf, 0x80000000 | last-run-of-state, a_run row offset, -}
+//             -> exactly ONE 512-byte gather per record, whatever its kind
+//   phase A   run record {beta row offset of the destination, exp row offset, a_run / W row offset, -}
+//   phase B   arc record {W row offset of the arc's run, -, prob bits | end-of-state sign, -}
+// =====================================================================================================
+struct TiedSmem {
+  float* red;    // [kDenMainWarps][BP]
+  float* tile;   // [kDenAuxWarps][32][33]
+  int4* tasks;   // [max tasks per CTA over both directions]
+  int4* arcs;    // [max records per CTA over both directions]
+  int4* runs;    // [max runs per CTA]
+};
+__device__ __forceinline__ TiedSmem carve_tied(unsigned char* base, const DenParams& p) {
+  TiedSmem s;
+  s.red = reinterpret_cast<float*>(base);
+  size_t off = sizeof(float) * kDenMainWarps * p.BP;
+  s.tile = reinterpret_cast<float*>(base + off);
+  off += sizeof(float) * kDenAuxWarps * 32 * 33;
+  off = (off + 15) & ~size_t(15);
+  s.tasks = reinterpret_cast<int4*>(base + off);
+  off += sizeof(int4) * max(p.dir[0].max_tasks_cta, p.dir[1].max_tasks_cta);
+  s.arcs = reinterpret_cast<int4*>(base + off);
+  off += sizeof(int4) * max(p.dir[0].max_arcs_cta, p.dir[1].max_arcs_cta);
+  s.runs = reinterpret_cast<int4*>(base + off);
+  return s;
+}
+
+template <int SA>
+struct RowBuf {
+  float a[SA][4];
+};
+
+__device__ __forceinline__ void alpha_step_tied(const DenParams& p, const int4* __restrict__ recs,
+                                                const int4* __restrict__ tasks, int abeg, int aend, int tb, int t,
+                                                float* red, int warp, int lane) {
+  constexpr int V = 4, kSA = 2, kStages = 3;
+  const int BP = p.BP, col = lane * V;
+  const float* __restrict__ alpha_prev = p.alpha + (size_t)((t - 1) & 1) * p.N * BP;
+  float* __restrict__ alpha_cur = p.alpha + (size_t)(t & 1) * p.N * BP;
+  const float* __restrict__ et = p.etile + (size_t)((t - 1) & 1) * p.P * BP;
+  float* __restrict__ arun = p.arun + (size_t)(t - 1) * p.R * BP;
+  const double* Sprev = p.Ssum + (size_t)(t - 1) * BP;
+  const int4* __restrict__ a = recs + abeg;
+  const int n = aend - abeg;
+  const unsigned rowbytes = (unsigned)BP * 4u;
+  const char* const ua = reinterpret_cast<const char*>(alpha_prev + col);
+  const char* const ue = reinterpret_cast<const char*>(et + col);
+  char* const ur = reinterpret_cast<char*>(arun + col);
+  double Sd[V];
+#pragma unroll
+  for (int v = 0; v < V; v++) Sd[v] = __ldcg(Sprev + col + v);
+  RowBuf<kSA> ring[kStages];
+  auto load = [&](RowBuf<kSA>& buf, int k) {
+    if (k < n) {
+#pragma unroll
+      for (int u = 0; u < kSA; u++) {
+        const int2 r = *reinterpret_cast<const int2*>(a + k + u);  // {row byte offset, prob >= 0 | run marker}
+        ld_cg<V>(reinterpret_cast<const float*>((r.y < 0 ? ue : ua) + (unsigned)r.x), buf.a[u]);
+      }
+    }
+  };
+  float lamS[V], invS[V], part[V], racc[V], sacc[V];
+  int task = tb;
+  auto consume = [&](RowBuf<kSA>& buf, int k) {
+#pragma unroll
+    for (int u = 0; u < kSA; u++) {
+      const int4 r = a[k + u];
+      if (r.y >= 0) {  // arc: racc += (alpha(src) + leaky * pi(src) * S) * p
+        const float pr = __int_as_float(r.y), pi = __int_as_float(r.z);
+        const u64 pr2 = pk2(pr, pr), pi2 = pk2(pi, pi);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const u64 ad = fma2(pi2, pk2(lamS[2 * h], lamS[2 * h + 1]), pk2(buf.a[u][2 * h], buf.a[u][2 * h + 1]));
+          upk2(fma2(ad, pr2, pk2(racc[2 * h], racc[2 * h + 1])), racc[2 * h], racc[2 * h + 1]);
+        }
+      } else {  // end of a run: buf holds exp(y) of the run's pdf
+        float out[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          out[v] = racc[v] * buf.a[u][v] * invS[v];
+          sacc[v] += out[v];
+          racc[v] = 0.f;
+        }
+        __stcs(reinterpret_cast<float4*>(ur + (unsigned)r.z), make_float4(out[0], out[1], out[2], out[3]));
+        if (r.y & 1) {  // last run of this state
+          const int4 tk = tasks[task++];
+#pragma unroll
+          for (int v = 0; v < V; v++) part[v] += sacc[v];
+          st_vec<V>(row_ptr(alpha_cur + col, tk.x, rowbytes), sacc);
+#pragma unroll
+          for (int v = 0; v < V; v++) sacc[v] = 0.f;
+        }
+      }
+    }
+  };
+#pragma unroll
+  for (int st = 0; st < kStages; st++) load(ring[st], st * kSA);
+#pragma unroll
+  for (int v = 0; v < V; v++) {
+    const float S = (float)Sd[v];
+    lamS[v] = p.leaky * S;
+    invS[v] = 1.0f / S;
+    part[v] = racc[v] = sacc[v] = 0.f;
+  }
+  for (int k = 0; k < n;) {
+#pragma unroll
+    for (int st = 0; st < kStages; st++) {
+      if (k < n) {
+        consume(ring[st], k);
+        load(ring[st], k + kStages * kSA);
+        k += kSA;
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < V; v++) red[warp * BP + col + v] = part[v];
+}
+
+// phase A of backward step t: per run, occupancy RED and W_t(run)
+__device__ __forceinline__ void runs_step_tied(const DenParams& p, const int4* __restrict__ runs, int rbeg, int rend,
+                                               int t, int lane) {
+  constexpr int V = 4, kD = 2;
+  const int BP = p.BP, col = lane * V;
+  const char* const ub = reinterpret_cast<const char*>(p.beta + (size_t)((t + 1) & 1) * p.N * BP + col);
+  const char* const ue = reinterpret_cast<const char*>(p.etile + (size_t)(t & 1) * p.P * BP + col);
+  const char* const ur = reinterpret_cast<const char*>(p.arun + (size_t)t * p.R * BP + col);
+  char* const ug = reinterpret_cast<char*>(p.gtile + (size_t)(t & 1) * p.P * BP + col);
+  char* const uw = reinterpret_cast<char*>(p.wbuf + col);
+  const double* Bn = p.Bsum + (size_t)(t + 1) * BP;
+  float bv[V];
+  float bn[kD][V], ev[kD][V], ar[kD][V];
+  auto load = [&](int slot, int k) {
+    if (k < rend) {
+      const int4 r = runs[k];
+      ld_cg<V>(reinterpret_cast<const float*>(ub + (unsigned)r.x), bn[slot]);
+      ld_cg<V>(reinterpret_cast<const float*>(ue + (unsigned)r.y), ev[slot]);
+      ld_cs<V>(reinterpret_cast<const float*>(ur + (unsigned)r.z), ar[slot]);
+    }
+  };
+#pragma unroll
+  for (int d = 0; d < kD; d++) load(d, rbeg + d);
+#pragma unroll
+  for (int v = 0; v < V; v++) bv[v] = p.leaky * (float)__ldcg(Bn + col + v);
+  for (int k = rbeg; k < rend; k += kD) {
+#pragma unroll
+    for (int d = 0; d < kD; d++) {
+      if (k + d < rend) {
+        const int4 r = runs[k + d];
+        float g[V], w[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          const float full = bn[d][v] + bv[v];
+          g[v] = ar[d][v] * full;
+          w[v] = full * ev[d][v];
+        }
+        red_add<V>(reinterpret_cast<float*>(ug + (unsigned)r.y), g);
+        st_vec<V>(reinterpret_cast<float*>(uw + (unsigned)r.z), w);
+        load(d, k + d + kD);
+      }
+    }
+  }
+}
+
+// phase B of backward step t: beta'_t(i) = (1/S_t) sum_{arcs i->j} p W_t(run of the arc)
+__device__ __forceinline__ void beta_step_tied(const DenParams& p, const int4* __restrict__ recs,
+                                               const int4* __restrict__ tasks, int abeg, int aend, int tb, int te, int t,
+                                               float* red, int warp, int lane, double& ab) {
+  constexpr int V = 4, kSA = 4, kStages = 2;
+  const int BP = p.BP, col = lane * V;
+  float* __restrict__ beta_cur = p.beta + (size_t)(t & 1) * p.N * BP;
+  const double* St = p.Ssum + (size_t)t * BP;
+  const int4* __restrict__ a = recs + abeg;
+  const int n = aend - abeg;
+  const unsigned rowbytes = (unsigned)BP * 4u;
+  const char* const uw = reinterpret_cast<const char*>(p.wbuf + col);
+  double Sd[V];
+#pragma unroll
+  for (int v = 0; v < V; v++) Sd[v] = __ldcg(St + col + v);
+  RowBuf<kSA> ring[kStages];
+  auto load = [&](RowBuf<kSA>& buf, int k) {
+    if (k < n) {
+#pragma unroll
+      for (int u = 0; u < kSA; u++) ld_cg<V>(reinterpret_cast<const float*>(uw + (unsigned)a[k + u].x), buf.a[u]);
+    }
+  };
+  float invS[V], part[V], X[V];
+  float S0[V];
+  int task = tb;
+  auto consume = [&](RowBuf<kSA>& buf, int k) {
+#pragma unroll
+    for (int u = 0; u < kSA; u++) {
+      const int prb = a[k + u].z;
+      const float pr = fabsf(__int_as_float(prb));
+      const u64 pr2 = pk2(pr, pr);
+#pragma unroll
+      for (int h = 0; h < 2; h++)
+        upk2(fma2(pr2, pk2(buf.a[u][2 * h], buf.a[u][2 * h + 1]), pk2(X[2 * h], X[2 * h + 1])), X[2 * h], X[2 * h + 1]);
+      if (prb < 0) {  // last arc of this state
+        const int4 tk = tasks[task++];
+        const float pi_h = __int_as_float(tk.w);
+        float bd[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+          bd[v] = X[v] * invS[v];
+          part[v] = fmaf(pi_h, bd[v], part[v]);
+          // sanity sum at t = 0: alpha'_0(h) = pi(h) (1 + leaky S_0)
+          if (t == 0 && col + v < p.B) ab += (double)(pi_h * (1.0f + p.leaky * S0[v])) * (double)bd[v];
+          X[v] = 0.f;
+        }
+        st_vec<V>(row_ptr(beta_cur + col, tk.x, rowbytes), bd);
+      }
+    }
+  };
+#pragma unroll
+  for (int st = 0; st < kStages; st++) load(ring[st], st * kSA);
+#pragma unroll
+  for (int v = 0; v < V; v++) {
+    S0[v] = (float)Sd[v];
+    invS[v] = 1.0f / S0[v];
+    part[v] = X[v] = 0.f;
+  }
+  (void)te;
+  for (int k = 0; k < n;) {
+#pragma unroll
+    for (int st = 0; st < kStages; st++) {
+      if (k < n) {
+        consume(ring[st], k);
+        load(ring[st], k + kStages * kSA);
+        k += kSA;
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < V; v++) red[warp * BP + col + v] = part[v];
+}
+
+template <int PHASE>
+__device__ __forceinline__ void den_tied_body(const DenBatch& batch) {
+  constexpr int V = 4;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const DenParams& p = batch.c[0];
+  const TiedSmem sm = carve_tied(smem_raw, p);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool is_aux = warp >= kDenMainWarps;
+  const int auxw = warp - kDenMainWarps;
+  float* tile = sm.tile + (is_aux ? auxw : 0) * 32 * 33;
+  const int BP = p.BP, T = p.T;
+  unsigned epoch = 0;
+  double sumsq = 0.0, ab = 0.0, gsum = 0.0;
+  unsigned long long* tl = (p.timeline && blockIdx.x == 0 && threadIdx.x == 0) ? p.timeline + PHASE * (T + 3) : nullptr;
+  int tli = 0;
+  auto stamp = [&]() {
+    if (tl) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      tl[tli++] = ns;
+    }
+  };
+  auto grid_barrier = [&]() {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      epoch += gridDim.x;
+      __threadfence();
+      atomicAdd(p.barrier + 32 * PHASE, 1u);
+      const unsigned* ctr = p.barrier + 32 * PHASE;
+      while (ld_acquire(ctr) < epoch) {
+      }
+    }
+    __syncthreads();
+  };
+  stamp();
+  // stage this CTA's slices: records + tasks of this launch's direction, and (backward) its runs
+  const DenDir& D = p.dir[PHASE];
+  const int task0 = D.cta_task_off[blockIdx.x], ntask = D.cta_task_off[blockIdx.x + 1] - task0;
+  const int arc0 = D.cta_arc_off[blockIdx.x], narc = D.cta_arc_off[blockIdx.x + 1] - arc0;
+  int tb = 0, te = 0, abeg = 0, aend = 0, rbeg = 0, rend = 0;
+  if (!is_aux) {
+    const int bin = blockIdx.x * kDenMainWarps + warp;
+    tb = D.warp_task_off[bin] - task0;
+    te = D.warp_task_off[bin + 1] - task0;
+    abeg = D.warp_arc_off[bin] - arc0;
+    aend = D.warp_arc_off[bin + 1] - arc0;
+  }
+  for (int i = threadIdx.x; i < ntask; i += kDenThreads) sm.tasks[i] = D.tasks[task0 + i];
+  for (int i = threadIdx.x; i < narc; i += kDenThreads) sm.arcs[i] = D.arcs[arc0 + i];
+  if constexpr (PHASE == 1) {
+    const int run0 = p.rdir.cta_arc_off[blockIdx.x], nrun = p.rdir.cta_arc_off[blockIdx.x + 1] - run0;
+    for (int i = threadIdx.x; i < nrun; i += kDenThreads) sm.runs[i] = p.rdir.arcs[run0 + i];
+    if (!is_aux) {
+      const int bin = blockIdx.x * kDenMainWarps + warp;
+      rbeg = p.rdir.warp_arc_off[bin] - run0;
+      rend = p.rdir.warp_arc_off[bin + 1] - run0;
+    }
+  }
+  __syncthreads();
+  const int4* arcs = sm.arcs;
+  const int4* tasks = sm.tasks;
+
+  if constexpr (PHASE == 0) {
+    // ---- prologue: alpha_0 = pi, S_0; stage exp(y_0)
+    if (is_aux) {
+      aux_work(p, -1, 0, tile, auxw, lane, true, sumsq, false, gsum);
+    } else {
+      const int col = lane * V;
+      float part = 0.f;
+      for (int task = tb; task < te; task++) {
+        const int4 tk = tasks[task];
+        const float pi_h = __int_as_float(tk.w);
+        float out[V];
+#pragma unroll
+        for (int v = 0; v < V; v++) out[v] = pi_h;
+        st_vec<V>(p.alpha + (size_t)tk.x * BP + col, out);
+        part += pi_h;
+      }
+#pragma unroll
+      for (int v = 0; v < V; v++) sm.red[warp * BP + col + v] = part;
+    }
+    cta_reduce_to(sm.red, BP, kDenMainWarps, p.Ssum);
+    grid_barrier();
+    for (int t = 1; t <= T; t++) {
+      stamp();
+      if (is_aux) {
+        if (t < T) aux_work(p, -1, t, tile, auxw, lane, true, sumsq, false, gsum);
+      } else {
+        alpha_step_tied(p, arcs, tasks, abeg, aend, tb, t, sm.red, warp, lane);
+      }
+      cta_reduce_to(sm.red, BP, kDenMainWarps, p.Ssum + (size_t)t * BP);
+      grid_barrier();
+    }
+    stamp();
+    if (is_aux) {
+      sumsq = warp_sum(sumsq);
+      if (lane == 0 && sumsq != 0.0) atomicAdd(p.scalars + 3, sumsq);
+    }
+    if (blockIdx.x == 0) {  // ComputeTotLogLike
+      double acc = 0.0;
+      for (int i = threadIdx.x; i < (T + 1) * BP; i += kDenThreads) {
+        const int t = i / BP, s = i - t * BP;
+        if (s < p.B) {
+          float S = (float)__ldcg(p.Ssum + i);
+          if (t == T) S = S * (1.0f + p.leaky * p.sum_pi);
+          acc += log((double)S);
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) atomicAdd(p.scalars + 2, acc);
+    }
+  } else {
+    // ---- backward prologue: beta'_T(h) = 1 / (S_T (1 + leaky*sum_pi))
+    if (!is_aux) {
+      const int col = lane * V;
+      const double* ST = p.Ssum + (size_t)T * BP;
+      float* betaT = p.beta + (size_t)(T & 1) * p.N * BP;
+      float inv[V], part[V];
+#pragma unroll
+      for (int v = 0; v < V; v++) {
+        const float S = (float)__ldcg(ST + col + v);
+        inv[v] = 1.0f / (S * (1.0f + p.leaky * p.sum_pi));
+        part[v] = 0.f;
+      }
+      for (int task = tb; task < te; task++) {
+        const int4 tk = tasks[task];
+        const float pi_h = __int_as_float(tk.w);
+        st_vec<V>(betaT + (size_t)tk.x * BP + col, inv);
+#pragma unroll
+        for (int v = 0; v < V; v++) part[v] = fmaf(pi_h, inv[v], part[v]);
+      }
+#pragma unroll
+      for (int v = 0; v < V; v++) sm.red[warp * BP + col + v] = part[v];
+    }
+    cta_reduce_to(sm.red, BP, kDenMainWarps, p.Bsum + (size_t)T * BP);
+    grid_barrier();
+    for (int t = T - 1; t >= 0; t--) {
+      stamp();
+      // phase A: runs (the aux warps only pass through the barrier: their work belongs to the long phase)
+      if (!is_aux) runs_step_tied(p, sm.runs, rbeg, rend, t, lane);
+      grid_barrier();
+      if (t < T - 1 && p.deriv_progress && blockIdx.x == 0 && warp == kDenMainWarps && lane == 0)
+        st_release_sys(p.deriv_progress, (unsigned)(T - 2 - t));  // rows of frames > t+1 were complete a step ago
+      // phase B: arcs
+      if (is_aux) aux_work(p, t + 1 < T ? t + 1 : -1, t - 1, tile, auxw, lane, false, sumsq, false, gsum, t);
+      else beta_step_tied(p, arcs, tasks, abeg, aend, tb, te, t, sm.red, warp, lane, ab);
+      cta_reduce_to(sm.red, BP, kDenMainWarps, p.Bsum + (size_t)t * BP);
+      grid_barrier();
+    }
+    stamp();
+    if (p.deriv_progress && blockIdx.x == 0 && warp == kDenMainWarps && lane == 0)
+      st_release_sys(p.deriv_progress, (unsigned)(T - 1));
+    if (is_aux) {
+      aux_work(p, 0, -1, tile, auxw, lane, false, sumsq, true, gsum);
+      gsum = warp_sum(gsum);
+      if (lane == 0 && gsum != 0.0) atomicAdd(p.scalars + 1, gsum);
+    } else {
+      ab = warp_sum(ab);
+      if (lane == 0 && ab != 0.0) atomicAdd(p.scalars + 0, ab);
+    }
+  }
+  __syncthreads();
+  stamp();
+}
+
+__global__ void __maxnreg__(DEN_F_MAXNREG_TIED) den_tied_forward_kernel(const __grid_constant__ DenBatch batch) {
+  den_tied_body<0>(batch);
+}
+__global__ void __launch_bounds__(kDenThreads, 1) den_tied_backward_kernel(const __grid_constant__ DenBatch batch) {
+  den_tied_body<1>(batch);
+}
+
 // The forward launch is capped at 112 registers/thread so that 8 K registers per SM stay free:
 // the numerator kernel (128 threads x 48 registers per CTA) can then run on the same SMs while
 // the forward recurrence is in flight.  The backward launch takes the whole register file.
@@ -1188,6 +1619,29 @@ size_t den_smem_bytes(const DenParams& p) {
     off += sizeof(int4) * (size_t)std::max(p.dir[0].max_arcs_cta, p.dir[1].max_arcs_cta);
   }
   return off;
+}
+
+size_t den_tied_smem_bytes(const DenParams& p) {
+  size_t off = sizeof(float) * kDenMainWarps * p.BP;
+  off += sizeof(float) * kDenAuxWarps * 32 * 33;
+  off = (off + 15) & ~size_t(15);
+  off += sizeof(int4) * (size_t)std::max(p.dir[0].max_tasks_cta, p.dir[1].max_tasks_cta);
+  off += sizeof(int4) * (size_t)std::max(p.dir[0].max_arcs_cta, p.dir[1].max_arcs_cta);
+  off += sizeof(int4) * (size_t)p.rdir.max_arcs_cta;
+  return off;
+}
+
+cudaError_t launch_den_tied(const DenBatch& b, int phase, int grid, cudaStream_t stream) {
+  const DenParams& p = b.c[0];
+  if (b.nctx != 1 || p.BP != kCtxBP || p.subs != 1) return cudaErrorInvalidValue;
+  const size_t smem = den_tied_smem_bytes(p);
+  void (*kern)(DenBatch) = phase == 0 ? den_tied_forward_kernel : den_tied_backward_kernel;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  void* args[] = {const_cast<DenBatch*>(&b)};
+  e = cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(kDenThreads), args, smem, stream);
+  if (e == cudaSuccess) count_launch();
+  return e;
 }
 
 int den_max_grid(int device) {

@@ -324,6 +324,8 @@ CONFIGS = {
     "tiny": dict(P=40, N=120, mean_deg=4.0, B=6, T=8, leaky=0.1, l2=5e-5),
     "chime5_hubs": dict(P=2928, N=10_000, mean_deg=26.0, B=128, T=50, leaky=0.1, l2=5e-5, hubs=2),
     "chime5": dict(P=2928, N=10_000, mean_deg=28.0, B=128, T=50, leaky=0.1, l2=5e-5),
+    # config 2's shape with pdfs tied to the state being entered, as in a real den.fst (~2 runs per state)
+    "chime5_tied": dict(P=2928, N=10_000, mean_deg=28.0, B=128, T=50, leaky=0.1, l2=5e-5, tied=True),
     "chime5_b512": dict(P=2928, N=10_000, mean_deg=28.0, B=512, T=50, leaky=0.1, l2=5e-5),
     "large_tree": dict(P=6000, N=20_000, mean_deg=28.0, B=256, T=50, leaky=0.1, l2=5e-5),
 }
@@ -335,7 +337,7 @@ def make_config(name, seed=1234, B=None, T=None, y_scale=2.0, with_y=True):
         c["B"] = int(B)
     if T is not None:
         c["T"] = int(T)
-    den = make_den_fst(seed, c["N"], c["P"], mean_deg=c["mean_deg"])
+    den = (make_den_fst_tied if c.get("tied") else make_den_fst)(seed, c["N"], c["P"], mean_deg=c["mean_deg"])
     sup = make_supervision(seed + 1, den, c["B"], c["T"], num_paths=4, weight=1.0)
     y = make_nnet_output(seed + 2, c["B"], c["T"], c["P"], scale=y_scale) if with_y else None
     c.update(den=den, sup=sup, y=y)
