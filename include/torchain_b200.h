@@ -71,6 +71,11 @@ void my_lib_denominator_graph_free(void* den_graph_ptr);
 int torchain_denominator_graph_num_states(void* den_graph_ptr);
 int torchain_denominator_graph_num_arcs(void* den_graph_ptr);
 int torchain_denominator_graph_num_pdfs(void* den_graph_ptr);
+/* Runs = distinct (destination state, pdf) pairs of the graph; a real den.fst, whose pdfs belong to the state
+ * being entered, has ~2 per state.  is_tied: 1 if the run-based kernels will be used for this graph (few runs
+ * per arc, no state with more arcs than the split cap), else 0 (per-arc kernels). */
+int torchain_denominator_graph_num_runs(void* den_graph_ptr);
+int torchain_denominator_graph_is_tied(void* den_graph_ptr);
 /* Copies the N initial probabilities (Kaldi DenominatorGraph::InitialProbs()). */
 int torchain_denominator_graph_initial_probs(void* den_graph_ptr, float* out_n);
 

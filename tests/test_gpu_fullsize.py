@@ -216,7 +216,8 @@ def test_tied_cfg2_graph_matches_oracle(B, T):
     B = 130 / 300 mix run-based passes of 128 with a per-arc pass for the remainder (2 / 44 sequences)."""
     den, oden, g = _den("chime5_tied")
     runs, _ = synth.in_pdf_runs(den)
-    assert runs * 3 <= den.num_arcs
+    assert g.tied and g.n_run == runs and runs * 3 <= den.num_arcs
+    assert not _den("chime5")[2].tied            # a pdf per arc: as many runs as arcs, per-arc kernels
     _compare(den, oden, g, B, T, 5e-5, 0.1, seed=5000 + B, want_xent=(B == 128))
 
 

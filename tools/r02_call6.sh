@@ -1,0 +1,19 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+O=gpurun_out
+timeout 300 python tools/variant_probe.py --config chime5_tied --no-parity torchain_b200/libtorchain_b200.so > $O/r02_tied_probe2.txt 2>&1
+cat $O/r02_tied_probe2.txt
+ncu --set full --clock-control none --import-source on -k regex:den_tied -s 8 -c 2 -f -o $O/r02_den_tied python tools/variant_probe.py --child --config chime5_tied --no-parity --steps 2 > $O/ncu_tied.log 2>&1
+tail -3 $O/ncu_tied.log
+ncu -i $O/r02_den_tied.ncu-rep --page raw --csv > $O/r02_den_tied_raw.csv 2>/dev/null
+python - <<'PY'
+import csv
+rows = list(csv.reader(open('gpurun_out/r02_den_tied_raw.csv')))
+hdr = rows[0]
+want = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread", "lts__t_sectors.sum", "lts__t_bytes.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "smsp__inst_executed.sum", "sm__inst_executed_pipe_lsu.sum", "lts__t_sectors_op_red.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]
+idx = [hdr.index(w) for w in want if w in hdr]
+for r in rows[2:]:
+    print({hdr[i]: r[i] for i in idx})
+PY

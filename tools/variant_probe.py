@@ -33,7 +33,7 @@ def one(args):
     lib.torchain_profile_enable(0)
     f, b = tl[:T + 3], tl[T + 3:]
     fwd, bwd = (np.diff(f) / 1e3)[1:1 + T], (np.diff(b) / 1e3)[1:1 + T]
-    out = {"lib": os.path.basename(_lib.LIB_PATH), "config": args.config, "B": c["B"], "T": T, "ms_per_step": round(ms, 4),
+    out = {"lib": os.path.basename(_lib.LIB_PATH), "tied": R.g.tied, "runs": R.g.n_run, "config": args.config, "B": c["B"], "T": T, "ms_per_step": round(ms, 4),
            "fwd_frame_us": round(float(fwd.mean()), 2), "bwd_frame_us": round(float(bwd.mean()), 2),
            "fwd_launch_us": round(float(f[-1] - f[0]) / 1e3, 1), "bwd_launch_us": round(float(b[-1] - b[0]) / 1e3, 1)}
     if not args.no_parity:

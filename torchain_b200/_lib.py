@@ -32,6 +32,8 @@ SIGNATURES = {
     "torchain_denominator_graph_num_states": (_c_i, [_c_p]),
     "torchain_denominator_graph_num_arcs": (_c_i, [_c_p]),
     "torchain_denominator_graph_num_pdfs": (_c_i, [_c_p]),
+    "torchain_denominator_graph_num_runs": (_c_i, [_c_p]),
+    "torchain_denominator_graph_is_tied": (_c_i, [_c_p]),
     "torchain_denominator_graph_initial_probs": (_c_i, [_c_p, _c_p]),
     "torchain_supervision_from_arrays": (
         _c_p, [_c_f, _c_i32, _c_i32, _c_i32, _c_i32, _c_p, _c_p, _c_p, _c_p, _c_p]),

@@ -2153,6 +2153,8 @@ void my_lib_denominator_graph_free(void* p) { delete static_cast<DenGraph*>(p); 
 int torchain_denominator_graph_num_states(void* p) { return p ? static_cast<DenGraph*>(p)->N : 0; }
 int torchain_denominator_graph_num_arcs(void* p) { return p ? static_cast<DenGraph*>(p)->A : 0; }
 int torchain_denominator_graph_num_pdfs(void* p) { return p ? static_cast<DenGraph*>(p)->P : 0; }
+int torchain_denominator_graph_num_runs(void* p) { return p ? static_cast<DenGraph*>(p)->R : 0; }
+int torchain_denominator_graph_is_tied(void* p) { return p && static_cast<DenGraph*>(p)->tied ? 1 : 0; }
 int torchain_denominator_graph_initial_probs(void* p, float* out) try {
   if (!p || !out) return fail("null argument");
   auto* g = static_cast<DenGraph*>(p);

@@ -1089,7 +1089,9 @@ __device__ __forceinline__ void den_chain_body(const DenBatch& batch) {
           st_release_sys(p0.deriv_progress, (unsigned)(T - 2 - t));
         }
         if (is_aux) {
+#ifndef DEN_DEBUG_SKIP_AUX_B  // timing experiment only (wrong results): how much of a backward frame is the aux warps'?
           aux_work(p, t + 1 < T ? t + 1 : -1, t - 1, tile, auxw, lane, false, sumsq, false, gsum, t);
+#endif
         } else {
           const long long c0 = clock64();
           if constexpr (DEN_ASYNC_B)
@@ -1531,8 +1533,20 @@ __device__ __forceinline__ void den_tied_body(const DenBatch& batch) {
       grid_barrier();
       if (t < T - 1 && p.deriv_progress && blockIdx.x == 0 && warp == kDenMainWarps && lane == 0)
         st_release_sys(p.deriv_progress, (unsigned)(T - 2 - t));  // rows of frames > t+1 were complete a step ago
-      // phase B: arcs
+      // phase B: arcs.  First, the a_run rows this warp reads in the NEXT step's phase A are requested into L2:
+      // they come from HBM (written a whole forward launch ago), and phase A is a short dependent chain of
+      // ~10 runs per warp that would otherwise pay the DRAM latency five times over.
+      if (!is_aux && t > 0) {
+        const char* nxt = reinterpret_cast<const char*>(p.arun + (size_t)(t - 1) * p.R * BP);
+        for (int k = rbeg + (lane >> 2); k < rend; k += 8)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + (unsigned)sm.runs[k].z + (lane & 3) * 128));
+      }
+#ifndef DEN_DEBUG_SKIP_AUX_B
       if (is_aux) aux_work(p, t + 1 < T ? t + 1 : -1, t - 1, tile, auxw, lane, false, sumsq, false, gsum, t);
+#else
+      if (is_aux) {
+      }
+#endif
       else beta_step_tied(p, arcs, tasks, abeg, aend, tb, te, t, sm.red, warp, lane, ab);
       cta_reduce_to(sm.red, BP, kDenMainWarps, p.Bsum + (size_t)t * BP);
       grid_barrier();

@@ -188,6 +188,16 @@ class DenominatorGraph:
         return _lib.load().torchain_denominator_graph_num_pdfs(self.ptr)
 
     @property
+    def n_run(self):
+        """Distinct (destination state, pdf) pairs; ~2 per state in a real den.fst."""
+        return _lib.load().torchain_denominator_graph_num_runs(self.ptr)
+
+    @property
+    def tied(self):
+        """True if the run-based (tied-pdf) kernels serve this graph, False for the per-arc kernels."""
+        return bool(_lib.load().torchain_denominator_graph_is_tied(self.ptr))
+
+    @property
     def initial_probs(self):
         out = np.empty(self.n_state, dtype=np.float32)
         if _lib.load().torchain_denominator_graph_initial_probs(self.ptr, _ptr(out)) != 1:
