@@ -1217,18 +1217,32 @@ __device__ __forceinline__ void alpha_step_tied(const DenParams& p, const int4* 
   };
   float lamS[V], invS[V], part[V], racc[V], sacc[V];
   int task = tb;
+  auto arc = [&](const float (&row)[V], int y, int z) {  // racc += (alpha(src) + leaky * pi(src) * S) * p
+    const float pr = __int_as_float(y), pi = __int_as_float(z);
+    const u64 pr2 = pk2(pr, pr), pi2 = pk2(pi, pi);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const u64 ad = fma2(pi2, pk2(lamS[2 * h], lamS[2 * h + 1]), pk2(row[2 * h], row[2 * h + 1]));
+      upk2(fma2(ad, pr2, pk2(racc[2 * h], racc[2 * h + 1])), racc[2 * h], racc[2 * h + 1]);
+    }
+  };
   auto consume = [&](RowBuf<kSA>& buf, int k) {
+    int4 r[kSA];
+    int kinds = 0;
 #pragma unroll
     for (int u = 0; u < kSA; u++) {
-      const int4 r = a[k + u];
-      if (r.y >= 0) {  // arc: racc += (alpha(src) + leaky * pi(src) * S) * p
-        const float pr = __int_as_float(r.y), pi = __int_as_float(r.z);
-        const u64 pr2 = pk2(pr, pr), pi2 = pk2(pi, pi);
+      r[u] = a[k + u];
+      kinds |= r[u].y;
+    }
+    if (kinds >= 0) {  // a stage of arcs only (15 arcs per run): straight-line code the compiler can overlap
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const u64 ad = fma2(pi2, pk2(lamS[2 * h], lamS[2 * h + 1]), pk2(buf.a[u][2 * h], buf.a[u][2 * h + 1]));
-          upk2(fma2(ad, pr2, pk2(racc[2 * h], racc[2 * h + 1])), racc[2 * h], racc[2 * h + 1]);
-        }
+      for (int u = 0; u < kSA; u++) arc(buf.a[u], r[u].y, r[u].z);
+      return;
+    }
+#pragma unroll
+    for (int u = 0; u < kSA; u++) {
+      if (r[u].y >= 0) {
+        arc(buf.a[u], r[u].y, r[u].z);
       } else {  // end of a run: buf holds exp(y) of the run's pdf
         float out[V];
 #pragma unroll
@@ -1237,8 +1251,8 @@ __device__ __forceinline__ void alpha_step_tied(const DenParams& p, const int4* 
           sacc[v] += out[v];
           racc[v] = 0.f;
         }
-        __stcs(reinterpret_cast<float4*>(ur + (unsigned)r.z), make_float4(out[0], out[1], out[2], out[3]));
-        if (r.y & 1) {  // last run of this state
+        __stcs(reinterpret_cast<float4*>(ur + (unsigned)r[u].z), make_float4(out[0], out[1], out[2], out[3]));
+        if (r[u].y & 1) {  // last run of this state
           const int4 tk = tasks[task++];
 #pragma unroll
           for (int v = 0; v < V; v++) part[v] += sacc[v];
