@@ -634,10 +634,13 @@ def test_gpu_chain_loss_3d_input_needs_no_to2d():
 
 
 @pytest.mark.parametrize("B,P,T", [(1, 1, 2), (3, 5, 7), (4, 33, 50), (2, 64, 256), (5, 70, 300), (128, 96, 50),
-                                   (2, 31, 1599)])
+                                   (2, 31, 1599), (128, 2928, 50), (7, 48, 150), (3, 40, 13), (2, 36, 4), (9, 2928, 1)])
 def test_gpu_relayout_kernels_equal_permute(B, P, T):
     """torchain_to2d / torchain_from2d are bit-exact copies of the reference's to2d
-    (functions.py:118-125) and of the permute its backward applies to the gradient."""
+    (functions.py:118-125) and of the permute its backward applies to the gradient.  Shapes whose blocks and rows
+    are 16-byte aligned (P*T and the last block's pdfs*T multiples of 4, row stride a multiple of 4, T <= 256) go
+    through the TMA kernels (bulk copy + 3-D tensor copy), every other shape -- and the padded stride P+3 below --
+    through the plain ones; both are covered, and a padded stride of P+4 sends the same data through TMA."""
     import torch
     from torchain_b200.functions import to2d
     x = torch.randn(B, P, T, device="cuda")
@@ -658,6 +661,13 @@ def test_gpu_relayout_kernels_equal_permute(B, P, T):
     assert lib.torchain_from2d(pad.data_ptr(), P + 3, B, P, T, back.data_ptr(), -2.0, 0, st) == 1, _lib.last_error()
     assert torch.equal(back, -2.0 * x)
     assert lib.torchain_to2d(x.data_ptr(), B, P, T, pad.data_ptr(), P - 1, 0, st) == 0
+    if T > 1:
+        pad4 = torch.full((T * B, P + 4), 7.0, device="cuda")
+        assert lib.torchain_to2d(x.data_ptr(), B, P, T, pad4.data_ptr(), P + 4, 0, st) == 1, _lib.last_error()
+        assert torch.equal(pad4[:, :P], want) and bool((pad4[:, P:] == 7.0).all())
+        back4 = torch.empty_like(x)
+        assert lib.torchain_from2d(pad4.data_ptr(), P + 4, B, P, T, back4.data_ptr(), 0.5, 0, st) == 1, _lib.last_error()
+        assert torch.equal(back4, 0.5 * x)
 
 
 def test_gpu_supervision_merge_matches_appended_fst():
