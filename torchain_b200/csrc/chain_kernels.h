@@ -33,7 +33,7 @@ constexpr int kDenMainWarps = kDenWarps - kDenAuxWarps;
 #define DEN_STREAM_PAD 4
 #endif
 constexpr int kStreamPad = DEN_STREAM_PAD;
-#define DEN_F_SA_DEFAULT 2
+#define DEN_F_SA_DEFAULT 4
 #define DEN_B_SA_DEFAULT 4
 constexpr int kCtxBP = 128;                    // sequences per context (lane width of the full-size kernels)
 constexpr int kMaxBP = 256;                    // sequences per launch pair: two contexts of kCtxBP

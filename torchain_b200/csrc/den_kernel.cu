@@ -358,16 +358,16 @@ __device__ __forceinline__ void aux_work(const DenParams& p, int flush_frame, in
 // ------------------------------------------------- main-warp work: recursions
 // A warp walks its contiguous arc list as ONE stream; the last arc of every state carries the
 // end-of-state flag (bit 31 of its pdf field), states without arcs get one zero-probability
-// arc.  Measured on B200 (profiles/r01_summary.md): the forward pass likes 6 arcs in flight
-// as a 3-stage ring of 2 (28.2 us/frame vs 28.7 for one stage of 4); 8 arcs in flight do not
-// fit its 112-register budget.  The backward pass is best with ONE stage of 4: every deeper
+// arc.  Measured on B200: round 1 (profiles/r01_summary.md) had the forward pass at 6 arcs in flight as a
+// 3-stage ring of 2; round 2 moved it to 2 stages of 4 with a branch-free fast path for stages that hold
+// no end of state (DEN_F_FAST below).  The backward pass is best with ONE stage of 4: every deeper
 // variant (more gathers in flight next to the REDs) is slower (44.4 us -> 48..52 us/frame).
 static_assert(kStreamPad % DEN_F_SA_DEFAULT == 0 && kStreamPad % DEN_B_SA_DEFAULT == 0, "stream padding");
 #ifndef DEN_F_SA
 #define DEN_F_SA DEN_F_SA_DEFAULT
 #endif
 #ifndef DEN_F_STAGES
-#define DEN_F_STAGES 3
+#define DEN_F_STAGES 2
 #endif
 #ifndef DEN_B_SA
 #define DEN_B_SA DEN_B_SA_DEFAULT
@@ -375,6 +375,17 @@ static_assert(kStreamPad % DEN_F_SA_DEFAULT == 0 && kStreamPad % DEN_B_SA_DEFAUL
 static_assert(kStreamPad % DEN_F_SA == 0 && kStreamPad % DEN_B_SA == 0, "arc streams are padded to kStreamPad arcs");
 #ifndef DEN_B_STAGES
 #define DEN_B_STAGES 1
+#endif
+// Round 2 (profiles/r02_fast_path_variants.txt): a stage of arcs WITHOUT an end of state (87 % of the stages of 4 at ~30
+// arcs per state) runs as straight-line code behind one test -- the warps are bound by the latency of their own
+// instruction streams (ncu: ~43 % of the stall samples are fixed-latency waits, issue slots 31 % used), so a branch per
+// arc costs more than its instruction.  Forward: 2 stages x 4 arcs with the fast path 24.0 us per frame against 25.4 us
+// for 3 x 2 without (25.7 us for 2 x 4 without the fast path).  Backward: the same change was SLOWER (42.8 vs 41.2 us).
+#ifndef DEN_F_FAST
+#define DEN_F_FAST 1
+#endif
+#ifndef DEN_B_FAST
+#define DEN_B_FAST 0
 #endif
 
 template <int V, int SA>
@@ -425,6 +436,30 @@ __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __res
       }
     };
     auto consume = [&](GatherBuf<V, kSA>& buf, int k) {
+      if constexpr (DEN_F_FAST && DEN_PACKED_MATH && V == 4) {
+        // a stage without an end of state (states have ~30 arcs): straight-line code, one test for the stage
+        int2 rec[kSA];
+        int ends = 0;
+#pragma unroll
+        for (int u = 0; u < kSA; u++) {
+          rec[u] = *(reinterpret_cast<const int2*>(a + k + u) + 1);
+          ends |= rec[u].x;
+        }
+        if (ends >= 0) {
+#pragma unroll
+          for (int u = 0; u < kSA; u++) {
+            const float pr = __int_as_float(rec[u].x), pi = __int_as_float(rec[u].y);
+            const u64 pr2 = pk2(pr, pr), pi2 = pk2(pi, pi);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const u64 ad = fma2(pi2, pk2(lamS[2 * h], lamS[2 * h + 1]), pk2(buf.a[u][2 * h], buf.a[u][2 * h + 1]));
+              const u64 r = fma2(mul2(ad, pr2), pk2(buf.e[u][2 * h], buf.e[u][2 * h + 1]), pk2(acc[2 * h], acc[2 * h + 1]));
+              upk2(r, acc[2 * h], acc[2 * h + 1]);
+            }
+          }
+          return;
+        }
+      }
 #pragma unroll
       for (int u = 0; u < kSA; u++) {
         {
@@ -535,6 +570,33 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
       }
     };
     auto consume = [&](GatherBuf<V, kSA>& buf, int k) {
+      if constexpr (DEN_B_FAST && DEN_PACKED_MATH && V == 4) {
+        int2 rec[kSA];  // {pdf row offset, prob | end flag}
+        int ends = 0;
+#pragma unroll
+        for (int u = 0; u < kSA; u++) {
+          const int4 r = a[k + u];
+          rec[u] = make_int2(r.y, r.z);
+          ends |= r.z;
+        }
+        if (ends >= 0) {  // no end of state in this stage: straight-line code
+#pragma unroll
+          for (int u = 0; u < kSA; u++) {
+            const float pr = __int_as_float(rec[u].y);
+            const u64 pr2 = pk2(pr, pr);
+            float g[V];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const u64 sum = add2(pk2(buf.a[u][2 * h], buf.a[u][2 * h + 1]), pk2(bv[2 * h], bv[2 * h + 1]));
+              const u64 vf = mul2(mul2(pr2, sum), pk2(buf.e[u][2 * h], buf.e[u][2 * h + 1]));
+              upk2(add2(pk2(X[2 * h], X[2 * h + 1]), vf), X[2 * h], X[2 * h + 1]);
+              upk2(mul2(vf, pk2(occ[2 * h], occ[2 * h + 1])), g[2 * h], g[2 * h + 1]);
+            }
+            red_add<V>(reinterpret_cast<float*>(ug + (unsigned)rec[u].x), g);
+          }
+          return;
+        }
+      }
 #pragma unroll
       for (int u = 0; u < kSA; u++) {
         {
