@@ -5,13 +5,13 @@
 set -u
 mkdir -p gpurun_out
 O=gpurun_out
-timeout 1200 python -m pytest tests -q -m gpu -rA > $O/r02_gpu_tests3.log 2>&1
-grep -E "passed|failed|^FAILED|^ERROR" $O/r02_gpu_tests3.log | tail -8
-timeout 600 python bench.py > $O/r02_bench3.json 2> $O/r02_bench3.err
-tail -2 $O/r02_bench3.err
-python tools/layout_probe.py > $O/r02_layout_probe.txt 2>&1
-tail -9 $O/r02_layout_probe.txt | head -8
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_ncu_launches.csv \
+timeout 1200 python -m pytest tests -q -m gpu -rA > $O/r02_gpu_tests_final.log 2>&1
+grep -E "passed|failed|^FAILED|^ERROR" $O/r02_gpu_tests_final.log | tail -8
+timeout 600 python bench.py > $O/r02_bench_final.json 2> $O/r02_bench_final.err
+tail -2 $O/r02_bench_final.err
+python tools/layout_probe.py > $O/r02_layout_probe_final.txt 2>&1
+tail -9 $O/r02_layout_probe_final.txt | head -8
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_ncu_launches_final.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-parity --no-extra-configs --no-fresh-supervision > $O/ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:den_ -s 8 -c 2 -f -o $O/r02_den \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity --no-extra-configs --no-fresh-supervision > $O/ncu_den.log 2>&1
@@ -30,7 +30,7 @@ for f in ("gpurun_out/r02_ncu_den_kernels_raw.csv", "gpurun_out/r02_ncu_relayout
     print(rows[1][idx[1]] if len(rows) > 1 else "", "(units row)")
     for r in rows[2:]:
         print({hdr[i]: r[i] for i in idx})
-d = json.load(open("gpurun_out/r02_bench3.json"))
+d = json.load(open("gpurun_out/r02_bench_final.json"))
 for k in ("ms_per_step", "value", "fresh_supervision_ms_per_step", "cfg3_strong_ms_per_step", "cfg4_ms_per_step", "parity_ok"):
     print(k, d.get(k))
 print("e2e", d["e2e"]["ms_per_step"], "frac", d["roofline"]["frac"], d["clocks"])
