@@ -71,3 +71,41 @@ for (B, T, N, P) in [(5, 4, 60, 17), (37, 6, 80, 33)]:
     torch.cuda.synchronize()
     print("ok strided/relayout/merge", B, T, N, P, res, res2, bool(torch.equal(back, y3)), bool(torch.equal(rows[:, :P], y2)),
           float((d3.permute(2, 0, 1).reshape(T * B, P) - d2).abs().max()))
+
+# round 2: the run-based (tied) kernels -- device and host-buffer entries, a remainder pass on the per-arc kernels --
+# the TMA relayout kernels (aligned shapes), a prefetched supervision whose pooled block is reused, chain-egs parsing
+for (B, T, N, P) in [(70, 4, 90, 24), (130, 3, 60, 16)]:
+    den = synth.make_den_fst_tied(B, N, P, mean_deg=6.0)
+    g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
+                                        den.final_cost, den.num_pdfs)
+    assert g.tied, (g.n_run, den.num_arcs)
+    y = synth.make_nnet_output(B + 2, B, T, P)
+    yt = torch.from_numpy(y).cuda()
+    side = torch.cuda.Stream()
+    for rep in range(3):   # three supervisions through the same pooled block
+        sup = synth.make_supervision(B + 10 + rep, den, B, T, num_paths=2)
+        s = io.Supervision.from_arrays(sup.weight, B, T, P, sup.arc_begin, sup.arc_dst, sup.arc_label, sup.arc_cost,
+                                       sup.final_cost).prefetch(0, side)
+        d = torch.empty_like(yt)
+        res = np.zeros(3, dtype=np.float32)
+        ok = lib.my_lib_ComputeChainObjfAndDeriv(g.ptr, s.ptr, yt.data_ptr(), B * T, P, P, res.ctypes.data_as(ctypes.c_void_p),
+                                                 d.data_ptr(), P, None, 0, 0.01, 0.1, 0.0, 0, None)
+        assert ok == 1, _lib.last_error()
+        torch.cuda.synchronize()
+        dh = np.empty_like(y)
+        ok = lib.torchain_ComputeChainObjfAndDeriv_host(g.ptr, s.ptr, y.ctypes.data_as(ctypes.c_void_p), B * T, P, P,
+                                                        res.ctypes.data_as(ctypes.c_void_p), dh.ctypes.data_as(ctypes.c_void_p),
+                                                        P, None, 0, 0.01, 0.1, 0.0, 0)
+        assert ok == 1, _lib.last_error()
+        del s
+    print("ok tied", B, T, N, P, res, float(np.abs(dh - d.cpu().numpy()).max()))
+for (B, P, T) in [(5, 64, 12), (3, 48, 50), (2, 36, 4)]:
+    x = torch.randn(B, P, T, device="cuda")
+    rows = torch.empty(T * B, P + 4, device="cuda")
+    assert lib.torchain_to2d(x.data_ptr(), B, P, T, rows.data_ptr(), P + 4, 0, None) == 1, _lib.last_error()
+    back = torch.empty_like(x)
+    assert lib.torchain_from2d(rows.data_ptr(), P + 4, B, P, T, back.data_ptr(), 1.0, 0, None) == 1, _lib.last_error()
+    torch.cuda.synchronize()
+    print("ok TMA relayout", B, P, T, bool(torch.equal(back, x)),
+          bool(torch.equal(rows[:, :P], x.permute(2, 0, 1).reshape(T * B, P))))
+lib.torchain_supervision_pool_trim()

@@ -74,6 +74,10 @@ struct DevBuf {
     ptr = nullptr;
     bytes = 0;
   }
+  // Grows the buffer (contents are not kept).  The old allocation goes first: workspaces are hundreds of MB and
+  // holding both would double the peak; a failed grow therefore leaves the buffer EMPTY (ptr == nullptr, bytes == 0),
+  // consistently, and the next call simply allocates again.  cudaErrorMemoryAllocation reaches the caller as
+  // "out of memory" in torchain_last_error(); the Python op then frees torch's cached blocks and retries once.
   cudaError_t reserve(size_t n) {
     if (n <= bytes) return cudaSuccess;
     if (ptr) cudaFree(ptr);
@@ -81,6 +85,7 @@ struct DevBuf {
     bytes = 0;
     cudaError_t e = cudaMalloc(&ptr, n);
     if (e == cudaSuccess) bytes = n;
+    else ptr = nullptr;
     return e;
   }
   template <typename T>
