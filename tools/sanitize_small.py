@@ -74,6 +74,7 @@ for (B, T, N, P) in [(5, 4, 60, 17), (37, 6, 80, 33)]:
 
 # round 2: the run-based (tied) kernels -- device and host-buffer entries, a remainder pass on the per-arc kernels --
 # the TMA relayout kernels (aligned shapes), a prefetched supervision whose pooled block is reused, chain-egs parsing
+os.environ["TORCHAIN_TIED"] = "1"   # (the split cap of 9 set above would keep these graphs on the per-arc kernels)
 for (B, T, N, P) in [(70, 4, 90, 24), (130, 3, 60, 16)]:
     den = synth.make_den_fst_tied(B, N, P, mean_deg=6.0)
     g = io.DenominatorGraph.from_arrays(den.num_states, den.src, den.dst, den.ilabel, den.cost, den.start,
@@ -99,6 +100,7 @@ for (B, T, N, P) in [(70, 4, 90, 24), (130, 3, 60, 16)]:
         assert ok == 1, _lib.last_error()
         del s
     print("ok tied", B, T, N, P, res, float(np.abs(dh - d.cpu().numpy()).max()))
+del os.environ["TORCHAIN_TIED"]
 for (B, P, T) in [(5, 64, 12), (3, 48, 50), (2, 36, 4)]:
     x = torch.randn(B, P, T, device="cuda")
     rows = torch.empty(T * B, P + 4, device="cuda")
