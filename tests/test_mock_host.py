@@ -743,3 +743,24 @@ def test_untied_graphs_and_small_batches_keep_the_per_arc_kernels(mock):
         finally:
             mock.my_lib_supervision_free(s)
             mock.my_lib_denominator_graph_free(g)
+
+
+def test_tied_graph_too_large_for_shared_memory_stays_per_arc(mock, monkeypatch):
+    """The run-based kernels keep a CTA's record streams in shared memory; a tied graph whose streams do not fit
+    (2 M arcs: ~220 KB per CTA) is served by the per-arc kernels (which can read their arcs from global memory)."""
+    monkeypatch.setenv("TORCHAIN_TIED", "1")
+    den = synth.make_den_fst_tied(3, 12_000, 500, mean_deg=165.0)
+    assert (den.num_arcs + 2 * den.num_states) / 148 * 16 > 200 * 1024
+    B, T = 70, 2
+    sup = synth.make_supervision(4, den, B, T, num_paths=1)
+    y = synth.make_nnet_output(5, B, T, den.num_pdfs).astype(np.float32)
+    g, s = _handles(mock, den, sup)
+    try:
+        assert mock.torchain_denominator_graph_is_tied(g) == 1
+        mock.mock_reset_launches()
+        _compute(mock, g, s, y)
+        names = [_kernel(mock.mock_launch_name(i).decode()) for i in range(mock.mock_launch_count())]
+        assert [n for n in names if "den_" in n] == ["den_forward_kernel", "den_backward_kernel"]
+    finally:
+        mock.my_lib_supervision_free(s)
+        mock.my_lib_denominator_graph_free(g)

@@ -1451,6 +1451,15 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
     std::lock_guard<std::mutex> lock(g->mu);
     if (!dd->tied && !build_tied_partition(g, dd)) return 0;
     tp = dd->tied.get();
+    // the run-based kernels keep a CTA's streams in shared memory; a graph too large for that stays per-arc
+    tb::DenParams probe = {};
+    probe.BP = tb::kCtxBP;
+    for (int dir = 0; dir < 2; dir++) {
+      probe.dir[dir].max_arcs_cta = tp->max_arcs_cta[dir];
+      probe.dir[dir].max_tasks_cta = tp->max_tasks_cta[dir];
+    }
+    probe.rdir.max_arcs_cta = tp->max_runs_cta;
+    if (tb::den_tied_smem_bytes(probe) > 200 * 1024) tp = nullptr;
   }
   const int pass_cap = tp ? tb::kCtxBP : tb::kMaxBP;  // sequences per launch pair
   const int rem = B % tb::kCtxBP;
@@ -1594,7 +1603,6 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
       dp.wbuf = ws->wbuf.as<float>();
       dp.has_split = 0;
       dp.arcs_in_smem = 1;
-      if (tb::den_tied_smem_bytes(dp) > 220 * 1024) return fail("tied denominator graph: a CTA's streams do not fit shared memory");
     } else {
       if (!partition_for(dp.subs, &part)) return 0;
       bind(part);
