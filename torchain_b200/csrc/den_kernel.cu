@@ -1196,6 +1196,15 @@ __device__ __forceinline__ void den_chain_body(const DenBatch& batch) {
 #ifndef DEN_F_MAXNREG_TIED
 #define DEN_F_MAXNREG_TIED 112
 #endif
+// ONE stage of 4 records: 21.7 us per frame against 24.4 for 3 stages of 2 and 22.0 for 2 of 4
+// (profiles/r02_tied_sa_probe.txt) -- the loop is bound by its own instruction stream, not by loads in flight
+#ifndef DEN_TIED_F_SA
+#define DEN_TIED_F_SA 4
+#endif
+#ifndef DEN_TIED_F_STAGES
+#define DEN_TIED_F_STAGES 1
+#endif
+static_assert(kStreamPad % DEN_TIED_F_SA == 0, "record streams are padded to kStreamPad");
 
 // =====================================================================================================
 // Tied-pdf ("run-based") recurrences.
@@ -1251,7 +1260,7 @@ struct RowBuf {
 __device__ __forceinline__ void alpha_step_tied(const DenParams& p, const int4* __restrict__ recs,
                                                 const int4* __restrict__ tasks, int abeg, int aend, int tb, int t,
                                                 float* red, int warp, int lane) {
-  constexpr int V = 4, kSA = 2, kStages = 3;
+  constexpr int V = 4, kSA = DEN_TIED_F_SA, kStages = DEN_TIED_F_STAGES;
   const int BP = p.BP, col = lane * V;
   const float* __restrict__ alpha_prev = p.alpha + (size_t)((t - 1) & 1) * p.N * BP;
   float* __restrict__ alpha_cur = p.alpha + (size_t)(t & 1) * p.N * BP;
