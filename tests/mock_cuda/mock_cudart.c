@@ -19,7 +19,7 @@ enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2
 /* ---- bookkeeping the tests read back ---- */
 #define MAX_FUNCS 512
 #define MAX_LAUNCHES 4096
-#define PARAM_BYTES 1024
+#define PARAM_BYTES 2048
 static struct { const void* host_fun; const char* name; } g_funcs[MAX_FUNCS];
 static int g_nfuncs = 0;
 typedef struct {

@@ -41,7 +41,7 @@ class DenParams(ctypes.Structure):  # tb::DenParams
                [(n, ctypes.c_int) for n in ("arcs_in_smem", "subs", "has_split")] + \
                [(n, ctypes.c_void_p) for n in ("num_frame_off", "num_frame_arcs", "num_arc_pdf", "num_arc_seq",
                                                "num_arc_post", "y_ready")] + \
-               [("y_chunk_frames", ctypes.c_int), ("deriv_progress", ctypes.c_void_p)] + \
+               [("y_chunk_frames", ctypes.c_int), ("deriv_progress", ctypes.c_void_p), ("progress_mask", ctypes.c_uint64 * 8)] + \
                [("rdir", DenDir), ("R", ctypes.c_int), ("arun", ctypes.c_void_p), ("wbuf", ctypes.c_void_p)] + \
                [(n, ctypes.c_void_p) for n in ("warp_busy", "cta_trace", "timeline")]
 
@@ -438,7 +438,7 @@ def _den_batches(lib):
 def test_denominator_launch_parameters(mock):
     """What the host hands the persistent kernels: geometry, sequence ranges of the contexts and passes,
     per-context buffers, the scales that fold supervision.weight / l2 / the sign into the derivative."""
-    assert ctypes.sizeof(DenParams) == 472 and ctypes.sizeof(DenBatch) == 952   # mirrors of chain_kernels.h
+    assert ctypes.sizeof(DenParams) == 536 and ctypes.sizeof(DenBatch) == 1080   # mirrors of chain_kernels.h
     den = synth.make_den_fst(25, 500, 48, mean_deg=5.0)
     B, T, l2, leaky, w = 300, 4, 0.01, 0.2, 0.5
     sup = synth.make_supervision(26, den, B, T, num_paths=2, weight=w)

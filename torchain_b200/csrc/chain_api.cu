@@ -1346,6 +1346,7 @@ struct ChunkedInput {
   cudaEvent_t all_landed = nullptr;  // recorded on the copy stream after the last chunk
   cudaEvent_t all_landed2 = nullptr; // same for the second copy stream (experiment), or null
   unsigned* deriv_progress = nullptr;  // device pointer of a mapped pinned counter (see DenParams)
+  unsigned long long progress_mask[8] = {~0ull, ~0ull, ~0ull, ~0ull, ~0ull, ~0ull, ~0ull, ~0ull};  // values worth publishing
   float* results4_dev = nullptr;       // device float[4]: objf, l2_term, weight, ok flag of the numeric guard
 };
 
@@ -1558,6 +1559,7 @@ int compute(DenGraph* g, Supervision* sup, const float* y, int64_t rows, int64_t
   dp.y_ready = chunked.flags;
   dp.y_chunk_frames = chunked.chunk_frames;
   dp.deriv_progress = (B <= pass_cap) ? chunked.deriv_progress : nullptr;  // single-pass calls only
+  for (int i = 0; i < 8; i++) dp.progress_mask[i] = chunked.progress_mask[i];
   dp.cta_trace = nullptr;
   if (g_profile.load() >= 2) {
     const size_t tb_bytes = sizeof(unsigned long long) * 2 * (size_t)(T + 1) * dd->grid * (4 + tb::kDenWarps);
@@ -1992,6 +1994,13 @@ int host_entry(DenGraph* g, Supervision* sp, const float* y_host, int64_t rows, 
     unsigned* dptr = nullptr;
     CUDA_OK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), h.progress, 0));
     ci.deriv_progress = dptr;
+    if (T <= 512) {  // chunk k (frames cb[k] ...) may leave once T - cb[k] trailing frames are complete
+      for (int i = 0; i < 8; i++) ci.progress_mask[i] = 0ull;
+      for (int k = 1; k < nchunks; k++) {
+        const int v = T - cb[k];
+        ci.progress_mask[(v >> 6) & 7] |= 1ull << (v & 63);
+      }
+    }
   }
   ci.results4_dev = h.results4.as<float>();
   // enqueue everything without synchronising (results are fetched below)

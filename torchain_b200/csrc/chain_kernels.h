@@ -95,6 +95,9 @@ struct DenParams {
   // release (at the start of step t-1, and once more after the last barrier), so the host can start
   // copying finished frame chunks out while the recurrence is still running.  null = unused.
   unsigned* deriv_progress;
+  // bit v set: publish v when v trailing frames are complete (the host sets the bits of its chunk boundaries: a
+  // system-scope release costs the publishing warp ~1.7 us, so it is paid per chunk, not per frame); T > 512: all ones
+  unsigned long long progress_mask[8];
   // ---- tied-pdf ("run-based") kernels only (den_tied_*): a run is a (destination state, pdf) pair
   // dir[0] then holds the forward stream of arc + run records, dir[1] the backward stream of arcs that
   // point at their run's W row, and rdir the runs dealt evenly over the bins (arcs = run records, no tasks).

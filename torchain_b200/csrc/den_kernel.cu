@@ -1140,14 +1140,17 @@ __device__ __forceinline__ void den_chain_body(const DenBatch& batch) {
           if (t < T - 1) trace_frame_end(t + 1);
           stamp();
         }
-        if (ci == NCTX - 1 && t < T - 1 && p0.deriv_progress && blockIdx.x == 0 && warp == kDenMainWarps && lane == 0) {
+        if (ci == NCTX - 1 && t < T - 1 && p0.deriv_progress && blockIdx.x == 0 && warp == kDenMainWarps && lane == 0 &&
+            ((p0.progress_mask[((T - 2 - t) >> 6) & 7] >> ((T - 2 - t) & 63)) & 1ull)) {
           // The derivative rows of frames > t+1 are complete in every context: every CTA wrote them before
           // it arrived at the barrier thread 0 of this CTA has just acquired, and the bar.sync inside wait()
           // orders that acquire before this store.  The release is at SYSTEM scope because the reader is
           // the host (which then enqueues copy-engine reads of those rows).  It is issued by an aux-warp
           // lane: on thread 0 -- the barrier thread -- the fence in front of the store held every frame
-          // back by the PCIe round trip (65 us per call, profiles/r01_host_trace.txt); the aux warps have
-          // that much slack in every frame.
+          // back by the PCIe round trip (65 us per call, profiles/r01_host_trace.txt).  The aux warps have less
+          // slack than round 1 assumed: published every frame it cost 83 us per call, and behind the barrier
+          // arrival 230 us (profiles/r02_host_trace_release_after_arrive.txt), so it is published only where the
+          // host has a chunk boundary (progress_mask: ~16 times per call).
           st_release_sys(p0.deriv_progress, (unsigned)(T - 2 - t));
         }
         if (is_aux) {
@@ -1616,7 +1619,8 @@ __device__ __forceinline__ void den_tied_body(const DenBatch& batch) {
       // phase A: runs (the aux warps only pass through the barrier: their work belongs to the long phase)
       if (!is_aux) runs_step_tied(p, sm.runs, rbeg, rend, t, lane);
       grid_barrier();
-      if (t < T - 1 && p.deriv_progress && blockIdx.x == 0 && warp == kDenMainWarps && lane == 0)
+      if (t < T - 1 && p.deriv_progress && blockIdx.x == 0 && warp == kDenMainWarps && lane == 0 &&
+          ((p.progress_mask[((T - 2 - t) >> 6) & 7] >> ((T - 2 - t) & 63)) & 1ull))
         st_release_sys(p.deriv_progress, (unsigned)(T - 2 - t));  // rows of frames > t+1 were complete a step ago
       // phase B: arcs.  First, the a_run rows this warp reads in the NEXT step's phase A are requested into L2:
       // they come from HBM (written a whole forward launch ago), and phase A is a short dependent chain of
