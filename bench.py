@@ -371,38 +371,41 @@ def run_b200(args):
     # while step k runs; `serial` builds it inline, for contrast.
     fresh = None
     if not args.no_fresh_supervision:
-        sups_np = [sup] + [synth.make_supervision(5000 + 1000 * rank + k, den, B, T, num_paths=4, weight=1.0)
-                           for k in range(3)]
-        side = torch.cuda.Stream(dev)
-        pool = ThreadPoolExecutor(max_workers=1)
+        try:
+            sups_np = [sup] + [synth.make_supervision(5000 + 1000 * rank + k, den, B, T, num_paths=4, weight=1.0)
+                               for k in range(3)]
+            side = torch.cuda.Stream(dev)
+            pool = ThreadPoolExecutor(max_workers=1)
 
-        def build(k):
-            torch.cuda.set_device(local)
-            return R.new_supervision(sups_np[k % len(sups_np)]).prefetch(local, side)
+            def build(k):
+                torch.cuda.set_device(local)
+                return R.new_supervision(sups_np[k % len(sups_np)]).prefetch(local, side)
 
-        n_fresh = max(4, min(args.steps, 20))
-        for mode in ("overlapped", "serial"):
-            for timed in (False, True):
-                k, fut = 0, (pool.submit(build, 0) if mode == "overlapped" else None)
-                sync_all()
-                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ev0.record(stream)
-                for _ in range(n_fresh if timed else 2):
+            n_fresh = max(4, min(args.steps, 20))
+            for mode in ("overlapped", "serial"):
+                for timed in (False, True):
+                    k, fut = 0, (pool.submit(build, 0) if mode == "overlapped" else None)
+                    sync_all()
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ev0.record(stream)
+                    for _ in range(n_fresh if timed else 2):
+                        if mode == "overlapped":
+                            h, fut = fut.result(), pool.submit(build, k + 1)
+                        else:
+                            h = R.new_supervision(sups_np[k % len(sups_np)])
+                        step(s=h)
+                        del h
+                        k += 1
+                    ev1.record(stream)
+                    sync_all()
                     if mode == "overlapped":
-                        h, fut = fut.result(), pool.submit(build, k + 1)
-                    else:
-                        h = R.new_supervision(sups_np[k % len(sups_np)])
-                    step(s=h)
-                    del h
-                    k += 1
-                ev1.record(stream)
-                sync_all()
-                if mode == "overlapped":
-                    fut.result()
-            t_ms = R.max_over_ranks(ev0.elapsed_time(ev1)) / n_fresh
-            fresh = dict(fresh or {}, **{mode + "_ms_per_step": t_ms})
-        pool.shutdown()
-        lib.torchain_supervision_pool_trim()
+                        fut.result()
+                t_ms = R.max_over_ranks(ev0.elapsed_time(ev1)) / n_fresh
+                fresh = dict(fresh or {}, **{mode + "_ms_per_step": t_ms})
+            pool.shutdown()
+            lib.torchain_supervision_pool_trim()
+        except Exception as e:  # the headline line must survive a failure of an auxiliary measurement
+            fresh = {"error": repr(e)[:200]}
 
     # ---- e2e: the reference-facing C-ABI call with HOST (pinned) buffers, copies inside the timed region
     y_pin = torch.empty(T * B, P, pin_memory=True)
@@ -432,55 +435,62 @@ def run_b200(args):
 
     # ---- parity: this rank's shard against the fp64 oracle on the same inputs (outside the timed regions)
     parity = None
+    parity_error = None
     if not args.no_parity:
-        ok = lib.torchain_ComputeChainObjfAndDeriv_ex(
-            g.ptr, s.ptr, y.data_ptr(), T * B, P, y.stride(0), res_host.ctypes.data_as(ctypes.c_void_p), None,
-            deriv.data_ptr(), deriv.stride(0), None, 0, c["l2"], c["leaky"], 0.0, -1.0, local,
-            ctypes.c_void_p(stream.cuda_stream))          # un-reduced results of this rank's own shard
-        if ok != 1:
-            raise RuntimeError(_lib.last_error())
-        torch.cuda.synchronize(dev)
-        parity = parity_check(c, sup, y.cpu().numpy(), res_host.copy(), deriv.cpu().numpy(),
-                              max(1, host_cores() // world))
-        d_host = d_pin.numpy()             # the e2e entry's derivative (not negated) must be the same matrix
-        parity["e2e_deriv_vs_device_rel"] = float(
-            np.abs(d_host + deriv.cpu().numpy()).max() / max(np.abs(d_host).max(), 1e-30))
-        parity["e2e_objf_rel_err"] = abs(float(r_e2e[0]) - parity["oracle_objf"]) / abs(parity["oracle_objf"])
-        parity["ok"] = bool(parity["ok"] and parity["e2e_deriv_vs_device_rel"] < 1e-4 and parity["e2e_objf_rel_err"] < 1e-5)
-        if world > 1:                      # worst rank; and the all-reduced totals against the sum of the oracles
-            tot = torch.tensor([parity["oracle_objf"]], device=dev, dtype=torch.float64)
-            dist.all_reduce(tot)
-            parity["reduced_objf_rel_err"] = abs(float(step_results[0]) - float(tot.item())) / abs(float(tot.item()))
-            parity["ok"] = bool(parity["ok"] and parity["reduced_objf_rel_err"] < 1e-5)
-            keys = ["objf_rel_err", "l2_rel_err", "weight_rel_err", "deriv_rel_err", "e2e_deriv_vs_device_rel",
-                    "e2e_objf_rel_err", "oracle_s"]
-            tmax = torch.tensor([parity[k] for k in keys] + [0.0 if parity["ok"] else 1.0], device=dev,
-                                dtype=torch.float64)
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            for k, v in zip(keys, tmax.tolist()):
-                parity[k] = v
-            parity["ok"] = bool(tmax[-1].item() == 0.0)
-            parity["ranks_checked"] = world
-        parity["tolerances"] = "objf, l2_term 1e-5 relative; derivative 1e-4 of max |oracle derivative|"
-        parity["oracle"] = "oracle/chain_oracle.cpp fp64 mode, every rank's own shard, max over ranks"
+        try:
+            ok = lib.torchain_ComputeChainObjfAndDeriv_ex(
+                g.ptr, s.ptr, y.data_ptr(), T * B, P, y.stride(0), res_host.ctypes.data_as(ctypes.c_void_p), None,
+                deriv.data_ptr(), deriv.stride(0), None, 0, c["l2"], c["leaky"], 0.0, -1.0, local,
+                ctypes.c_void_p(stream.cuda_stream))          # un-reduced results of this rank's own shard
+            if ok != 1:
+                raise RuntimeError(_lib.last_error())
+            torch.cuda.synchronize(dev)
+            parity = parity_check(c, sup, y.cpu().numpy(), res_host.copy(), deriv.cpu().numpy(),
+                                  max(1, host_cores() // world))
+            d_host = d_pin.numpy()             # the e2e entry's derivative (not negated) must be the same matrix
+            parity["e2e_deriv_vs_device_rel"] = float(
+                np.abs(d_host + deriv.cpu().numpy()).max() / max(np.abs(d_host).max(), 1e-30))
+            parity["e2e_objf_rel_err"] = abs(float(r_e2e[0]) - parity["oracle_objf"]) / abs(parity["oracle_objf"])
+            parity["ok"] = bool(parity["ok"] and parity["e2e_deriv_vs_device_rel"] < 1e-4 and parity["e2e_objf_rel_err"] < 1e-5)
+            if world > 1:                      # worst rank; and the all-reduced totals against the sum of the oracles
+                tot = torch.tensor([parity["oracle_objf"]], device=dev, dtype=torch.float64)
+                dist.all_reduce(tot)
+                parity["reduced_objf_rel_err"] = abs(float(step_results[0]) - float(tot.item())) / abs(float(tot.item()))
+                parity["ok"] = bool(parity["ok"] and parity["reduced_objf_rel_err"] < 1e-5)
+                keys = ["objf_rel_err", "l2_rel_err", "weight_rel_err", "deriv_rel_err", "e2e_deriv_vs_device_rel",
+                        "e2e_objf_rel_err", "oracle_s"]
+                tmax = torch.tensor([parity[k] for k in keys] + [0.0 if parity["ok"] else 1.0], device=dev,
+                                    dtype=torch.float64)
+                dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                for k, v in zip(keys, tmax.tolist()):
+                    parity[k] = v
+                parity["ok"] = bool(tmax[-1].item() == 0.0)
+                parity["ranks_checked"] = world
+            parity["tolerances"] = "objf, l2_term 1e-5 relative; derivative 1e-4 of max |oracle derivative|"
+            parity["oracle"] = "oracle/chain_oracle.cpp fp64 mode, every rank's own shard, max over ranks"
+        except Exception as e:  # reported, never fatal to the line (a missing parity block is visible as such)
+            parity, parity_error = None, repr(e)[:200]
 
     # ---- the other BASELINE.json configurations on this launch geometry (flat keys on the same line):
     # cfg 3 = 512 sequences in total, strong-split over the ranks; cfg 4 = large tree, 256 sequences per GPU
     extras = {}
     if not args.no_extra_configs and args.config == "chime5" and not args.batch and not args.frames:
-        del R
-        torch.cuda.empty_cache()
-        if 512 % world == 0:
-            e3 = extra_config(torch, lib, "chime5", 512 // world, 50, dev, local, world, rank)
-            extras.update(cfg3_strong_total_seqs=512, cfg3_strong_seqs_per_gpu=512 // world,
-                          cfg3_strong_ms_per_step=e3["ms_per_step"], cfg3_strong_frames_per_sec=e3["frames_per_sec"],
-                          cfg3_strong_gather_gbs_per_gpu=e3["gather_gbs"])
-        e4 = extra_config(torch, lib, "large_tree", 0, 0, dev, local, world, rank)
-        extras.update(cfg4_seqs_per_gpu=256, cfg4_ms_per_step=e4["ms_per_step"],
-                      cfg4_frames_per_sec=e4["frames_per_sec"], cfg4_gather_gbs_per_gpu=e4["gather_gbs"])
-        if world == 8:   # cfg 5's small end: 64 sequences over 8 GPUs
-            e5 = extra_config(torch, lib, "chime5", 8, 50, dev, local, world, rank)
-            extras.update(cfg5_64seqs_ms_per_step=e5["ms_per_step"], cfg5_64seqs_frames_per_sec=e5["frames_per_sec"])
+        try:
+            del R
+            torch.cuda.empty_cache()
+            if 512 % world == 0:
+                e3 = extra_config(torch, lib, "chime5", 512 // world, 50, dev, local, world, rank)
+                extras.update(cfg3_strong_total_seqs=512, cfg3_strong_seqs_per_gpu=512 // world,
+                              cfg3_strong_ms_per_step=e3["ms_per_step"], cfg3_strong_frames_per_sec=e3["frames_per_sec"],
+                              cfg3_strong_gather_gbs_per_gpu=e3["gather_gbs"])
+            e4 = extra_config(torch, lib, "large_tree", 0, 0, dev, local, world, rank)
+            extras.update(cfg4_seqs_per_gpu=256, cfg4_ms_per_step=e4["ms_per_step"],
+                          cfg4_frames_per_sec=e4["frames_per_sec"], cfg4_gather_gbs_per_gpu=e4["gather_gbs"])
+            if world == 8:   # cfg 5's small end: 64 sequences over 8 GPUs
+                e5 = extra_config(torch, lib, "chime5", 8, 50, dev, local, world, rank)
+                extras.update(cfg5_64seqs_ms_per_step=e5["ms_per_step"], cfg5_64seqs_frames_per_sec=e5["frames_per_sec"])
+        except Exception as e:
+            extras["extra_configs_error"] = repr(e)[:200]
 
     if rank != 0:
         if world > 1:
@@ -543,13 +553,17 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
-    if fresh:
+    if fresh and "error" in fresh:
+        line["fresh_supervision_error"] = fresh["error"]
+    elif fresh:
         line["fresh_supervision_ms_per_step"] = fresh["overlapped_ms_per_step"]
         line["fresh_supervision_serial_ms_per_step"] = fresh["serial_ms_per_step"]
         line["fresh_supervision_vs_step"] = fresh["overlapped_ms_per_step"] / ms_per_step
     line.update(extras)
     if cpu:
         line["cpu_baseline"] = cpu
+    if parity_error:
+        line["parity_error"] = parity_error
     if parity:
         line["parity"] = parity
         # flat copies at top level and inside `config` (which survives the driver's parser whole)

@@ -764,3 +764,37 @@ def test_tied_graph_too_large_for_shared_memory_stays_per_arc(mock, monkeypatch)
     finally:
         mock.my_lib_supervision_free(s)
         mock.my_lib_denominator_graph_free(g)
+
+
+def test_host_entry_publishes_progress_only_at_chunk_boundaries(mock):
+    """The backward launch releases the progress word at system scope (a ~1.7 us fence on a warp of CTA 0) only for the
+    frame counts at which the host can send a chunk: DenParams::progress_mask carries exactly the values T - cb[k]."""
+    den = synth.make_den_fst(13, 80, 16, mean_deg=3.0)
+    B, T = 6, 50
+    sup = synth.make_supervision(14, den, B, T, num_paths=2, weight=1.0)
+    y = synth.make_nnet_output(15, B, T, den.num_pdfs).astype(np.float32)
+    d = np.empty_like(y)
+    res = np.zeros(3, dtype=np.float32)
+    g, s = _handles(mock, den, sup)
+    try:
+        mock.mock_set_auto_progress(T)
+        mock.mock_reset_launches()
+        ok = mock.torchain_ComputeChainObjfAndDeriv_host(g, s, _p(y), y.shape[0], y.shape[1], y.shape[1], _p(res), _p(d),
+                                                         y.shape[1], None, 0, 5e-5, 0.1, 0.0, 0)
+        assert ok == 1, mock.torchain_last_error()
+        c = _den_batches(mock)[1][1].c[0]               # the backward launch's parameters
+        assert c.deriv_progress
+        bounds = (ctypes.c_int * 64)()
+        n = mock.torchain_host_chunk_bounds(T, bounds, 64)
+        want = {T - bounds[k] for k in range(1, n - 1)}
+        got = {v for v in range(512) if (c.progress_mask[v >> 6] >> (v & 63)) & 1}
+        assert got == want and 0 < len(want) < T - 1
+        # the device entry publishes nothing and leaves the mask at "every frame"
+        mock.mock_reset_launches()
+        _compute(mock, g, s, y)
+        c2 = _den_batches(mock)[1][1].c[0]
+        assert not c2.deriv_progress and all(c2.progress_mask[i] == 2**64 - 1 for i in range(8))
+    finally:
+        mock.mock_set_auto_progress(0)
+        mock.my_lib_supervision_free(s)
+        mock.my_lib_denominator_graph_free(g)
