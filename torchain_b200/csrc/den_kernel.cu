@@ -1201,6 +1201,19 @@ __device__ __forceinline__ void den_chain_body(const DenBatch& batch) {
 #endif
 // ONE stage of 4 records: 21.7 us per frame against 24.4 for 3 stages of 2 and 22.0 for 2 of 4
 // (profiles/r02_tied_sa_probe.txt) -- the loop is bound by its own instruction stream, not by loads in flight
+// phase A: ONE run in flight per warp.  Two cost the whole backward kernel 2 us per frame, four 15 us
+// (profiles/r02_tied_phaseA_probe.txt): the kernel lives at its 128-register cap, and what phase A keeps in
+// registers is spilled around phase B's loop.
+#ifndef DEN_TIED_A_DEPTH
+#define DEN_TIED_A_DEPTH 1
+#endif
+#ifndef DEN_TIED_B_SA
+#define DEN_TIED_B_SA 4
+#endif
+#ifndef DEN_TIED_B_STAGES
+#define DEN_TIED_B_STAGES 1  // one stage of 4: 36.8 us per backward step against 39.7 for two (profiles/r02_tied_phaseB_probe.txt)
+#endif
+static_assert(kStreamPad % DEN_TIED_B_SA == 0, "record streams are padded to kStreamPad");
 #ifndef DEN_TIED_F_SA
 #define DEN_TIED_F_SA 4
 #endif
@@ -1363,7 +1376,7 @@ __device__ __forceinline__ void alpha_step_tied(const DenParams& p, const int4* 
 // phase A of backward step t: per run, occupancy RED and W_t(run)
 __device__ __forceinline__ void runs_step_tied(const DenParams& p, const int4* __restrict__ runs, int rbeg, int rend,
                                                int t, int lane) {
-  constexpr int V = 4, kD = 2;
+  constexpr int V = 4, kD = DEN_TIED_A_DEPTH;
   const int BP = p.BP, col = lane * V;
   const char* const ub = reinterpret_cast<const char*>(p.beta + (size_t)((t + 1) & 1) * p.N * BP + col);
   const char* const ue = reinterpret_cast<const char*>(p.etile + (size_t)(t & 1) * p.P * BP + col);
@@ -1409,7 +1422,7 @@ __device__ __forceinline__ void runs_step_tied(const DenParams& p, const int4* _
 __device__ __forceinline__ void beta_step_tied(const DenParams& p, const int4* __restrict__ recs,
                                                const int4* __restrict__ tasks, int abeg, int aend, int tb, int te, int t,
                                                float* red, int warp, int lane, double& ab) {
-  constexpr int V = 4, kSA = 4, kStages = 2;
+  constexpr int V = 4, kSA = DEN_TIED_B_SA, kStages = DEN_TIED_B_STAGES;
   const int BP = p.BP, col = lane * V;
   float* __restrict__ beta_cur = p.beta + (size_t)(t & 1) * p.N * BP;
   const double* St = p.Ssum + (size_t)t * BP;
@@ -1614,11 +1627,25 @@ __device__ __forceinline__ void den_tied_body(const DenBatch& batch) {
     }
     cta_reduce_to(sm.red, BP, kDenMainWarps, p.Bsum + (size_t)T * BP);
     grid_barrier();
+#ifdef DEN_TIED_DEBUG_PHASES  // tools: per-phase time of the backward step (globaltimer accumulators, printed by a few warps)
+    unsigned long long dbg[5] = {0, 0, 0, 0, 0}, dbg_t = 0;
+    auto tick = [&](int slot) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      if (slot >= 0) dbg[slot] += ns - dbg_t;
+      dbg_t = ns;
+    };
+#else
+    auto tick = [&](int) {};
+#endif
+    tick(-1);
     for (int t = T - 1; t >= 0; t--) {
       stamp();
       // phase A: runs (the aux warps only pass through the barrier: their work belongs to the long phase)
       if (!is_aux) runs_step_tied(p, sm.runs, rbeg, rend, t, lane);
+      tick(0);
       grid_barrier();
+      tick(1);
       if (t < T - 1 && p.deriv_progress && blockIdx.x == 0 && warp == kDenMainWarps && lane == 0 &&
           ((p.progress_mask[((T - 2 - t) >> 6) & 7] >> ((T - 2 - t) & 63)) & 1ull))
         st_release_sys(p.deriv_progress, (unsigned)(T - 2 - t));  // rows of frames > t+1 were complete a step ago
@@ -1637,9 +1664,17 @@ __device__ __forceinline__ void den_tied_body(const DenBatch& batch) {
       }
 #endif
       else beta_step_tied(p, arcs, tasks, abeg, aend, tb, te, t, sm.red, warp, lane, ab);
+      tick(2);
       cta_reduce_to(sm.red, BP, kDenMainWarps, p.Bsum + (size_t)t * BP);
+      tick(3);
       grid_barrier();
+      tick(4);
     }
+#ifdef DEN_TIED_DEBUG_PHASES
+    if (p.timeline && lane == 0 && (blockIdx.x == 0 || blockIdx.x == 77) && (warp == 0 || warp == 7 || warp == kDenMainWarps))
+      printf("tied bwd cta %d warp %d: per frame us: phase A %.2f | barrier1 %.2f | phase B %.2f | reduce %.2f | barrier2 %.2f\n",
+             (int)blockIdx.x, warp, dbg[0] / 1e3 / T, dbg[1] / 1e3 / T, dbg[2] / 1e3 / T, dbg[3] / 1e3 / T, dbg[4] / 1e3 / T);
+#endif
     stamp();
     if (p.deriv_progress && blockIdx.x == 0 && warp == kDenMainWarps && lane == 0)
       st_release_sys(p.deriv_progress, (unsigned)(T - 1));
