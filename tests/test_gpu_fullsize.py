@@ -286,3 +286,24 @@ def test_tied_host_buffer_entry():
         return res, dh.numpy().copy(), None
 
     _compare(den, oden, g, 128, 30, 5e-5, 0.1, seed=5201, entry=entry)
+
+
+def test_tied_host_buffer_entry_two_passes():
+    """B = 200 on the tied graph through the host-buffer entry: two run-based passes (128 + 72 sequences), so the
+    backward launches publish no progress and the derivative leaves after the compute stream has drained."""
+    import torch
+    den, oden, g = _den("chime5_tied")
+
+    def entry(g, s, y, l2, leaky, xent=0.0, want_xent=False):
+        lib = _lib.load()
+        rows, cols = y.shape
+        yh = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32)).pin_memory()
+        dh = torch.full((rows, cols), float("nan")).pin_memory()
+        res = np.zeros(3, dtype=np.float32)
+        ok = lib.torchain_ComputeChainObjfAndDeriv_host(g.ptr, s.ptr, yh.data_ptr(), rows, cols, cols,
+                                                        res.ctypes.data_as(ctypes.c_void_p), dh.data_ptr(), cols,
+                                                        None, 0, l2, leaky, 0.0, 0)
+        assert ok == 1, _lib.last_error()
+        return res, dh.numpy().copy(), None
+
+    _compare(den, oden, g, 200, 10, 5e-5, 0.1, seed=5301, entry=entry)
