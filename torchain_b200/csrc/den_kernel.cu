@@ -258,7 +258,7 @@ __device__ __forceinline__ void stage_exp_tile(const DenParams& p, int t, float*
   const float* ycol = p.y + (int64_t)t * p.yl.t + (int64_t)(p.seq0 + s0) * p.yl.s + (int64_t)pdf * p.yl.p;
   float v[32];
 #pragma unroll
-  for (int j = 0; j < 32; j++) v[j] = (s0 + j < p.B && pdf < p.P) ? __ldg(ycol + (int64_t)j * p.yl.s) : 0.f;
+  for (int j = 0; j < 32; j++) v[j] = (s0 + j < p.B && pdf < p.P) ? __ldcg(ycol + (int64_t)j * p.yl.s) : 0.f;
 #pragma unroll
   for (int j = 0; j < 32; j++) {
     if (want_sq) sumsq += (double)v[j] * (double)v[j];

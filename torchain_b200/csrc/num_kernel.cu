@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(kNumThreads) num_fb_kernel(const __grid_consta
   const int a0 = p.chain_arc_off[chain], a1 = p.chain_arc_off[chain + 1];
   for (int a = a0 + lane; a < a1; a += 32) {
     const int row = p.arc_row[a], fr = row / p.B;
+    // ld.global.nc is fine HERE: this kernel is launched behind the event that marks nnet_output complete (every chunk
+    // of the host-buffer entry has landed), so the matrix is read-only for the kernel's lifetime
     const float yv = __ldg(p.y + fr * p.yl.t + (row - fr * p.B) * p.yl.s + p.arc_pdf[a] * p.yl.p);
     p.arc_val[a] = (double)yv - (double)p.arc_cost[a];
   }
