@@ -75,3 +75,41 @@ def chain_objf(den, pi, sup, y_np, leaky, l2):
     l2_term = -0.5 * w * l2 * (y * y).sum()
     (objf + l2_term).backward()
     return float(objf.detach()), float(l2_term.detach()), w * B * T, y.grad.numpy().copy()
+
+
+def den_logprob_batched(den, pi, y, B, T, leaky):
+    """The same linear recursion as den_logprob with all B sequences advanced together, so that
+    it can run on graphs of BASELINE.json's real sizes (N = 10 000 states, A ~ 300 000 arcs): the
+    per-arc products are one (A, B) array per frame and the scatter is torch's index_add.  It
+    shares no code with oracle/ (no arc loops, no hand-written backward pass, no Kaldi-style
+    normaliser bookkeeping: derivatives are autograd's), which is what makes it a second,
+    independent formulation at realistic size.  y: (T*B, P) float64, rows frame-major."""
+    N = den.num_states
+    src = torch.as_tensor(den.src.astype(np.int64))
+    dst = torch.as_tensor(den.dst.astype(np.int64))
+    pdf = torch.as_tensor(den.ilabel.astype(np.int64) - 1)
+    p = torch.exp(-torch.as_tensor(den.cost.astype(np.float32))).double()[:, None]  # float exp as Kaldi
+    pi = torch.as_tensor(np.asarray(pi, dtype=np.float64))[:, None]
+    e = torch.exp(y).reshape(T, B, -1)
+    alpha = pi.expand(N, B)
+    logscale = y.new_zeros(B)
+    for t in range(T):
+        alpha_dash = alpha + leaky * pi * alpha.sum(0, keepdim=True)
+        contrib = alpha_dash[src] * p * e[t].t()[pdf]
+        alpha = torch.zeros(N, B, dtype=torch.float64).index_add(0, dst, contrib)
+        sc = alpha.sum(0)
+        alpha = alpha / sc
+        logscale = logscale + torch.log(sc)
+    alpha_dash = alpha + leaky * pi * alpha.sum(0, keepdim=True)
+    return (torch.log(alpha_dash.sum(0)) + logscale).sum()
+
+
+def chain_objf_batched(den, pi, sup, y_np, leaky, l2):
+    """chain_objf with the batched denominator: usable on the full-size graphs at small B."""
+    y = torch.tensor(np.asarray(y_np, dtype=np.float64), requires_grad=True)
+    B, T = sup.num_sequences, sup.frames_per_sequence
+    w = float(sup.weight)
+    objf = w * num_logprob(sup, y) - w * den_logprob_batched(den, pi, y, B, T, leaky)
+    l2_term = -0.5 * w * l2 * (y * y).sum()
+    (objf + l2_term).backward()
+    return float(objf.detach()), float(l2_term.detach()), w * B * T, y.grad.numpy().copy()

@@ -86,6 +86,27 @@ def test_cfg2_full_size_matches_oracle():
     assert den_post.min() > -1e-5 and abs(den_post.sum() - B * T) < 1e-4 * B * T
 
 
+def test_cfg2_graph_against_the_independent_autograd_formulation():
+    """The CUDA path against tests/dense_ref.py's batched index_add + autograd formulation directly
+    (the oracle is not involved): cfg 2's den graph, all T=50 frames, 8 sequences.  The CPU suite holds
+    the oracle to the same formulation at this size (test_oracle_vs_independent_autograd_at_full_graph_size)."""
+    import dense_ref
+    den, oden, g = _den("chime5")
+    c = synth.CONFIGS["chime5"]
+    B, T = 8, c["T"]
+    sup = synth.make_supervision(4101, den, B, T, num_paths=4, weight=1.0)
+    y = synth.make_nnet_output(4102, B, T, den.num_pdfs, scale=2.0)
+    objf, l2_term, w, ref = dense_ref.chain_objf_batched(den, oden.initial_probs(), sup, y, c["leaky"], c["l2"])
+    s = io.Supervision.from_arrays(sup.weight, B, T, sup.label_dim, sup.arc_begin, sup.arc_dst, sup.arc_label,
+                                   sup.arc_cost, sup.final_cost)
+    res, d, _ = run_abi(g, s, y, c["l2"], c["leaky"])
+    print("autograd parity: objf %.9g vs %.9g, deriv %.2e" % (res[0], objf, deriv_err(d, ref)))
+    assert rel(res[0], objf) < OBJF_RTOL
+    assert rel(res[1], l2_term) < OBJF_RTOL
+    assert res[2] == pytest.approx(w)
+    assert deriv_err(d, ref) < DERIV_RTOL
+
+
 def test_cfg2_graph_weight_half_and_leaky_small():
     """Same graph, supervision.weight 0.5 and the reference's default leaky coefficient 1e-5
     (torchain/functions.py:129): the normalisers then carry the whole dynamic range."""

@@ -59,6 +59,40 @@ def test_oracle_vs_dense_autograd(seed):
     assert deriv_err(r["deriv"], g) < 1e-7
 
 
+def test_batched_autograd_equals_per_sequence_autograd():
+    c = synth.small_case(3)
+    pi = ol.OracleDen(c["den"]).initial_probs()
+    c = dict(c)
+    c["T"] = T = 6
+    c["sup"] = synth.make_supervision(4, c["den"], c["B"], T, num_paths=3, weight=c["sup"].weight)
+    c["y"] = synth.make_nnet_output(5, c["B"], T, c["P"])
+    a = dense_ref.chain_objf(c["den"], pi, c["sup"], c["y"], c["leaky"], c["l2"])
+    b = dense_ref.chain_objf_batched(c["den"], pi, c["sup"], c["y"], c["leaky"], c["l2"])
+    assert rel(a[0], b[0]) < 1e-12 and rel(a[1], b[1]) < 1e-12 and a[2] == b[2]
+    assert deriv_err(a[3], b[3]) < 1e-12
+
+
+@pytest.mark.parametrize("name,B,T", [("chime5", 4, 50), ("large_tree", 2, 20)])
+def test_oracle_vs_independent_autograd_at_full_graph_size(name, B, T):
+    """The oracle against the second formulation (dense_ref.den_logprob_batched: index_add recursion +
+    autograd) on the den graphs of BASELINE.json cfg 2 (N=10 000, A~300k, all T=50 frames) and cfg 4:
+    the sizes the GPU parity tests and bench.py's parity block trust the oracle at."""
+    c = synth.CONFIGS[name]
+    den = synth.make_den_fst(1234, c["N"], c["P"], mean_deg=c["mean_deg"])
+    oden = ol.OracleDen(den)
+    sup = synth.make_supervision(77, den, B, T, num_paths=4, weight=0.75)
+    y = synth.make_nnet_output(78, B, T, den.num_pdfs, scale=2.0)
+    r = ol.chain(oden, ol.OracleSup(sup), y, l2=c["l2"], leaky=c["leaky"], mode="fp64", threads=4)
+    objf, l2_term, w, g = dense_ref.chain_objf_batched(den, oden.initial_probs(), sup, y, c["leaky"], c["l2"])
+    assert r["ok"]
+    assert rel(r["objf"], objf) < 1e-8
+    assert rel(r["l2_term"], l2_term) < 1e-10
+    assert r["weight"] == pytest.approx(w)
+    assert deriv_err(r["deriv"], g) < 1e-7
+    rk = ol.chain(oden, ol.OracleSup(sup), y, l2=c["l2"], leaky=c["leaky"], mode="kaldi_fp32", threads=4)
+    assert rel(rk["objf"], objf) < OBJF_RTOL and deriv_err(rk["deriv"], g) < DERIV_RTOL
+
+
 @pytest.mark.parametrize("seed", range(50))
 def test_chain_training_properties(seed):
     """ChainTrainingTest assertions (chain-supervision-test.hpp:267-285)."""
