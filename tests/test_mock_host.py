@@ -798,3 +798,67 @@ def test_host_entry_publishes_progress_only_at_chunk_boundaries(mock):
         mock.mock_set_auto_progress(0)
         mock.my_lib_supervision_free(s)
         mock.my_lib_denominator_graph_free(g)
+
+
+@pytest.mark.parametrize("B,subs", [(64, 2), (16, 4)])
+def test_small_batch_streams_are_complete_and_aligned(mock, B, subs):
+    """Batches of <= 64 sequences: every warp walks `subs` arc streams in lockstep, one per lane group.  The host
+    puts states of equal arc count side by side and pads them to the same length, so that an end of state is
+    warp-uniform (build_dir, "aligned streams").  Read the uploaded per-arc streams of both directions back and check
+    (1) they hold every state once and every arc of the graph once, with its probability, pdf and the other state's
+    initial probability, (2) the padding carries no probability, (3) the ends of state of a warp's streams coincide,
+    (4) the padding is small."""
+    P, N, T = 40, 3000, 3
+    den = synth.make_den_fst(11, N, P, mean_deg=9.0)
+    sup = synth.make_supervision(12, den, B, T, num_paths=2)
+    y = synth.make_nnet_output(13, B, T, P).astype(np.float32)
+    g, s = _handles(mock, den, sup)
+    try:
+        mock.mock_reset_launches()
+        _compute(mock, g, s, y)
+        names = [mock.mock_launch_name(i).decode() for i in range(mock.mock_launch_count())]
+        i_f = [i for i, n in enumerate(names) if "den_forward_kernel" in n][0]
+        c = DenBatch.from_buffer_copy(ctypes.string_at(mock.mock_launch_param0(i_f), ctypes.sizeof(DenBatch))).c[0]
+        assert c.subs == subs and c.BP == 128 // subs
+        grid, warps, rowbytes = 148, 14, 4 * c.BP
+        prob = np.exp(-den.cost.astype(np.float32)).astype(np.float32)
+        import oracle_lib as ol
+        pi = ol.OracleDen(den).initial_probs().astype(np.float32)
+        for d, (key, other) in enumerate([(den.dst, den.src), (den.src, den.dst)]):
+            D = _dir_arrays(c.dir[d], grid * warps * subs, grid)
+            recs, tasks, aoff, toff = D["recs"], D["tasks"], D["warp_arc_off"], D["warp_task_off"]
+            assert sorted(tasks[:, 0].tolist()) == list(range(N))
+            got, pad = [], 0
+            for b in range(grid * warps * subs):
+                task = toff[b]
+                for k in range(aoff[b], aoff[b + 1]):
+                    r = recs[k]
+                    pr = abs(_f32(r[2]))
+                    if pr != 0.0:
+                        assert task < toff[b + 1]
+                        got.append((int(tasks[task][0]), int(r[0]) // rowbytes, int(r[1]) // rowbytes,
+                                    float(np.float32(pr)), float(np.float32(_f32(r[3])))))
+                    else:
+                        pad += 1
+                    if r[2] < 0:
+                        task += 1
+                assert task == toff[b + 1]                       # every task of the stream is closed by an end flag
+            want = sorted((int(key[a]), int(other[a]), int(den.ilabel[a]) - 1, float(prob[a]), float(pi[other[a]]))
+                          for a in range(den.num_arcs))
+            got.sort()
+            assert [x[:3] for x in got] == [x[:3] for x in want]
+            assert np.allclose([x[3:] for x in got], [x[3:] for x in want], rtol=1e-6, atol=0)   # expf of the library
+            print("dir %d: %d padding records for %d arcs" % (d, pad, den.num_arcs))
+            nstreams = int((np.diff(aoff) > 0).sum())
+            assert pad <= 0.02 * den.num_arcs + 8 * nstreams       # alignment (neighbours in sorted order) + kStreamPad
+            for w in range(grid * warps):
+                ends = []
+                for j in range(subs):
+                    b = w * subs + j
+                    z = recs[aoff[b]:aoff[b + 1], 2]
+                    ends.append(np.nonzero(z < 0)[0].tolist())
+                for j in range(1, subs):                          # a short last group leaves later streams shorter
+                    assert ends[j] == ends[0][:len(ends[j])]
+    finally:
+        mock.my_lib_supervision_free(s)
+        mock.my_lib_denominator_graph_free(g)

@@ -195,16 +195,19 @@ struct Workspace {
 //   TORCHAIN_FORCE_UNSTAGED=1   arc slices stay in global memory even when they would fit shared memory
 //   TORCHAIN_NO_AUTOTUNE=1      the partition is not re-dealt from measured per-warp busy cycles
 //   TORCHAIN_TIED=0|1           never / always use the run-based kernels (default: when the graph has few runs per arc)
+//   TORCHAIN_ALIGN_STREAMS=0    small batches: the lane groups of a warp get independently dealt streams (the A/B switch
+//                               of the aligned-stream partition, see build_dir)
 struct GraphHooks {
   int split_cap = 192;
   int tied = -1;
-  bool force_unstaged = false, no_autotune = false;
+  bool force_unstaged = false, no_autotune = false, align_streams = true;
   static GraphHooks from_env() {
     GraphHooks h;
     if (const char* e = getenv("TORCHAIN_SPLIT_CAP")) h.split_cap = std::max(2, atoi(e));
     h.force_unstaged = getenv("TORCHAIN_FORCE_UNSTAGED") != nullptr;
     h.no_autotune = getenv("TORCHAIN_NO_AUTOTUNE") != nullptr;
     if (const char* e = getenv("TORCHAIN_TIED")) h.tied = atoi(e) != 0;
+    if (const char* e = getenv("TORCHAIN_ALIGN_STREAMS")) h.align_streams = atoi(e) != 0;
     return h;
   }
 };
@@ -262,7 +265,8 @@ void lpt(const std::vector<int>& items, const std::vector<int>& cost, const std:
 void build_dir(const DenGraph& g, int dir, int grid, int bins_per_cta, const std::vector<double>& speed /* [grid*bins_per_cta] */,
                unsigned rowbytes /* bytes of one [state|pdf] row of this geometry: 4 * BP */, DirHost* out,
                std::vector<double>* work, const std::vector<int>* x_index = nullptr /* per arc: row index stored in
-               the record's first field instead of the other state (tied phase B: the arc's run); never split */) {
+               the record's first field instead of the other state (tied phase B: the arc's run); never split */,
+               int align = 1 /* lane groups per warp (small batches): see "aligned streams" below */) {
   const int N = g.N, A = g.A;
   std::vector<int> deg(N, 0), begin(N + 1, 0);
   const std::vector<int>& key = dir == 0 ? g.dst : g.src;
@@ -311,16 +315,52 @@ void build_dir(const DenGraph& g, int dir, int grid, int bins_per_cta, const std
   out->warp_task_off.assign(1, 0);
   out->warp_arc_off.assign(1, 0);
   out->max_arcs_cta = out->max_tasks_cta = 0;
+  // Aligned streams (align = lane groups per warp > 1): the groups of a warp walk their own streams in lockstep, so
+  // an end of state in one group sends the whole warp through the end-of-state block and keeps it off the
+  // straight-line path of the arc loop.  States of (nearly) equal arc count are therefore put side by side in the
+  // `align` streams of one warp and padded with zero-probability arcs to the same length: every end of state is then
+  // warp-uniform, as it is with one stream per warp.  (Arc counts are Poisson-like, so neighbours in sorted order
+  // differ by 0-1 arcs: the padding is ~1 % of the arcs.)
+  struct Slot {
+    int item, pad_to;  // pad_to = arcs this item occupies in its stream (>= its own count)
+  };
   for (int c = 0; c < grid; c++) {
-    std::vector<std::vector<int>> by_warp;
-    lpt(by_cta[c], cost,
-        std::vector<double>(speed.begin() + c * bins_per_cta, speed.begin() + (c + 1) * bins_per_cta), &by_warp);
+    std::vector<std::vector<Slot>> by_bin(bins_per_cta);
+    if (align <= 1) {
+      std::vector<std::vector<int>> by_warp;
+      lpt(by_cta[c], cost,
+          std::vector<double>(speed.begin() + c * bins_per_cta, speed.begin() + (c + 1) * bins_per_cta), &by_warp);
+      for (int w = 0; w < bins_per_cta; w++)
+        for (int it : by_warp[w]) by_bin[w].push_back({it, 0});
+    } else {
+      std::vector<int> order(by_cta[c]);
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+      const int ngroups = ((int)order.size() + align - 1) / align, warps = bins_per_cta / align;
+      std::vector<int> gcost(ngroups), gid(ngroups);
+      for (int gi = 0; gi < ngroups; gi++) {
+        gcost[gi] = cost[order[(size_t)gi * align]];  // the first member is the largest
+        gid[gi] = gi;
+      }
+      std::vector<double> wspeed(warps, 0.0);
+      for (int w = 0; w < warps; w++)
+        for (int j = 0; j < align; j++) wspeed[w] += speed[c * bins_per_cta + w * align + j];
+      std::vector<std::vector<int>> by_warp;
+      lpt(gid, gcost, wspeed, &by_warp);
+      for (int w = 0; w < warps; w++)
+        for (int gi : by_warp[w]) {
+          const int pad_to = std::max(1, items[order[(size_t)gi * align]].count);
+          for (int j = 0; j < align && (size_t)gi * align + j < order.size(); j++)
+            by_bin[w * align + j].push_back({order[(size_t)gi * align + j], pad_to});
+        }
+    }
     const int arc0 = (int)out->arcs.size(), task0 = (int)out->tasks.size();
     for (int w = 0; w < bins_per_cta; w++) {
-      for (int it : by_warp[w]) {
+      for (const Slot& slot : by_bin[w]) {
+        const int it = slot.item;
         const Item& item = items[it];
         const int s = item.state;
         (*work)[c * bins_per_cta + w] += cost[it];
+        const size_t item_arc0 = out->arcs.size();
         int4 tk;
         tk.x = s;
         tk.y = (int)out->arcs.size() - arc0;
@@ -343,6 +383,12 @@ void build_dir(const DenGraph& g, int dir, int grid, int bins_per_cta, const std
           ar.x = x_index ? 0 : (int)((unsigned)s * rowbytes);
           ar.y = 0;
           ar.z = 0;  // probability 0.0f
+          ar.w = 0;
+          out->arcs.push_back(ar);
+        }
+        while ((int)(out->arcs.size() - item_arc0) < slot.pad_to) {  // aligned streams: same length as the neighbours
+          int4 ar = out->arcs.back();
+          ar.z = 0;
           ar.w = 0;
           out->arcs.push_back(ar);
         }
@@ -987,7 +1033,7 @@ int build_partition(DenGraph* g, DenDevice* d, int subs = 1) {
   for (int dir = 0; dir < 2; dir++) {
     DirHost h;
     build_dir(*g, dir, d->grid, bins, subs == 1 ? d->speed[dir] : uniform, 4u * (unsigned)(tb::kCtxBP / subs), &h,
-              &part->work[dir]);
+              &part->work[dir], nullptr, g->hooks.align_streams ? subs : 1);
     CUDA_OK(upload(part->arcs[dir], h.arcs));
     CUDA_OK(upload(part->tasks[dir], h.tasks));
     CUDA_OK(upload(part->cta_arc_off[dir], h.cta_arc_off));
