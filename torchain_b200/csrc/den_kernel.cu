@@ -90,6 +90,23 @@ __device__ __forceinline__ void red_add(float* ptr, const float (&v)[V]) {
   }
 }
 
+// Per-sequence normalisers (S_t, b_t: one row of BP doubles per frame) are read by EVERY main warp of EVERY CTA at the
+// start of a frame.  With ld.global.cg all 2072 warps send their requests for the same 8 lines to the same L2 slices
+// at the same moment: 2 MB through one or two slices = ~4 us in which the warps only wait (measured on a graph with
+// almost no arcs: profiles/r02_state_cost.txt).  A plain (L1-allocating) load turns the 14 requests of a CTA into
+// one.  It is coherent here: the row was completed before the grid barrier the CTA has just left (thread 0's
+// ld.acquire.gpu + bar.sync order every thread's later weak loads after those writes), and nothing writes it again.
+#ifndef DEN_S_CACHED
+#define DEN_S_CACHED 1
+#endif
+__device__ __forceinline__ double ld_norm(const double* ptr) {
+#if DEN_S_CACHED
+  return *ptr;
+#else
+  return __ldcg(ptr);
+#endif
+}
+
 // Address of row `idx` of a [rows][BP] fp32 table whose column offset is already folded into
 // `base`: one IMAD.WIDE.U32 instead of the ~7 instructions of generic 64-bit index arithmetic
 // (the gather loops are close to issue-bound at 3.5 warps per scheduler).
@@ -416,7 +433,7 @@ __device__ __forceinline__ void alpha_step(const DenParams& p, const int4* __res
     float lamS[V], invS[V], part[V], acc[V];
     double Sd[V];
 #pragma unroll
-    for (int v = 0; v < V; v++) Sd[v] = __ldcg(Sprev + col + v);
+    for (int v = 0; v < V; v++) Sd[v] = ld_norm(Sprev + col + v);
     int task = tb;
     constexpr int kSA = DEN_F_SA, kStages = DEN_F_STAGES;
     GatherBuf<V, kSA> ring[kStages];
@@ -547,8 +564,8 @@ __device__ __forceinline__ void beta_step(const DenParams& p, const int4* __rest
     double Sd[V], Bd[V];
 #pragma unroll
     for (int v = 0; v < V; v++) {
-      Sd[v] = __ldcg(St + col + v);
-      Bd[v] = __ldcg(Bn + col + v);
+      Sd[v] = ld_norm(St + col + v);
+      Bd[v] = ld_norm(Bn + col + v);
       aln[v] = 0.f;
       al0[v] = 0.f;
     }
@@ -816,7 +833,7 @@ __device__ __forceinline__ void beta_step_async(const DenParams& p, const int4* 
     const float S = (float)__ldcg(St + col + v);
     lamS[v] = p.leaky * S;
     invS[v] = 1.0f / S;
-    bv[v] = p.leaky * (float)__ldcg(Bn + col + v);
+    bv[v] = p.leaky * (float)ld_norm(Bn + col + v);
     part[v] = 0.f;
     X[v] = 0.f;
     occ[v] = fmaf(pi_h, lamS[v], al0[v]) * invS[v];
@@ -1291,7 +1308,7 @@ __device__ __forceinline__ void alpha_step_tied(const DenParams& p, const int4* 
   char* const ur = reinterpret_cast<char*>(arun + col);
   double Sd[V];
 #pragma unroll
-  for (int v = 0; v < V; v++) Sd[v] = __ldcg(Sprev + col + v);
+  for (int v = 0; v < V; v++) Sd[v] = ld_norm(Sprev + col + v);
   RowBuf<kSA> ring[kStages];
   auto load = [&](RowBuf<kSA>& buf, int k) {
     if (k < n) {
@@ -1397,7 +1414,7 @@ __device__ __forceinline__ void runs_step_tied(const DenParams& p, const int4* _
 #pragma unroll
   for (int d = 0; d < kD; d++) load(d, rbeg + d);
 #pragma unroll
-  for (int v = 0; v < V; v++) bv[v] = p.leaky * (float)__ldcg(Bn + col + v);
+  for (int v = 0; v < V; v++) bv[v] = p.leaky * (float)ld_norm(Bn + col + v);
   for (int k = rbeg; k < rend; k += kD) {
 #pragma unroll
     for (int d = 0; d < kD; d++) {
@@ -1432,7 +1449,7 @@ __device__ __forceinline__ void beta_step_tied(const DenParams& p, const int4* _
   const char* const uw = reinterpret_cast<const char*>(p.wbuf + col);
   double Sd[V];
 #pragma unroll
-  for (int v = 0; v < V; v++) Sd[v] = __ldcg(St + col + v);
+  for (int v = 0; v < V; v++) Sd[v] = ld_norm(St + col + v);
   RowBuf<kSA> ring[kStages];
   auto load = [&](RowBuf<kSA>& buf, int k) {
     if (k < n) {
