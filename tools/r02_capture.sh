@@ -1,4 +1,5 @@
 #!/bin/bash
+# (the .ncu-rep files stay in /tmp on the box: gpurun copies back at most 64 MiB; the raw csv pages come back)
 # Round-2 capture on ONE B200: the whole GPU suite, a bench line, the ncu launch list of the same command, one
 # `ncu --set full` capture of the denominator kernels (per-arc on config 2, run-based on the tied graph), the
 # relayout kernels, the layout probe.  Everything lands in gpurun_out/r02_*; summaries go to profiles/ by hand.
@@ -13,12 +14,12 @@ python tools/layout_probe.py > $O/r02_layout_probe_final.txt 2>&1
 tail -9 $O/r02_layout_probe_final.txt | head -8
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_ncu_launches_final.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-parity --no-extra-configs --no-fresh-supervision > $O/ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:den_ -s 8 -c 2 -f -o $O/r02_den \
+ncu --set full --clock-control none --import-source on -k regex:den_ -s 8 -c 2 -f -o /tmp/r02_den \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-parity --no-extra-configs --no-fresh-supervision > $O/ncu_den.log 2>&1
-ncu -i $O/r02_den.ncu-rep --page raw --csv > $O/r02_ncu_den_kernels_raw.csv 2>/dev/null
-ncu --set full --clock-control none --import-source on -k regex:relayout -s 2 -c 2 -f -o $O/r02_relayout \
+ncu -i /tmp/r02_den.ncu-rep --page raw --csv > $O/r02_ncu_den_kernels_raw.csv 2>/dev/null
+ncu --set full --clock-control none --import-source on -k regex:relayout -s 2 -c 2 -f -o /tmp/r02_relayout \
     python tools/layout_probe.py --iters 1 > $O/ncu_relayout.log 2>&1
-ncu -i $O/r02_relayout.ncu-rep --page raw --csv > $O/r02_ncu_relayout_kernels_raw.csv 2>/dev/null
+ncu -i /tmp/r02_relayout.ncu-rep --page raw --csv > $O/r02_ncu_relayout_kernels_raw.csv 2>/dev/null
 python - <<'PY'
 import csv, json
 for f in ("gpurun_out/r02_ncu_den_kernels_raw.csv", "gpurun_out/r02_ncu_relayout_kernels_raw.csv"):

@@ -2,8 +2,8 @@
 set -u
 mkdir -p gpurun_out
 O=gpurun_out
-ncu --set full --clock-control none --import-source on -k regex:den_tied -s 8 -c 2 -f -o $O/r02_den_tied_final python tools/variant_probe.py --child --config chime5_tied --no-parity --steps 2 > $O/ncu_tied.log 2>&1
-ncu -i $O/r02_den_tied_final.ncu-rep --page raw --csv > $O/r02_ncu_den_tied_final_raw.csv 2>/dev/null
+ncu --set full --clock-control none --import-source on -k regex:den_tied -s 8 -c 2 -f -o /tmp/r02_den_tied_final python tools/variant_probe.py --child --config chime5_tied --no-parity --steps 2 > $O/ncu_tied.log 2>&1
+ncu -i /tmp/r02_den_tied_final.ncu-rep --page raw --csv > $O/r02_ncu_den_tied_final_raw.csv 2>/dev/null
 python - <<'PY'
 import csv
 rows = list(csv.reader(open('gpurun_out/r02_ncu_den_tied_final_raw.csv')))
